@@ -1,0 +1,32 @@
+// TEST-ONLY host emulation of kernel K1 (the per-vertex warp solve).  Compiles the same
+// vertex_ipm.cuh / vertex_update.cuh sources with GCS_EMULATE so the CPU test suite can check the
+// kernel's arithmetic against the oracle without a GPU.  It is never linked into libgcsadmm.so
+// and nothing in the product path loads it.
+#define GCS_EMULATE 1
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "vertex_update.cuh"
+
+extern "C" int gcsemu_vertex_update_all(int nV, int nE, const int *poly_off, const double *polyA, const double *polyb,
+                                        const int *he_off, const int *he_edge, const unsigned char *he_flags,
+                                        const unsigned char *vtype, const double *cent, double *xc, const double *mu,
+                                        const double *z, double *x_v, double *z_v, double *y_v, double rho, double mu_scale,
+                                        double tol, int max_iter, int dcap, int mcap, long *total_iters) {
+    GcsGraphView G = {nV, nE, poly_off, polyA, polyb, he_off, he_edge, he_flags, vtype, cent};
+    GcsStateView St = {xc, mu, z, x_v, z_v, y_v};
+    GcsScratchLayout L = gcs_scratch_layout(dcap, mcap);
+    double *S = (double *)malloc(sizeof(double) * L.total);
+    int fails = 0;
+    long iters = 0;
+    for (int v = 0; v < nV; ++v) {
+        int status = 0;
+        memset(S, 0, sizeof(double) * L.total);
+        iters += gcs_vertex_update(G, St, v, rho, mu_scale, tol, max_iter, L, S, 0, &status);
+        if (status != 0 && status != 5) { fails++; if (getenv("GCSEMU_VERBOSE")) fprintf(stderr, "emu: vertex %d status %d\n", v, status); }
+    }
+    free(S);
+    *total_iters = iters;
+    return fails;
+}
+extern "C" int gcsemu_scratch_doubles(int dcap, int mcap) { return gcs_scratch_layout(dcap, mcap).total; }

@@ -334,6 +334,40 @@ class PackedGraph:
         self.edge_he_head[edges[is_out == 0]] = hid[is_out == 0]
         self.d_in = np.bincount(head, minlength=nV).astype(np.int32)
         self.d_out = np.bincount(tail, minlength=nV).astype(np.int32)
+        self._classify()
+
+    def _classify(self):
+        """Presolve flags the kernels consume (same rule as the oracle's ``classify``).
+
+        he_flags bit0 = outgoing, bit1 = flow forced to 0 (in-edges of 's', out-edges of
+        't', every edge of a vertex left without a live in- or out-edge).
+        vtype: 0 generic, 1 source, 2 target, 3 dead (no flow can pass)."""
+        nV, H = self.nV, 2 * self.nE
+        owner, out = self.he_owner.astype(np.int64), self.he_out.astype(bool)
+        zero = np.zeros(H, dtype=bool)
+        if self.src >= 0:
+            zero |= (owner == self.src) & ~out
+        if self.dst >= 0:
+            zero |= (owner == self.dst) & out
+        live_in = np.bincount(owner[~out & ~zero], minlength=nV)
+        live_out = np.bincount(owner[out & ~zero], minlength=nV)
+        vid = np.arange(nV)
+        dead = ((vid != self.src) & (live_in == 0)) | ((vid != self.dst) & (live_out == 0))
+        zero |= dead[owner]
+        vtype = np.zeros(nV, dtype=np.uint8)
+        if self.src >= 0:
+            vtype[self.src] = 1
+        if self.dst >= 0:
+            vtype[self.dst] = 2
+        vtype[dead] = 3
+        for t, name in ((self.src, "source has no outgoing edge"), (self.dst, "target has no incoming edge")):
+            if t >= 0 and dead[t]:
+                raise ValueError(f"infeasible problem: {name}")
+        self.he_flags = (out.astype(np.uint8) | (zero.astype(np.uint8) << 1)).astype(np.uint8)
+        self.vtype = vtype
+        live_deg = np.bincount(owner[~zero], minlength=nV)
+        self.max_live_degree = int(live_deg.max()) if nV else 0
+        self.max_rows = int(np.diff(self.poly_off).max()) if nV else 0
 
     @property
     def H(self):

@@ -475,7 +475,7 @@ static IpmInfo vprog_solve(const VProg *p, const int *out, double tol, int max_i
             memcpy(dv, rhs, sizeof(double) * n);
             chol_fwd(L, n, dv); chol_bwd(L, n, dv);
             double en_prev = 1e300;
-            for (int ref = 0; ref < 3; ++ref) { /* iterative refinement against H */
+            for (int ref = 0; ref < (getenv("GCSO_NOREF") ? 0 : 3); ++ref) { /* iterative refinement against H */
                 double en = 0.0, bn = 0.0;
                 for (int i = 0; i < n; ++i) {
                     double s = rhs[i];
