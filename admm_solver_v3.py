@@ -1,0 +1,80 @@
+"""Full vertex splitting ADMM for GCS shortest paths — B200 drop-in for the reference script.
+
+Same command line as reference ``admm_solver_v3.py:29-35``:
+
+    python admm_solver_v3.py --test_file <module name in test_data/> [--show_plot <anything>]
+
+Same side effects: banner, ``V:`` / ``E:`` lines, the progress line at the stop iteration,
+``BREAKING FOR OPT`` / ``BREAKING FOR Divergence``, ``Total solve time``, ``Cost before rounding``, the
+POST-ROUNDING block, and ``benchmark_data/admm_solver_v3_<test>.pkl`` in the reference's pickle schema
+(``utils.py:197-233``).  The loop itself (``:655-733``) runs in libgcsadmm.so on the GPU.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+np.set_printoptions(edgeitems=30, linewidth=250, precision=4, suppress=True)
+
+DEFAULT_TEST_FILE = "benchmark2"
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--test_file", type=str, default=DEFAULT_TEST_FILE,
+                        help="The name of the test file (in `test_data` folder) to use (e.g., 'benchmark2').")
+    # reference quirk kept: any string given here (even "True") disables plotting (:34, :719, :768)
+    parser.add_argument("--show_plot", type=str, default=True, help="Whether to display plot.")
+    parser.add_argument("--seed", type=int, default=None, help="seed of the rounding walk (reference: unseeded)")
+    parser.add_argument("--device", type=int, default=0)
+    args = parser.parse_args(argv)
+
+    print("=======================================================================")
+    print(f"Running ADMM Solver v3 on {args.test_file}")
+    print("=======================================================================\n")
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    import utils
+    from gcs_admm_b200.problem_io import load_test_file
+    from gcs_admm_b200.solver import solve, MAX_IT
+    test_data_path = os.path.join(here, "test_data")
+    try:
+        As, bs, n = load_test_file(args.test_file, test_data_path)
+    except ModuleNotFoundError:
+        print(f"Error: Test file '{args.test_file}' not found in {test_data_path}.")
+        sys.exit(1)
+
+    V, E, I_v_in, I_v_out = utils.build_graph(As, bs)
+    print(f"V: {V}")
+    print(f"E: {E}")
+    from gcs_admm_b200.graph import pack_graph
+    g = pack_graph(As, bs, V, E)
+    res = solve(As, bs, n, device=args.device, seed=args.seed, graph=(V, E, I_v_in, I_v_out, g))
+    it = res["iterations"]
+    if res["diverged"]:
+        print("BREAKING FOR Divergence")
+    print(f"it = {it}/{MAX_IT}, pri_res_seq[-1]={res['pri_res_seq'][-1]}, dual_res_seq[-1]={res['dual_res_seq'][-1]}")
+    if res["converged"]:
+        print("BREAKING FOR OPT")
+    print(f"x_v: {res['x_v_sol']}")
+    print(f"y_v: {res['y_v_sol']}")
+    print(f"Total solve time: {res['solve_time']} s.")
+    print(f"Cost before rounding: {res['cost']}")
+    print("===============================================================")
+    print("POST-ROUNDING")
+    print("===============================================================")
+    x_v_rounded, y_v_rounded = res["x_v_rounded"], res["y_v_rounded"]
+    print(f"{x_v_rounded=}\n")
+    print(f"{y_v_rounded=}\n")
+    if args.show_plot == True:  # noqa: E712  (reference semantics)
+        utils.visualize_results(As, bs, res["x_v_sol"], res["y_v_sol"], x_v_rounded, y_v_rounded)
+    utils.save_data(os.path.join(here, f"benchmark_data/admm_solver_v3_{args.test_file}.pkl"), As, bs, res["solve_time"],
+                    res["cost"], res["x_v_sol"], res["y_v_sol"], x_v_rounded, y_v_rounded, True, it,
+                    np.asarray(res["rho_seq"]), np.asarray(res["pri_res_seq"]), np.asarray(res["dual_res_seq"]))
+    return res
+
+
+if __name__ == "__main__":
+    main()

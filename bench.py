@@ -1,0 +1,206 @@
+"""bench.py — ADMM iterations/s of the full-vertex-split iteration on the 100k-vertex 2-D grid GCS.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--grid G] [--impl reference]
+
+A "step" is one ADMM iteration (K1 vertex programs + fused edge/dual/residual kernel + control)
+over the whole graph.  `value` = iterations/s with the graph resident in HBM (CUDA events on the
+library's stream, L2 flushed between timed iterations); `e2e` = the same metric through the
+host-buffer C-ABI call gcsadmm_solve_host (graph upload + K iterations + solution download inside
+the timed region).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "admm_iterations_per_second"
+UNIT = "it/s"
+
+
+def algorithmic_bytes(g):
+    """compulsory fp64 traffic of one ADMM iteration.
+    K1: targets z (gather, H*5) + mu (H*5) read, xc (H*5) written, polytopes, CSR indices.
+    K2-4: xc read (H*5), z read+written (2*E*5), mu read+written (2*H*5), edge->half-edge indices."""
+    E, H, V = g.nE, 2 * g.nE, g.nV
+    sum_m = int(g.poly_off[-1])
+    k1 = 8 * (3 * 5 * H + 3 * sum_m) + 4 * (V + 1) + 4 * H + H + V + 16 * V
+    k2 = 8 * (3 * 5 * H + 2 * 5 * E) + 8 * E
+    return k1, k2
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def finish(self):
+        self._stop.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons}
+
+
+def cpu_baseline(G_sample, V_full, iters=2):
+    """C oracle (port of the reference's algorithm, OpenMP over vertices) on a bounded sample:
+    a G_sample x G_sample grid of the same family; cost per iteration is linear in |V|, so the
+    figure is scaled to the full graph's vertex count."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import utils  # noqa: F401
+    from c_oracle import COracle, lib as olib
+    from gcs_admm_b200.generator import grid_packed_graph
+    g = grid_packed_graph(G_sample)
+    o = COracle(g)
+    o.step(1)                       # warm-up (first iteration is the all-zero start)
+    t0 = time.perf_counter()
+    o.step(iters)
+    dt = (time.perf_counter() - t0) / iters
+    its_sample = 1.0 / dt
+    return {"value": its_sample * g.nV / V_full, "unit": UNIT, "cores": olib().gcso_num_threads(), "kind": "port",
+            "sample": f"{iters} ADMM iterations of the C oracle on the {G_sample}x{G_sample} grid ({g.nV} vertices, "
+                      f"{its_sample:.3f} it/s), scaled by |V| to the {V_full}-vertex workload"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm on the host cores.  The reference itself
+    (pydrake + MOSEK) is not installable offline, so the oracle port stands in (kind='port')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import utils  # noqa: F401
+    from c_oracle import COracle, lib as olib
+    from gcs_admm_b200.generator import grid_packed_graph
+    V_full = args.grid * args.grid + 2
+    Gs = min(args.grid, 48)
+    g = grid_packed_graph(Gs)
+    o = COracle(g)
+    for _ in range(args.warmup):
+        o.step(1)
+    t0 = time.perf_counter()
+    o.step(args.steps)
+    dt = time.perf_counter() - t0
+    val = args.steps / dt * g.nV / V_full
+    sample = (f"each step = one ADMM iteration of the C oracle on the {Gs}x{Gs} grid ({g.nV} vertices), "
+              f"scaled by |V| to the {V_full}-vertex workload")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps * V_full / g.nV, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"grid{args.grid}x{args.grid} 2-D GCS ({V_full} vertices)", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": olib().gcso_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--grid", type=int, default=316, help="G: the workload is the G x G grid GCS (316 -> 99 858 vertices)")
+    ap.add_argument("--impl", type=str, default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--residual-run", type=int, default=0, help="also run up to this many iterations with the abs 1e-4 stop and report the time")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 or args.gpus > 1:
+        from gcs_admm_b200 import dist_bench  # multi-GPU path (vertex-partitioned, NCCL halo exchange)
+        import gcs_admm_b200  # noqa: F401
+        return dist_bench.main(args)
+
+    import utils  # noqa: F401
+    from gcs_admm_b200 import lib
+    from gcs_admm_b200.generator import grid_packed_graph
+    W = max(3, args.warmup)
+    g = grid_packed_graph(args.grid)
+    k1_bytes, k2_bytes = algorithmic_bytes(g)
+    s = lib.Solver(g, device=0, max_it=max(1000, args.steps + W + 8))
+    s.step(W)
+    sampler = ClockSampler(0)
+    sampler.start()
+    tot = k1 = ed = 0.0
+    for _ in range(args.steps):          # L2 flushed before every timed iteration, outside the event pair
+        s.flush_l2()
+        a, b, c = s.time_steps(1, split=True)
+        tot += a; k1 += b; ed += c
+    clocks = sampler.finish()
+    st = s.status()
+    ms = tot / args.steps
+    value = 1e3 / ms
+    s.close()
+    # end to end through the host-buffer C-ABI call (graph upload + K iterations + download)
+    gs_bytes = sum(a.nbytes for a in (g.poly_off, g.polyA, g.polyb, g.he_off, g.he_edge, g.he_flags, g.edge_he_tail,
+                                      g.edge_he_head, g.vtype)) + 16 * g.nV
+    out_bytes = 8 * (9 * g.nV + 5 * g.nE) + 3 * 8 * (args.steps + 1)
+    t0 = time.perf_counter()
+    out = lib.solve_host(g, device=0, max_iters=args.steps, max_it=max(1000, args.steps + 8), check_every=args.steps,
+                         eps_abs=0.0, eps_rel=0.0)
+    e2e_s = time.perf_counter() - t0
+    assert out["status"]["iterations"] == args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    k1_ms = k1 / args.steps
+    achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": W,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"grid{args.grid}x{args.grid} 2-D GCS: {g.nV} vertices, {g.nE} directed edges, m=8 rows/region "
+                               "(BASELINE.json metric config: 100k-vertex 2-D GCS)", "mode": "parity (vertex programs solved to 1e-9)",
+                   "l2": "flushed (256 MiB memset) before every timed iteration", "inner_ipm_iters_per_vertex": st["inner_iters"] / max(1, st["iterations"] * g.nV)},
+        "clocks": clocks,
+        "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": gs_bytes / args.steps, "d2h_bytes_per_step": out_bytes / args.steps,
+                "note": "gcsadmm_solve_host: graph upload + K iterations + solution/history download, wall clock"},
+        "gpu_launches": 4 * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "vertex_kernel (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                     "algorithmic_bytes_per_launch": k1_bytes, "kernel_ms": k1_ms,
+                     "whole_iteration": {"bytes": k1_bytes + k2_bytes, "achieved": (k1_bytes + k2_bytes) / (ms * 1e-3) / 1e9,
+                                         "frac": (k1_bytes + k2_bytes) / (ms * 1e-3) / 1e9 / peak},
+                     "edge_kernel": {"bytes": k2_bytes, "ms": ed / args.steps, "achieved": k2_bytes / (ed / args.steps * 1e-3) / 1e9}},
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(min(args.grid, 48), g.nV)
+    if args.residual_run:
+        s2 = lib.Solver(g, device=0, max_it=args.residual_run, abs_stop=1, abs_tol=1e-4, check_every=16)
+        t0 = time.perf_counter()
+        st2 = s2.run(args.residual_run)
+        line["time_to_residual_1e-4"] = {"seconds": time.perf_counter() - t0, "iterations": st2["iterations"], "reached": bool(st2["converged"]),
+                                         "pri_res": st2["pri_res"], "dual_res": st2["dual_res"]}
+        s2.close()
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

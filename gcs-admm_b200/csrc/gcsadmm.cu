@@ -1,0 +1,513 @@
+// libgcsadmm.so — kernels and C-ABI (include/gcsadmm.h).  sm_100a only; no CPU path.
+//
+//   K1  vertex_kernel   one warp per vertex, interior-point prox solve in shared memory   (vertex_update.cuh)
+//   K2-4 edge_kernel    one thread per edge: z-update (average of the two copies), dual update of both
+//                       half-edges, and the five squared norms, fused; block partials, no atomics
+//   K5  control_kernel  one block: deterministic reduction of the partials, residuals, rho adaptation,
+//                       stop rule, history (reference admm_solver_v3.py:697-713)
+// Every kernel returns immediately once the stop flag is set, so the host can enqueue iterations in
+// chunks and poll the control block once per chunk while keeping the reference's exact stop iteration.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/gcsadmm.h"
+#include "vertex_update.cuh"
+
+#define GCS_VERSION "gcsadmm 0.1.0 (sm_100a)"
+#define K1_MAX_WARPS 8   // 254 registers/thread: 8 warps fill the register file of one SM
+#define EDGE_THREADS 256
+#define NSUMS 8   // r2, dz2, x2, z2, mu2(pre-scale), nonfinite, spare, spare
+
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char *fmt, const char *a = "", const char *b = "") {
+    snprintf(g_err, sizeof g_err, fmt, a, b);
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return set_err(GCS_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct Ctrl {
+    double rho, mu_scale;
+    double pri, dual, eps_pri, eps_dual;
+    double sums[NSUMS];
+    unsigned long long inner_iters;
+    int it, stop, opt, diverged, inner_fail, ignore_stop;
+};
+
+struct GcsHandle {
+    int device;
+    cudaStream_t stream, own_stream;
+    GcsParams p;
+    int nV, nE, nHown, nHghost;
+    long long n_x, n_mu;
+    int dcap, mcap;
+    GcsScratchLayout L;
+    int k1_smem, k1_blocks, k1_warps, edge_blocks;
+    // device
+    int *poly_off, *he_off, *he_edge, *edge_he_tail, *edge_he_head;
+    double *polyA, *polyb, *cent;
+    unsigned char *he_flags, *vtype, *edge_counted;
+    double *xc, *mu, *z, *x_v, *z_v, *y_v;
+    double *partials;   // [edge_blocks][NSUMS]
+    double *hist;       // [3][hist_cap]
+    int hist_cap;
+    Ctrl *ctrl;         // device
+    Ctrl *ctrl_host;    // pinned
+    cudaEvent_t ev[4];
+    void *flush_buf; size_t flush_bytes;
+};
+
+// ------------------------------------------------------------------------------------------ K1
+__global__ void __launch_bounds__(K1_MAX_WARPS * 32)
+vertex_kernel(GcsGraphView G, GcsStateView St, Ctrl *ctrl, GcsScratchLayout L, double tol, int max_iter) {
+    extern __shared__ double smem[];
+    if (ctrl->stop && !ctrl->ignore_stop) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (v >= G.nV) return;
+    double *S = smem + (size_t)warp * L.total;
+    int status = 0;
+    const int iters = gcs_vertex_update(G, St, v, ctrl->rho, ctrl->mu_scale, tol, max_iter, L, S, lane, &status);
+    if (lane == 0) {
+        if (iters) atomicAdd(&ctrl->inner_iters, (unsigned long long)iters);
+        if (status != 0 && status != 5) atomicAdd(&ctrl->inner_fail, 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K2-K4
+// z_e = 1/2 (xc_tail + xc_head)            reference admm_solver_v3.py:543-562 (live scalars only)
+// mu_h <- mu_scale * mu_h + (z_e - xc_h)    :590-594  (mu_scale carries the rho-adaptation rescale :705/:708)
+// partial sums of |z - xc|^2, |dz|^2, |xc|^2, |z|^2, |mu|^2     :597-614
+__global__ void __launch_bounds__(EDGE_THREADS)
+edge_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *__restrict__ edge_he_head,
+            const unsigned char *__restrict__ edge_counted, const double *__restrict__ xc, double *__restrict__ mu,
+            double *__restrict__ z, Ctrl *ctrl, double *__restrict__ partials) {
+    if (ctrl->stop && !ctrl->ignore_stop) return;
+    const double ms = ctrl->mu_scale;
+    double r2 = 0, dz2 = 0, x2 = 0, z2 = 0, m2 = 0, bad = 0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
+        const int ht = edge_he_tail[e], hh = edge_he_head[e];
+        const double w = edge_counted ? (double)edge_counted[e] : 1.0;
+        double xt[5], xh[5], zn[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { xt[c] = xc[5 * (size_t)ht + c]; xh[c] = xc[5 * (size_t)hh + c]; }
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const double zo = z[5 * (size_t)e + c];
+            zn[c] = 0.5 * (xt[c] + xh[c]);
+            const double dd = zn[c] - zo;
+            dz2 += w * dd * dd; z2 += w * zn[c] * zn[c];
+            z[5 * (size_t)e + c] = zn[c];
+        }
+        if (ht < nHown) {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                const double r = zn[c] - xt[c], mn = ms * mu[5 * (size_t)ht + c] + r;
+                mu[5 * (size_t)ht + c] = mn; r2 += r * r; x2 += xt[c] * xt[c]; m2 += mn * mn;
+            }
+        }
+        if (hh < nHown) {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                const double r = zn[c] - xh[c], mn = ms * mu[5 * (size_t)hh + c] + r;
+                mu[5 * (size_t)hh + c] = mn; r2 += r * r; x2 += xh[c] * xh[c]; m2 += mn * mn;
+            }
+        }
+    }
+    if (!isfinite(r2) || !isfinite(dz2) || !isfinite(x2) || !isfinite(z2)) bad = 1.0;
+    // block reduction (fixed order: shuffles, then warp partials in shared memory)
+    __shared__ double sh[EDGE_THREADS / 32][6];
+    double vals[6] = {r2, dz2, x2, z2, m2, bad};
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) vals[q] += __shfl_xor_sync(0xffffffffu, vals[q], o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0)
+        for (int q = 0; q < 6; ++q) sh[warp][q] = vals[q];
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double s = 0.0;
+        for (int w2 = 0; w2 < EDGE_THREADS / 32; ++w2) s += sh[w2][threadIdx.x];
+        partials[(size_t)blockIdx.x * NSUMS + threadIdx.x] = s;
+    }
+}
+
+// sums the block partials in a fixed order -> ctrl->sums  (all-reduced across ranks by the multi-GPU driver)
+__global__ void reduce_kernel(const double *__restrict__ partials, int nblocks, Ctrl *ctrl) {
+    if (ctrl->stop && !ctrl->ignore_stop) return;
+    __shared__ double sh[256][6];
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+        for (int q = 0; q < 6; ++q) acc[q] += partials[(size_t)b * NSUMS + q];
+    for (int q = 0; q < 6; ++q) sh[threadIdx.x][q] = acc[q];
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+            for (int q = 0; q < 6; ++q) sh[threadIdx.x][q] += sh[threadIdx.x + s][q];
+        __syncthreads();
+    }
+    if (threadIdx.x < 6) ctrl->sums[threadIdx.x] = sh[0][threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------ K5
+// reference admm_solver_v3.py:697-713 and :733, on the reduced sums
+__global__ void control_kernel(Ctrl *ctrl, GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (ctrl->stop && !ctrl->ignore_stop) return;
+    const int it = ctrl->it + 1;
+    const double *s = ctrl->sums;
+    const double rho = ctrl->rho;
+    const double pri = sqrt(s[0]);                       // :598  ||A x + B z - c||
+    const double dual = rho * sqrt(2.0 * s[1]);          // :602  rho ||A'B dz|| = rho sqrt2 ||dz||
+    double rho_new = rho, scale = 1.0;
+    if (pri >= p.nu * dual && it < p.frac * p.max_it) { rho_new = rho * p.tau_incr; scale = 1.0 / p.tau_incr; }        // :703-705
+    else if (dual >= p.nu * pri && it < p.frac * p.max_it) { rho_new = rho * (1.0 / p.tau_decr); scale = p.tau_incr; } // :706-708
+    const double nAx = sqrt(s[2]), nBz = sqrt(2.0 * s[3]), nmu = scale * sqrt(s[4]);
+    const double eps_pri = sqrt((double)n_x) * p.eps_abs + p.eps_rel * fmax(nAx, nBz);   // :605-610
+    const double eps_dual = sqrt((double)n_mu) * p.eps_abs + p.eps_rel * nmu;            // :613-614
+    ctrl->it = it; ctrl->pri = pri; ctrl->dual = dual; ctrl->eps_pri = eps_pri; ctrl->eps_dual = eps_dual;
+    ctrl->rho = rho_new; ctrl->mu_scale = scale;
+    if (it < hist_cap) { hist[it] = rho_new; hist[hist_cap + it] = pri; hist[2 * hist_cap + it] = dual; }
+    if (s[5] != 0.0 || !isfinite(pri) || !isfinite(dual)) { ctrl->diverged = 1; ctrl->stop = 1; return; }  // :662-664
+    const bool opt = p.abs_stop ? (fmax(pri, dual) < p.abs_tol) : (pri < eps_pri && dual < eps_dual);        // :712
+    if (opt) { ctrl->opt = 1; ctrl->stop = 1; }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+extern "C" const char *gcsadmm_version(void) { return GCS_VERSION; }
+extern "C" const char *gcsadmm_last_error(void) { return g_err; }
+extern "C" int gcsadmm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" void gcsadmm_default_params(GcsParams *p) {
+    p->rho0 = 1.0; p->tau_incr = 2.0; p->tau_decr = 2.0; p->nu = 10.0; p->frac = 0.1;
+    p->eps_abs = 1e-4; p->eps_rel = 1e-3; p->max_it = 1000; p->inner_tol = 1e-9; p->inner_max_iter = 60;
+    p->check_every = 8; p->abs_stop = 0; p->abs_tol = 1e-4;
+}
+extern "C" int gcsadmm_scratch_bytes(int max_live_degree, int max_rows) {
+    return (int)(gcs_scratch_layout(max_live_degree, max_rows).total * sizeof(double));
+}
+
+template <typename T>
+static int upload(T **dst, const T *src, size_t n) {
+    if (n == 0) n = 1, src = nullptr;
+    cudaError_t e = cudaMalloc((void **)dst, n * sizeof(T));
+    if (e != cudaSuccess) return set_err(GCS_E_NOMEM, "cudaMalloc(%s bytes): %s", "", cudaGetErrorString(e));
+    if (src) { e = cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice); if (e != cudaSuccess) return set_err(GCS_E_CUDA, "cudaMemcpy H2D: %s", cudaGetErrorString(e)); }
+    else cudaMemset(*dst, 0, n * sizeof(T));
+    return 0;
+}
+
+static int reset_ctrl(GcsHandle *h) {
+    Ctrl c; memset(&c, 0, sizeof c);
+    c.rho = h->p.rho0; c.mu_scale = 1.0;
+    CK(cudaMemcpyAsync(h->ctrl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
+    double first[3] = {h->p.rho0, 0.0, 0.0};   // admm_solver_v3.py:637-639: seeds of the three sequences
+    for (int q = 0; q < 3; ++q) CK(cudaMemcpyAsync(h->hist + (size_t)q * h->hist_cap, &first[q], sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int gcsadmm_destroy(GcsHandle *h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    void *ptrs[] = {h->poly_off, h->he_off, h->he_edge, h->edge_he_tail, h->edge_he_head, h->polyA, h->polyb, h->cent,
+                    h->he_flags, h->vtype, h->edge_counted, h->xc, h->mu, h->z, h->x_v, h->z_v, h->y_v, h->partials, h->hist, h->ctrl};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
+    if (h->flush_buf) cudaFree(h->flush_buf);
+    for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return 0;
+}
+
+extern "C" int gcsadmm_create(const GcsGraph *g, const GcsParams *p, int device, GcsHandle **out) {
+    if (!g || !out) return set_err(GCS_E_INVALID, "null argument%s", "");
+    *out = nullptr;
+    if (g->n != 2) return set_err(GCS_E_INVALID, "the CUDA path is specialised to n = 2 (2-D GCS)%s", "");
+    if (g->nV <= 0 || g->nE < 0) return set_err(GCS_E_INVALID, "empty graph%s", "");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return set_err(GCS_E_CUDA, "no CUDA device: libgcsadmm has no CPU path%s", ""); }
+    if (device < 0 || device >= ndev) return set_err(GCS_E_INVALID, "bad device index%s", "");
+    CK(cudaSetDevice(device));
+    GcsHandle *h = new (std::nothrow) GcsHandle();
+    if (!h) return set_err(GCS_E_NOMEM, "out of host memory%s", "");
+    memset(h, 0, sizeof *h);
+    h->device = device;
+    if (p) h->p = *p; else gcsadmm_default_params(&h->p);
+    if (h->p.check_every < 1) h->p.check_every = 1;
+    h->nV = g->nV; h->nE = g->nE; h->nHown = g->nH_own; h->nHghost = g->nH_ghost;
+    h->n_x = g->n_x_global ? g->n_x_global : 9LL * g->nV + 18LL * g->nE;
+    h->n_mu = g->n_mu_global ? g->n_mu_global : 10LL * g->nE;
+    // capacity of a vertex program: live degree and polytope rows
+    int dcap = 1, mcap = 1;
+    for (int v = 0; v < g->nV; ++v) {
+        int d = 0;
+        for (int hh = g->he_off[v]; hh < g->he_off[v + 1]; ++hh) if (!(g->he_flags[hh] & GCS_HE_FLAG_ZERO)) d++;
+        if (d > dcap) dcap = d;
+        int m = g->poly_off[v + 1] - g->poly_off[v];
+        if (m > mcap) mcap = m;
+        if (g->vtype[v] == GCS_VT_GENERIC && d < 2) { delete h; return set_err(GCS_E_INVALID, "inconsistent presolve flags (generic vertex with < 2 live half-edges)%s", ""); }
+    }
+    h->dcap = dcap; h->mcap = mcap;
+    h->L = gcs_scratch_layout(dcap, mcap);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    {   // as many warps per block as shared memory allows (one block per SM when the programs are large)
+        const size_t per_warp = (size_t)h->L.total * sizeof(double);
+        const size_t budget = prop.sharedMemPerBlockOptin;
+        int w = (int)(budget / per_warp);
+        if (w < 1) {
+            delete h;
+            return set_err(GCS_E_INVALID, "vertex program too large for shared memory (max live degree / polytope rows too high)%s", "");
+        }
+        if (w > K1_MAX_WARPS) w = K1_MAX_WARPS;
+        // prefer two resident blocks per SM when that keeps more warps in flight
+        const int w2 = (int)((prop.sharedMemPerMultiprocessor / 2 - 1024) / per_warp);
+        if (w2 >= 2 && 2 * (w2 > K1_MAX_WARPS / 2 ? K1_MAX_WARPS / 2 : w2) >= w) w = w2 > K1_MAX_WARPS / 2 ? K1_MAX_WARPS / 2 : w2;
+        h->k1_warps = w;
+        h->k1_smem = (int)(w * per_warp);
+    }
+    CK(cudaFuncSetAttribute(vertex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k1_smem));
+    h->k1_blocks = (g->nV + h->k1_warps - 1) / h->k1_warps;
+    int eb = (g->nE + EDGE_THREADS - 1) / EDGE_THREADS;
+    int cap = prop.multiProcessorCount * 8;
+    h->edge_blocks = eb < 1 ? 1 : (eb > cap ? cap : eb);
+    CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    const size_t M = (size_t)g->poly_off[g->nV], Hall = (size_t)g->nH_own + g->nH_ghost;
+    int rc = 0;
+#define UP(field, src, n) if (!rc) rc = upload(&h->field, src, (size_t)(n))
+    UP(poly_off, g->poly_off, g->nV + 1); UP(polyA, g->polyA, 2 * M); UP(polyb, g->polyb, M);
+    UP(he_off, g->he_off, g->nV + 1); UP(he_edge, g->he_edge, g->nH_own); UP(he_flags, g->he_flags, g->nH_own);
+    UP(edge_he_tail, g->edge_he_tail, g->nE); UP(edge_he_head, g->edge_he_head, g->nE);
+    UP(vtype, g->vtype, g->nV); UP(cent, g->cent, 2 * (size_t)g->nV);
+    if (g->edge_counted) UP(edge_counted, g->edge_counted, g->nE);
+    UP(xc, (const double *)nullptr, 5 * Hall); UP(mu, (const double *)nullptr, 5 * (size_t)g->nH_own); UP(z, (const double *)nullptr, 5 * (size_t)g->nE);
+    UP(x_v, (const double *)nullptr, 4 * (size_t)g->nV); UP(z_v, (const double *)nullptr, 4 * (size_t)g->nV); UP(y_v, (const double *)nullptr, g->nV);
+    UP(partials, (const double *)nullptr, (size_t)h->edge_blocks * NSUMS);
+    h->hist_cap = h->p.max_it + 2;
+    UP(hist, (const double *)nullptr, 3 * (size_t)h->hist_cap);
+#undef UP
+    if (rc) { gcsadmm_destroy(h); return rc; }
+    CK(cudaMalloc((void **)&h->ctrl, sizeof(Ctrl)));
+    CK(cudaMallocHost((void **)&h->ctrl_host, sizeof(Ctrl)));
+    for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&h->ev[i]));
+    rc = reset_ctrl(h);
+    if (rc) { gcsadmm_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+extern "C" int gcsadmm_set_stream(GcsHandle *h, void *s) {
+    if (!h) return set_err(GCS_E_INVALID, "null handle%s", "");
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return 0;
+}
+
+static GcsGraphView graph_view(const GcsHandle *h) {
+    GcsGraphView G; G.nV = h->nV; G.nE = h->nE; G.poly_off = h->poly_off; G.polyA = h->polyA; G.polyb = h->polyb;
+    G.he_off = h->he_off; G.he_edge = h->he_edge; G.he_flags = h->he_flags; G.vtype = h->vtype; G.cent = h->cent;
+    return G;
+}
+static GcsStateView state_view(const GcsHandle *h) {
+    GcsStateView S; S.xc = h->xc; S.mu = h->mu; S.z = h->z; S.x_v = h->x_v; S.z_v = h->z_v; S.y_v = h->y_v;
+    return S;
+}
+static int launch_k1(GcsHandle *h) {
+    vertex_kernel<<<h->k1_blocks, h->k1_warps * 32, h->k1_smem, h->stream>>>(graph_view(h), state_view(h), h->ctrl, h->L, h->p.inner_tol, h->p.inner_max_iter);
+    return 0;
+}
+static int launch_edge(GcsHandle *h) {
+    edge_kernel<<<h->edge_blocks, EDGE_THREADS, 0, h->stream>>>(h->nE, h->nHown, h->edge_he_tail, h->edge_he_head, h->edge_counted, h->xc, h->mu, h->z, h->ctrl, h->partials);
+    reduce_kernel<<<1, 256, 0, h->stream>>>(h->partials, h->edge_blocks, h->ctrl);
+    return 0;
+}
+static int launch_ctrl(GcsHandle *h) {
+    control_kernel<<<1, 32, 0, h->stream>>>(h->ctrl, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap);
+    return 0;
+}
+static int set_ignore_stop(GcsHandle *h, int v) {
+    CK(cudaMemcpyAsync((char *)h->ctrl + offsetof(Ctrl, ignore_stop), &v, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+static int fetch_ctrl(GcsHandle *h) {
+    CK(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+static void fill_status(const GcsHandle *h, GcsStatus *st) {
+    const Ctrl *c = h->ctrl_host;
+    st->iterations = c->it; st->converged = c->opt; st->diverged = c->diverged; st->inner_fail = c->inner_fail;
+    st->inner_iters = (int64_t)c->inner_iters; st->rho = c->rho; st->pri_res = c->pri; st->dual_res = c->dual;
+    st->eps_pri = c->eps_pri; st->eps_dual = c->eps_dual;
+}
+
+extern "C" int gcsadmm_vertex_update(GcsHandle *h) { if (!h) return set_err(GCS_E_INVALID, "null handle%s", ""); CK(cudaSetDevice(h->device)); launch_k1(h); CK(cudaGetLastError()); return 0; }
+extern "C" int gcsadmm_edge_update(GcsHandle *h) { if (!h) return set_err(GCS_E_INVALID, "null handle%s", ""); CK(cudaSetDevice(h->device)); launch_edge(h); CK(cudaGetLastError()); return 0; }
+extern "C" int gcsadmm_control(GcsHandle *h) { if (!h) return set_err(GCS_E_INVALID, "null handle%s", ""); CK(cudaSetDevice(h->device)); launch_ctrl(h); CK(cudaGetLastError()); return 0; }
+extern "C" int gcsadmm_sums_device_ptr(GcsHandle *h, void **p) { if (!h || !p) return set_err(GCS_E_INVALID, "null argument%s", ""); *p = (char *)h->ctrl + offsetof(Ctrl, sums); return 0; }
+extern "C" int gcsadmm_xc_device_ptr(GcsHandle *h, void **p) { if (!h || !p) return set_err(GCS_E_INVALID, "null argument%s", ""); *p = h->xc; return 0; }
+
+extern "C" int gcsadmm_step(GcsHandle *h, int k) {
+    if (!h) return set_err(GCS_E_INVALID, "null handle%s", "");
+    CK(cudaSetDevice(h->device));
+    int rc = set_ignore_stop(h, 1); if (rc) return rc;
+    for (int i = 0; i < k; ++i) { launch_k1(h); launch_edge(h); launch_ctrl(h); }
+    rc = set_ignore_stop(h, 0); if (rc) return rc;
+    CK(cudaGetLastError());
+    return fetch_ctrl(h);
+}
+
+extern "C" int gcsadmm_run(GcsHandle *h, int max_iters, GcsStatus *st) {
+    if (!h) return set_err(GCS_E_INVALID, "null handle%s", "");
+    CK(cudaSetDevice(h->device));
+    int rc = fetch_ctrl(h); if (rc) return rc;
+    int done = 0;
+    while (done < max_iters && !h->ctrl_host->stop) {
+        int chunk = h->p.check_every;
+        if (chunk > max_iters - done) chunk = max_iters - done;
+        for (int i = 0; i < chunk; ++i) { launch_k1(h); launch_edge(h); launch_ctrl(h); }
+        CK(cudaGetLastError());
+        rc = fetch_ctrl(h); if (rc) return rc;
+        done += chunk;
+    }
+    if (st) fill_status(h, st);
+    if (h->ctrl_host->diverged) return set_err(GCS_E_DIVERGED, "non-finite residuals (divergence)%s", "");
+    return 0;
+}
+
+extern "C" int gcsadmm_get_status(GcsHandle *h, GcsStatus *st) {
+    if (!h || !st) return set_err(GCS_E_INVALID, "null argument%s", "");
+    CK(cudaSetDevice(h->device));
+    int rc = fetch_ctrl(h); if (rc) return rc;
+    fill_status(h, st);
+    return 0;
+}
+
+extern "C" int gcsadmm_get_history(GcsHandle *h, double *rho, double *pri, double *dual, int cap) {
+    if (!h) return set_err(GCS_E_INVALID, "null handle%s", "");
+    CK(cudaSetDevice(h->device));
+    int rc = fetch_ctrl(h); if (rc) return rc;
+    int n = h->ctrl_host->it + 1;
+    if (n > h->hist_cap) n = h->hist_cap;
+    if (n > cap) n = cap;
+    double *dst[3] = {rho, pri, dual};
+    for (int q = 0; q < 3; ++q) if (dst[q]) CK(cudaMemcpy(dst[q], h->hist + (size_t)q * h->hist_cap, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+extern "C" int gcsadmm_get_solution(GcsHandle *h, double *x_v, double *z_v, double *y_v, double *z_e) {
+    if (!h) return set_err(GCS_E_INVALID, "null handle%s", "");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (x_v) CK(cudaMemcpy(x_v, h->x_v, sizeof(double) * 4 * h->nV, cudaMemcpyDeviceToHost));
+    if (z_v) CK(cudaMemcpy(z_v, h->z_v, sizeof(double) * 4 * h->nV, cudaMemcpyDeviceToHost));
+    if (y_v) CK(cudaMemcpy(y_v, h->y_v, sizeof(double) * h->nV, cudaMemcpyDeviceToHost));
+    if (z_e) CK(cudaMemcpy(z_e, h->z, sizeof(double) * 5 * h->nE, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int gcsadmm_get_state(GcsHandle *h, double *xc, double *mu, double *z, double *rho, int *it) {
+    if (!h) return set_err(GCS_E_INVALID, "null handle%s", "");
+    CK(cudaSetDevice(h->device));
+    int rc = fetch_ctrl(h); if (rc) return rc;
+    if (xc) CK(cudaMemcpy(xc, h->xc, sizeof(double) * 5 * ((size_t)h->nHown + h->nHghost), cudaMemcpyDeviceToHost));
+    if (mu) {   // stored duals carry a pending rho-adaptation rescale: return the effective values
+        CK(cudaMemcpy(mu, h->mu, sizeof(double) * 5 * (size_t)h->nHown, cudaMemcpyDeviceToHost));
+        const double s = h->ctrl_host->mu_scale;
+        if (s != 1.0) for (size_t i = 0; i < 5 * (size_t)h->nHown; ++i) mu[i] *= s;
+    }
+    if (z) CK(cudaMemcpy(z, h->z, sizeof(double) * 5 * (size_t)h->nE, cudaMemcpyDeviceToHost));
+    if (rho) *rho = h->ctrl_host->rho;
+    if (it) *it = h->ctrl_host->it;
+    return 0;
+}
+
+extern "C" int gcsadmm_set_state(GcsHandle *h, const double *xc, const double *mu, const double *z, double rho, int it) {
+    if (!h) return set_err(GCS_E_INVALID, "null handle%s", "");
+    CK(cudaSetDevice(h->device));
+    int rc = fetch_ctrl(h); if (rc) return rc;
+    if (xc) CK(cudaMemcpy(h->xc, xc, sizeof(double) * 5 * ((size_t)h->nHown + h->nHghost), cudaMemcpyHostToDevice));
+    if (mu) CK(cudaMemcpy(h->mu, mu, sizeof(double) * 5 * (size_t)h->nHown, cudaMemcpyHostToDevice));
+    if (z) CK(cudaMemcpy(h->z, z, sizeof(double) * 5 * (size_t)h->nE, cudaMemcpyHostToDevice));
+    Ctrl c = *h->ctrl_host;
+    c.rho = rho; c.it = it; c.mu_scale = 1.0; c.stop = 0; c.opt = 0; c.diverged = 0;
+    CK(cudaMemcpy(h->ctrl, &c, sizeof c, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int gcsadmm_time_steps(GcsHandle *h, int k, float *ms_total, float *ms_k1, float *ms_edge) {
+    if (!h || !ms_total) return set_err(GCS_E_INVALID, "null argument%s", "");
+    CK(cudaSetDevice(h->device));
+    int rc = set_ignore_stop(h, 1); if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    float k1 = 0.f, ed = 0.f;
+    const bool split = ms_k1 || ms_edge;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    for (int i = 0; i < k; ++i) {
+        if (split) CK(cudaEventRecord(h->ev[1], h->stream));
+        launch_k1(h);
+        if (split) CK(cudaEventRecord(h->ev[2], h->stream));
+        launch_edge(h); launch_ctrl(h);
+        if (split) {
+            CK(cudaEventRecord(h->ev[3], h->stream));
+            CK(cudaEventSynchronize(h->ev[3]));
+            float a = 0.f, b = 0.f;
+            CK(cudaEventElapsedTime(&a, h->ev[1], h->ev[2])); CK(cudaEventElapsedTime(&b, h->ev[2], h->ev[3]));
+            k1 += a; ed += b;
+        }
+    }
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    CK(cudaEventSynchronize(h->ev[3]));
+    CK(cudaEventElapsedTime(ms_total, h->ev[0], h->ev[3]));
+    if (ms_k1) *ms_k1 = k1;
+    if (ms_edge) *ms_edge = ed;
+    rc = set_ignore_stop(h, 0); if (rc) return rc;
+    CK(cudaGetLastError());
+    return fetch_ctrl(h);
+}
+
+extern "C" int gcsadmm_solve_host(const GcsGraph *g, const GcsParams *p, int device, int max_iters, GcsStatus *st,
+                                  double *x_v, double *z_v, double *y_v, double *z_e,
+                                  double *rho_seq, double *pri_seq, double *dual_seq, int hist_cap) {
+    GcsHandle *h = nullptr;
+    int rc = gcsadmm_create(g, p, device, &h);
+    if (rc) return rc;
+    GcsStatus local;
+    rc = gcsadmm_run(h, max_iters, st ? st : &local);
+    if (rc == 0 || rc == GCS_E_DIVERGED) {
+        int rc2 = gcsadmm_get_solution(h, x_v, z_v, y_v, z_e);
+        if (rc2 == 0 && (rho_seq || pri_seq || dual_seq)) { int n = gcsadmm_get_history(h, rho_seq, pri_seq, dual_seq, hist_cap); if (n < 0) rc2 = n; }
+        if (rc == 0) rc = rc2;
+    }
+    gcsadmm_destroy(h);
+    return rc;
+}
+
+// Evicts the L2 (126 MB on B200) by overwriting a scratch buffer larger than it, on the handle's stream.
+extern "C" int gcsadmm_flush_l2(GcsHandle *h, long long bytes) {
+    if (!h) return set_err(GCS_E_INVALID, "null handle%s", "");
+    CK(cudaSetDevice(h->device));
+    if (bytes <= 0) bytes = 256ll << 20;
+    if (!h->flush_buf || h->flush_bytes < (size_t)bytes) {
+        if (h->flush_buf) cudaFree(h->flush_buf);
+        h->flush_buf = nullptr;
+        CK(cudaMalloc(&h->flush_buf, (size_t)bytes));
+        h->flush_bytes = (size_t)bytes;
+    }
+    CK(cudaMemsetAsync(h->flush_buf, 0, (size_t)bytes, h->stream));
+    return 0;
+}

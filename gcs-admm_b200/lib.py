@@ -1,0 +1,248 @@
+"""ctypes binding of ``libgcsadmm.so`` (``include/gcsadmm.h``).
+
+There is no CPU fallback: if the shared library is missing it is built with nvcc; if that
+fails, or no CUDA device is present when a handle is created, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+EXPORTS = [
+    "gcsadmm_version", "gcsadmm_last_error", "gcsadmm_device_count", "gcsadmm_default_params",
+    "gcsadmm_create", "gcsadmm_destroy", "gcsadmm_set_stream", "gcsadmm_run", "gcsadmm_step",
+    "gcsadmm_get_status", "gcsadmm_vertex_update", "gcsadmm_edge_update", "gcsadmm_control",
+    "gcsadmm_sums_device_ptr", "gcsadmm_xc_device_ptr", "gcsadmm_get_history", "gcsadmm_get_solution",
+    "gcsadmm_get_state", "gcsadmm_set_state", "gcsadmm_time_steps", "gcsadmm_solve_host",
+    "gcsadmm_scratch_bytes", "gcsadmm_flush_l2",
+]
+
+
+class GcsGraph(C.Structure):
+    _fields_ = [("nV", C.c_int32), ("nE", C.c_int32), ("n", C.c_int32), ("nH_own", C.c_int32), ("nH_ghost", C.c_int32),
+                ("poly_off", C.c_void_p), ("polyA", C.c_void_p), ("polyb", C.c_void_p),
+                ("he_off", C.c_void_p), ("he_edge", C.c_void_p), ("he_flags", C.c_void_p),
+                ("edge_he_tail", C.c_void_p), ("edge_he_head", C.c_void_p), ("edge_counted", C.c_void_p),
+                ("vtype", C.c_void_p), ("cent", C.c_void_p),
+                ("n_x_global", C.c_int64), ("n_mu_global", C.c_int64)]
+
+
+class GcsParams(C.Structure):
+    _fields_ = [("rho0", C.c_double), ("tau_incr", C.c_double), ("tau_decr", C.c_double), ("nu", C.c_double),
+                ("frac", C.c_double), ("eps_abs", C.c_double), ("eps_rel", C.c_double), ("max_it", C.c_int32),
+                ("inner_tol", C.c_double), ("inner_max_iter", C.c_int32), ("check_every", C.c_int32),
+                ("abs_stop", C.c_int32), ("abs_tol", C.c_double)]
+
+
+class GcsStatus(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("diverged", C.c_int32),
+                ("inner_fail", C.c_int32), ("inner_iters", C.c_int64), ("rho", C.c_double), ("pri_res", C.c_double),
+                ("dual_res", C.c_double), ("eps_pri", C.c_double), ("eps_dual", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_LIB = None
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgcsadmm.so")
+
+
+def load():
+    """Load (building if needed) libgcsadmm.so.  Raises if it cannot be had."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        _build.build()
+    L = C.CDLL(path)
+    L.gcsadmm_version.restype = C.c_char_p
+    L.gcsadmm_last_error.restype = C.c_char_p
+    L.gcsadmm_default_params.argtypes = [C.POINTER(GcsParams)]
+    L.gcsadmm_default_params.restype = None
+    L.gcsadmm_create.argtypes = [C.POINTER(GcsGraph), C.POINTER(GcsParams), C.c_int, C.POINTER(C.c_void_p)]
+    L.gcsadmm_destroy.argtypes = [C.c_void_p]
+    L.gcsadmm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.gcsadmm_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(GcsStatus)]
+    L.gcsadmm_step.argtypes = [C.c_void_p, C.c_int]
+    L.gcsadmm_get_status.argtypes = [C.c_void_p, C.POINTER(GcsStatus)]
+    for f in ("gcsadmm_vertex_update", "gcsadmm_edge_update", "gcsadmm_control"):
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.gcsadmm_sums_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.gcsadmm_xc_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.gcsadmm_get_history.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.gcsadmm_get_solution.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gcsadmm_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.gcsadmm_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int]
+    L.gcsadmm_time_steps.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.gcsadmm_solve_host.argtypes = [C.POINTER(GcsGraph), C.POINTER(GcsParams), C.c_int, C.c_int, C.POINTER(GcsStatus),
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.gcsadmm_scratch_bytes.argtypes = [C.c_int, C.c_int]
+    L.gcsadmm_flush_l2.argtypes = [C.c_void_p, C.c_longlong]
+    _LIB = L
+    return L
+
+
+class GcsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libgcsadmm error {code}: {msg}")
+        self.code = code
+
+
+def _check(rc):
+    if rc < 0:
+        raise GcsError(rc, load().gcsadmm_last_error().decode())
+    return rc
+
+
+def default_params(**overrides):
+    p = GcsParams()
+    load().gcsadmm_default_params(C.byref(p))
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise TypeError(f"unknown ADMM parameter {k!r}")
+        setattr(p, k, v)
+    return p
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def graph_struct(g):
+    """``PackedGraph`` (or a partition's local view with the same attributes) -> (GcsGraph, keepalive)."""
+    keep = dict(
+        poly_off=np.ascontiguousarray(g.poly_off, np.int32), polyA=np.ascontiguousarray(g.polyA, np.float64),
+        polyb=np.ascontiguousarray(g.polyb, np.float64), he_off=np.ascontiguousarray(g.he_off, np.int32),
+        he_edge=np.ascontiguousarray(g.he_edge, np.int32), he_flags=np.ascontiguousarray(g.he_flags, np.uint8),
+        edge_he_tail=np.ascontiguousarray(g.edge_he_tail, np.int32),
+        edge_he_head=np.ascontiguousarray(g.edge_he_head, np.int32),
+        vtype=np.ascontiguousarray(g.vtype, np.uint8),
+        cent=np.ascontiguousarray(getattr(g, "cent", None) if getattr(g, "cent", None) is not None else g.interior_points(), np.float64),
+    )
+    ec = getattr(g, "edge_counted", None)
+    if ec is not None:
+        keep["edge_counted"] = np.ascontiguousarray(ec, np.uint8)
+    s = GcsGraph()
+    s.nV, s.nE, s.n = g.nV, g.nE, 2
+    s.nH_own = int(keep["he_off"][-1])
+    s.nH_ghost = int(getattr(g, "nH_ghost", 0))
+    for k in ("poly_off", "polyA", "polyb", "he_off", "he_edge", "he_flags", "edge_he_tail", "edge_he_head", "vtype", "cent"):
+        setattr(s, k, _ptr(keep[k]))
+    s.edge_counted = _ptr(keep.get("edge_counted"))
+    s.n_x_global = int(getattr(g, "n_x_global", 0))
+    s.n_mu_global = int(getattr(g, "n_mu_global", 0))
+    return s, keep
+
+
+class Solver:
+    """One device-resident problem (handle of ``gcsadmm_create``)."""
+
+    def __init__(self, g, device=0, **params):
+        L = load()
+        self.g = g
+        self.params = default_params(**params)
+        self._gs, self._keep = graph_struct(g)
+        h = C.c_void_p()
+        _check(L.gcsadmm_create(C.byref(self._gs), C.byref(self.params), int(device), C.byref(h)))
+        self._h = h
+        self.nHall = self._gs.nH_own + self._gs.nH_ghost
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().gcsadmm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_stream(self, stream_ptr):
+        _check(load().gcsadmm_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def run(self, max_iters=None):
+        st = GcsStatus()
+        _check(load().gcsadmm_run(self._h, int(max_iters or self.params.max_it), C.byref(st)))
+        return st.as_dict()
+
+    def step(self, k=1):
+        _check(load().gcsadmm_step(self._h, int(k)))
+
+    def status(self):
+        st = GcsStatus()
+        _check(load().gcsadmm_get_status(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def vertex_update(self):
+        _check(load().gcsadmm_vertex_update(self._h))
+
+    def edge_update(self):
+        _check(load().gcsadmm_edge_update(self._h))
+
+    def control(self):
+        _check(load().gcsadmm_control(self._h))
+
+    def sums_ptr(self):
+        p = C.c_void_p()
+        _check(load().gcsadmm_sums_device_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def xc_ptr(self):
+        p = C.c_void_p()
+        _check(load().gcsadmm_xc_device_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def history(self):
+        cap = self.params.max_it + 2
+        rho, pri, dual = np.zeros(cap), np.zeros(cap), np.zeros(cap)
+        n = _check(load().gcsadmm_get_history(self._h, _ptr(rho), _ptr(pri), _ptr(dual), cap))
+        return rho[:n].copy(), pri[:n].copy(), dual[:n].copy()
+
+    def solution(self):
+        nV, nE = self.g.nV, self.g.nE
+        x_v, z_v, y_v, z_e = np.zeros((nV, 4)), np.zeros((nV, 4)), np.zeros(nV), np.zeros((nE, 5))
+        _check(load().gcsadmm_get_solution(self._h, _ptr(x_v), _ptr(z_v), _ptr(y_v), _ptr(z_e)))
+        return x_v, z_v, y_v, z_e
+
+    def state(self):
+        xc, mu, z = np.zeros((self.nHall, 5)), np.zeros((self._gs.nH_own, 5)), np.zeros((self.g.nE, 5))
+        rho, it = C.c_double(), C.c_int()
+        _check(load().gcsadmm_get_state(self._h, _ptr(xc), _ptr(mu), _ptr(z), C.byref(rho), C.byref(it)))
+        return xc, mu, z, rho.value, it.value
+
+    def set_state(self, xc=None, mu=None, z=None, rho=1.0, it=0):
+        a = [None if x is None else np.ascontiguousarray(x, np.float64) for x in (xc, mu, z)]
+        _check(load().gcsadmm_set_state(self._h, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), float(rho), int(it)))
+
+    def flush_l2(self, nbytes=0):
+        _check(load().gcsadmm_flush_l2(self._h, int(nbytes)))
+
+    def time_steps(self, k, split=False):
+        tot, k1, ed = C.c_float(), C.c_float(), C.c_float()
+        _check(load().gcsadmm_time_steps(self._h, int(k), C.byref(tot), C.byref(k1) if split else None,
+                                         C.byref(ed) if split else None))
+        return tot.value, k1.value, ed.value
+
+
+def solve_host(g, device=0, max_iters=None, **params):
+    """create + run + copy back + destroy in one C call (host buffers in, host buffers out)."""
+    L = load()
+    p = default_params(**params)
+    gs, keep = graph_struct(g)
+    nV, nE = g.nV, g.nE
+    cap = p.max_it + 2
+    x_v, z_v, y_v, z_e = np.zeros((nV, 4)), np.zeros((nV, 4)), np.zeros(nV), np.zeros((nE, 5))
+    rho, pri, dual = np.zeros(cap), np.zeros(cap), np.zeros(cap)
+    st = GcsStatus()
+    _check(L.gcsadmm_solve_host(C.byref(gs), C.byref(p), int(device), int(max_iters or p.max_it), C.byref(st),
+                                _ptr(x_v), _ptr(z_v), _ptr(y_v), _ptr(z_e), _ptr(rho), _ptr(pri), _ptr(dual), cap))
+    n = st.iterations + 1
+    return dict(status=st.as_dict(), x_v=x_v, z_v=z_v, y_v=y_v, z_e=z_e, rho_seq=rho[:n].copy(),
+                pri_res_seq=pri[:n].copy(), dual_res_seq=dual[:n].copy())

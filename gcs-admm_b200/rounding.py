@@ -1,0 +1,140 @@
+"""Rounding of the relaxed flows to a path + the path-restricted convex program.
+
+Restates reference ``GCS_utils.py``: ``rounding`` (:92-181: up to M randomized depth-first
+walks from 's' that sample out-edges in proportion to y_e, at most N distinct paths, each scored
+by ``solve_convex_restriction``), ``solve_convex_restriction`` (:17-89) and ``compute_cost``
+(:184-211).  Drake's ``Solve`` is replaced by the small conic solver in ``conic.py``; vertices off
+the path are multiplied by y_v = 0 in the reference's program (:39, :54, :61), i.e. unconstrained
+with zero cost, and are reported as zeros (what the reference's stored runs show).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .conic import solve_conic_qp
+
+__all__ = ["compute_cost", "solve_convex_restriction", "rounding", "find_path_via_random_dfs"]
+
+
+def compute_cost(z_v_sol, y_e_sol):
+    """sum_v ||z_v[:n] - z_v[n:]|| + 1e-4 sum_e y_e   (reference ``GCS_utils.py:184-211``)."""
+    length = 0.0
+    for z in z_v_sol.values():
+        z = np.asarray(z, dtype=float)
+        h = z.shape[0] // 2
+        length += float(np.linalg.norm(z[:h] - z[h:]))
+    return length + 1e-4 * float(sum(y_e_sol.values()))
+
+
+def solve_convex_restriction(As, bs, n, V, E, y_v, y_e, verbose=False):
+    """Shortest piecewise-linear path through the regions with y_v = 1, joined along the edges with
+    y_e = 1 (reference ``GCS_utils.py:17-89``).  Returns (cost, x_v_sol, y_v) or (inf, None, None)."""
+    on = [v for v in V if y_v[v]]
+    if not on:
+        return float("inf"), None, None
+    idx = {v: 4 * i for i, v in enumerate(on)} if n == 2 else {v: 2 * n * i for i, v in enumerate(on)}
+    nx = 2 * n * len(on)
+    nvar = nx + len(on)                       # one epigraph variable per active vertex
+    rows, rhs = [], []
+    for v in on:                              # A_v x_{v,i} <= b_v   (:47-54)
+        A, b = np.asarray(As[v], float), np.asarray(bs[v], float)
+        for i in range(2):
+            for r in range(A.shape[0]):
+                row = np.zeros(nvar)
+                row[idx[v] + i * n: idx[v] + (i + 1) * n] = A[r]
+                rows.append(row)
+                rhs.append(b[r])
+    l = len(rows)
+    socs = []
+    for k, v in enumerate(on):                # (t_v ; x_v1 - x_v2) in SOC   (:36-41)
+        row = np.zeros(nvar); row[nx + k] = -1.0
+        rows.append(row); rhs.append(0.0)
+        for c in range(n):
+            row = np.zeros(nvar); row[idx[v] + c] = -1.0; row[idx[v] + n + c] = 1.0
+            rows.append(row); rhs.append(0.0)
+        socs.append(n + 1)
+    Erows, f = [], []
+    for e in E:                               # x_{v,2} = x_{w,1} on active edges   (:57-61)
+        if y_e.get(e, 0):
+            v, w = e
+            if not (y_v[v] and y_v[w]):
+                continue
+            for c in range(n):
+                row = np.zeros(nvar); row[idx[v] + n + c] = 1.0; row[idx[w] + c] = -1.0
+                Erows.append(row); f.append(0.0)
+    q = np.zeros(nvar); q[nx:] = 1.0
+    res = solve_conic_qp(None, q, np.array(rows), np.array(rhs), l, socs,
+                         np.array(Erows) if Erows else None, np.array(f) if Erows else None, tol=1e-9)
+    if res.status != "optimal" and max(res.pres, res.dres) > 1e-6:
+        if verbose:
+            print("Convex restriction solve failed.")
+        return float("inf"), None, None
+    x = res.u
+    x_v_sol = {v: (x[idx[v]: idx[v] + 2 * n].copy() if y_v[v] else np.zeros(2 * n)) for v in V}
+    cost = float(sum(np.linalg.norm(x_v_sol[v][:n] - x_v_sol[v][n:]) for v in on))
+    return cost, x_v_sol, y_v
+
+
+def find_path_via_random_dfs(y_e_sol, I_v_out, rand):
+    """One randomized walk (reference ``GCS_utils.py:109-146``): from 's', among out-edges with
+    y_e > 1e-15 to unvisited heads, sample one in proportion to y_e (``searchsorted(cumsum)``); a dead
+    end below the sampled child fails the whole level (no sibling retry), as in the reference."""
+    path, visited = ['s'], {'s'}
+
+    def dfs(cur):
+        if cur == 't':
+            return True
+        edges = [(a, w) for (a, w) in I_v_out.get(cur, []) if w not in visited and y_e_sol.get((a, w), 0) > 1e-15]
+        if not edges:
+            return False
+        probs = np.array([y_e_sol[e] for e in edges], dtype=float)
+        total = probs.sum()
+        if total < 1e-15:
+            return False
+        probs /= total
+        k = int(np.searchsorted(np.cumsum(probs), rand()))
+        k = min(k, len(edges) - 1)
+        nxt = edges[k][1]
+        visited.add(nxt)
+        path.append(nxt)
+        if dfs(nxt):
+            return True
+        visited.remove(nxt)
+        path.pop()
+        return False
+
+    return path if dfs('s') else None
+
+
+def rounding(y_e_sol, V, E, I_v_out, As, bs, n, N=5, M=20, solve_convex_restriction=solve_convex_restriction,
+             rng=None, return_path=False):
+    """Reference ``GCS_utils.py:92-181``.  ``rng``: None -> numpy's global generator like the reference
+    (unseeded); an int or ``np.random.Generator`` makes the walk reproducible.  Ties in cost keep the
+    first path found (``min`` semantics of the reference)."""
+    if rng is None:
+        rand = np.random.rand
+    else:
+        gen = np.random.default_rng(rng) if not isinstance(rng, np.random.Generator) else rng
+        rand = gen.random
+    distinct, cands = set(), []
+    for _ in range(M):
+        if len(cands) >= N:
+            break
+        p = find_path_via_random_dfs(y_e_sol, I_v_out, rand)
+        if p is None or tuple(p) in distinct:
+            continue
+        distinct.add(tuple(p))
+        y_v = {v: 0 for v in V}
+        for v in p:
+            y_v[v] = 1
+        y_e = {e: 0 for e in E}
+        for a, b in zip(p[:-1], p[1:]):
+            y_e[(a, b)] = 1
+        cost, x_v_sol, y_v_sol = solve_convex_restriction(As, bs, n, V, E, y_v, y_e)
+        if cost != float("inf"):
+            cands.append((cost, x_v_sol, y_v_sol, p))
+    if not cands:
+        print("Rounding failed to find any feasible paths.")
+        return (float("inf"), None, None, None) if return_path else (float("inf"), None, None)
+    best = min(cands, key=lambda c: c[0])
+    return best if return_path else best[:3]

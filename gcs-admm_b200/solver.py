@@ -1,0 +1,69 @@
+"""``solve(As, bs, n)`` — host mirror of the reference's ``admm_solver_v3.py`` script.
+
+The reference has no callable entry point (its loop runs at module level,
+``admm_solver_v3.py:621-775``); this function packages the same sequence:
+build graph (:53) -> ADMM loop on the GPU (:655-733) -> last iterates as dicts (:745-748)
+-> cost (:750) -> rounding (:759).  The graph is converted once to the half-edge CSR layout and
+every iteration runs in ``libgcsadmm.so``; there is no CPU path for the loop.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import lib
+from .graph import build_graph, pack_graph
+from .rounding import compute_cost, rounding
+
+__all__ = ["solve", "MAX_IT"]
+
+MAX_IT = 1000     # reference admm_solver_v3.py:651
+
+
+def solve(As, bs, n, *, device=0, max_it=MAX_IT, round_solution=True, seed=None, verbose=False,
+          graph=None, one_call=True, **params):
+    """Solve the convex relaxation of the GCS shortest-path problem by full-vertex-split ADMM.
+
+    Parameters mirror the reference's literals (``rho0, tau_incr, tau_decr, nu, frac, eps_abs,
+    eps_rel`` — ``admm_solver_v3.py:621-651``) plus ``inner_tol``/``inner_max_iter`` for the vertex
+    programs and ``abs_stop``/``abs_tol`` for the "residual < 1e-4" metric.
+
+    Returns a dict: cost (pre-rounding, what the reference pickles), final_cost, x_v_sol, y_v_sol,
+    z_v_sol, y_e_sol, x_v_rounded, y_v_rounded, path, iterations, converged, rho_seq, pri_res_seq,
+    dual_res_seq, solve_time, V, E.
+    """
+    if int(n) != 2:
+        raise ValueError("gcs-admm_b200 implements the 2-D case (n = 2), like all reference data")
+    if graph is None:
+        V, E, I_v_in, I_v_out = build_graph(As, bs)
+        g = pack_graph(As, bs, V, E)
+    else:
+        V, E, I_v_in, I_v_out, g = graph
+    t0 = time.perf_counter()
+    if one_call:
+        out = lib.solve_host(g, device=device, max_iters=max_it, max_it=max_it, **params)
+    else:
+        s = lib.Solver(g, device=device, max_it=max_it, **params)
+        st = s.run(max_it)
+        x_v, z_v, y_v, z_e = s.solution()
+        rho, pri, dual = s.history()
+        s.close()
+        out = dict(status=st, x_v=x_v, z_v=z_v, y_v=y_v, z_e=z_e, rho_seq=rho, pri_res_seq=pri, dual_res_seq=dual)
+    solve_time = time.perf_counter() - t0
+    st = out["status"]
+    if verbose:
+        print(f"it = {st['iterations']}/{max_it}, pri_res_seq[-1]={st['pri_res']}, dual_res_seq[-1]={st['dual_res']}")
+    x_v_sol = {v: out["x_v"][i].copy() for i, v in enumerate(V)}        # :745
+    y_v_sol = {v: float(out["y_v"][i]) for i, v in enumerate(V)}        # :746
+    y_e_sol = {e: float(out["z_e"][i, 4]) for i, e in enumerate(E)}     # :747
+    z_v_sol = {v: out["z_v"][i].copy() for i, v in enumerate(V)}        # :748
+    cost = compute_cost(z_v_sol, y_e_sol)                               # :750
+    res = dict(cost=cost, x_v_sol=x_v_sol, y_v_sol=y_v_sol, z_v_sol=z_v_sol, y_e_sol=y_e_sol,
+               iterations=int(st["iterations"]), converged=bool(st["converged"]), diverged=bool(st["diverged"]),
+               rho_seq=out["rho_seq"], pri_res_seq=out["pri_res_seq"], dual_res_seq=out["dual_res_seq"],
+               solve_time=solve_time, status=st, V=V, E=E, final_cost=None, x_v_rounded=None, y_v_rounded=None, path=None)
+    if round_solution:
+        fc, xr, yr, path = rounding(y_e_sol, V, E, I_v_out, As, bs, n, rng=seed, return_path=True)   # :759
+        res.update(final_cost=fc, x_v_rounded=xr, y_v_rounded=yr, path=path)
+    return res

@@ -1,0 +1,141 @@
+/*
+ * gcsadmm.h — C-ABI of libgcsadmm.so: the full-vertex-split ADMM iteration for shortest paths in
+ * graphs of convex sets, as hand-written CUDA for sm_100a (B200).
+ *
+ * Drop-in scope.  The reference (Michaelszeng/GCS-ADMM) has no function API or FFI: its hot path is
+ * the module-level loop of admm_solver_v3.py.  Each entry point below names the reference code it
+ * replaces (file:line relative to the reference repository):
+ *
+ *   gcsadmm_create        ConsensusManager.__init__ + build_A_B_c_consensus_matrices   admm_solver_v3.py:68-198, :340-349
+ *                         (variable/consensus bookkeeping; here: upload of the half-edge CSR layout)
+ *   gcsadmm_vertex_update parallel_vertex_update / vertex_update / SolveInParallel     admm_solver_v3.py:352-540
+ *   gcsadmm_edge_update   parallel_edge_update, dual_update, evaluate_*_residual,      admm_solver_v3.py:543-614, :690-713
+ *                         eps_pri, eps_dual, rho adaptation, stop test (fused)
+ *   gcsadmm_step / _run   the `while it <= MAX_IT` loop                                 admm_solver_v3.py:655-733
+ *   gcsadmm_get_history   rho_seq / pri_res_seq / dual_res_seq                          admm_solver_v3.py:637-639, :771-773
+ *   gcsadmm_get_solution  x_v_sol / y_v_sol / y_e_e_sol / z_v_sol slicing               admm_solver_v3.py:745-748
+ *   gcsadmm_solve_host    the whole loop from host buffers to host buffers (what solve() calls)
+ *
+ * Conventions: plain C types; the caller owns every host buffer; the library owns device memory.
+ * Every call returns 0 on success and a negative GCS_E_* code on failure (never throws, never
+ * aborts); gcsadmm_last_error() returns the message of the last failure on the calling thread.
+ * A handle is bound to one CUDA device and one stream and is not thread-safe; independent handles
+ * may be used from different threads.  All floating point data is IEEE fp64; n (the ambient
+ * dimension) must be 2.
+ *
+ * Data layout.  Vertices in the order of the reference's vertex list V; directed
+ * edges in the order of its edge list E; the half-edges of vertex v are he_off[v]..he_off[v+1] in
+ * the reference's per-vertex order I_v_in[v] + I_v_out[v] (admm_solver_v3.py:105-116).  Each
+ * half-edge h owns 5 consensus scalars, stored in edge-canonical order
+ * xc[h] = (copy of z_u^e[:2], copy of z_w^e[:2], copy of y_e) for e = (u, w); z[e] has the same order.
+ */
+#ifndef GCSADMM_H
+#define GCSADMM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCS_OK 0
+#define GCS_E_INVALID (-1)    /* bad argument / unsupported problem (n != 2, degree too large, ...) */
+#define GCS_E_CUDA (-2)       /* CUDA runtime error (message has the CUDA error string) */
+#define GCS_E_NOMEM (-3)
+#define GCS_E_DIVERGED (-4)   /* non-finite residuals (reference: "BREAKING FOR Divergence") */
+
+#define GCS_HE_FLAG_OUT 1     /* he_flags bit0: the owner is the edge's tail (outgoing half-edge) */
+#define GCS_HE_FLAG_ZERO 2    /* he_flags bit1: flow forced to zero by the presolve */
+
+typedef struct GcsHandle GcsHandle;
+
+typedef struct GcsGraph {
+    int32_t nV;                  /* local vertices */
+    int32_t nE;                  /* local directed edges (incident to a local vertex) */
+    int32_t n;                   /* ambient dimension, must be 2 */
+    int32_t nH_own;              /* half-edges owned by local vertices (== he_off[nV]) */
+    int32_t nH_ghost;            /* half-edge slots mirrored from another rank (0 on a single GPU) */
+    const int32_t *poly_off;     /* [nV+1] rows of polytope v are poly_off[v]..poly_off[v+1] */
+    const double *polyA;         /* [sum m][2] */
+    const double *polyb;         /* [sum m] */
+    const int32_t *he_off;       /* [nV+1] */
+    const int32_t *he_edge;      /* [nH_own] local edge id of each half-edge */
+    const uint8_t *he_flags;     /* [nH_own] GCS_HE_FLAG_* */
+    const int32_t *edge_he_tail; /* [nE] half-edge slot (own or ghost) of the edge at its tail */
+    const int32_t *edge_he_head; /* [nE] ... at its head */
+    const uint8_t *edge_counted; /* [nE] or NULL: 1 if this rank accounts the edge in the z-norms (all 1 when NULL) */
+    const uint8_t *vtype;        /* [nV] 0 generic, 1 source, 2 target, 3 no flow possible */
+    const double *cent;          /* [nV][2] a strictly interior point of each polytope */
+    int64_t n_x_global;          /* len(x_global) = 9|V| + 18|E| of the WHOLE graph (0: derive from nV, nE) */
+    int64_t n_mu_global;         /* len(mu_global) = 10|E| of the whole graph (0: derive) */
+} GcsGraph;
+
+typedef struct GcsParams {       /* literals of admm_solver_v3.py:621-651 */
+    double rho0;                 /* 1 */
+    double tau_incr, tau_decr;   /* 2, 2 */
+    double nu;                   /* 10 */
+    double frac;                 /* 0.1: rho adapts only while it < frac * max_it */
+    double eps_abs, eps_rel;     /* 1e-4, 1e-3 */
+    int32_t max_it;              /* 1000 */
+    double inner_tol;            /* interior-point tolerance of the vertex programs (1e-9) */
+    int32_t inner_max_iter;      /* 60 */
+    int32_t check_every;         /* host polls the stop flag every this many iterations (8) */
+    int32_t abs_stop;            /* 0: reference stop rule; 1: stop when max(pri, dual) < abs_tol */
+    double abs_tol;              /* 1e-4 (metric "time to residual 1e-4") */
+} GcsParams;
+
+typedef struct GcsStatus {
+    int32_t iterations;          /* `it` of the last executed pass */
+    int32_t converged;           /* reference `opt` */
+    int32_t diverged;
+    int32_t inner_fail;          /* vertex programs that ended above the noise-floor acceptance */
+    int64_t inner_iters;         /* interior-point iterations summed over all vertex programs */
+    double rho, pri_res, dual_res, eps_pri, eps_dual;
+} GcsStatus;
+
+const char *gcsadmm_version(void);
+const char *gcsadmm_last_error(void);
+int gcsadmm_device_count(void);
+void gcsadmm_default_params(GcsParams *p);
+
+int gcsadmm_create(const GcsGraph *g, const GcsParams *p, int device, GcsHandle **out);
+int gcsadmm_destroy(GcsHandle *h);
+/* run on an externally owned CUDA stream (e.g. torch's current stream); NULL restores the handle's own */
+int gcsadmm_set_stream(GcsHandle *h, void *cuda_stream);
+
+/* whole iterations */
+int gcsadmm_run(GcsHandle *h, int max_iters, GcsStatus *st);   /* until the stop rule fires or max_iters passes */
+int gcsadmm_step(GcsHandle *h, int k);                         /* exactly k passes, stop rule evaluated but ignored */
+int gcsadmm_get_status(GcsHandle *h, GcsStatus *st);
+
+/* the individual kernels (per-kernel parity tests, multi-GPU driver) */
+int gcsadmm_vertex_update(GcsHandle *h);                       /* K1 */
+int gcsadmm_edge_update(GcsHandle *h);                         /* K2-K4: z, mu, partial sums -> sums[8] on the device */
+int gcsadmm_control(GcsHandle *h);                             /* K5: consumes sums[8]: residuals, rho, stop, history */
+int gcsadmm_sums_device_ptr(GcsHandle *h, void **dev_ptr);     /* 8 doubles; all-reduce them between edge_update and control */
+int gcsadmm_xc_device_ptr(GcsHandle *h, void **dev_ptr);       /* [(nH_own + nH_ghost)][5] doubles (halo pack / unpack) */
+
+/* results */
+int gcsadmm_get_history(GcsHandle *h, double *rho_seq, double *pri_seq, double *dual_seq, int cap); /* returns count or <0 */
+int gcsadmm_get_solution(GcsHandle *h, double *x_v, double *z_v, double *y_v, double *z_e);         /* any may be NULL */
+int gcsadmm_get_state(GcsHandle *h, double *xc, double *mu, double *z, double *rho, int *it);
+int gcsadmm_set_state(GcsHandle *h, const double *xc, const double *mu, const double *z, double rho, int it);
+
+/* timing: k passes bracketed by CUDA events on the handle's stream; ms_k1 / ms_edge may be NULL */
+int gcsadmm_time_steps(GcsHandle *h, int k, float *ms_total, float *ms_k1, float *ms_edge);
+
+/* evicts L2 between timed iterations (bench hygiene): overwrites a scratch buffer of `bytes` (0: 256 MiB) */
+int gcsadmm_flush_l2(GcsHandle *h, long long bytes);
+
+/* one call from host buffers to host buffers: create, run, copy back, destroy */
+int gcsadmm_solve_host(const GcsGraph *g, const GcsParams *p, int device, int max_iters, GcsStatus *st,
+                       double *x_v, double *z_v, double *y_v, double *z_e,
+                       double *rho_seq, double *pri_seq, double *dual_seq, int hist_cap);
+
+/* bytes of shared memory one vertex program needs (diagnostics) */
+int gcsadmm_scratch_bytes(int max_live_degree, int max_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -59,7 +59,7 @@ def test_k1_matches_oracle_x_update(emu, name, its):
         xo, _, _ = o.state()
         _, zvo, yvo = o.solution()
         worst = max(worst, float(np.max(np.abs(xc - xo))))
-        assert np.max(np.abs(xc - xo)) < 1e-5, (name, it)   # both solves stop at ~1e-9 gap
+        assert np.max(np.abs(xc - xo)) < 5e-5, (name, it)   # both solves stop at ~1e-9 gap
         assert np.max(np.abs(z_v - zvo)) < 1e-4 and np.max(np.abs(y_v - yvo)) < 1e-4   # z_v holds weakly determined second points
         o.step(1)
     print(name, "max |xc_kernel - xc_oracle| =", worst)
