@@ -58,15 +58,15 @@ __device__ __forceinline__ double gcs_warp_min(double x) {
 #define GCS_UT 4
 #define GCS_UZ 5
 #define GCS_UYV 9
-#define GCS_EPP 16             // doubles per edge-point partial record
+#define GCS_EPP 9              // doubles per row-family record
 #define GCS_NB_GAMMA 1e-5      // width of the central-path neighbourhood
 #define GCS_LOQO_C 0.02        // weight of the centrality-aware floor on sigma
 
 // Scratch layout (offsets in doubles) of one warp, for <= dcap live half-edges and <= mcap polytope rows.
 struct GcsScratchLayout {
     int dcap, mcap, ncap, nucap, ldh;
-    int H, M, B, C, u, dua, du, gu, ru, Pu, qu, v, dv, rv, vbest, zr, dsr, dzr, zc, dsc, dzc, zy, dsy, dzy, sy;
-    int ep, cp, A, b, AA, tgt, ints, total;
+    int H, M, B, C, u, dua, du, gu, ru, Pu, qu, v, dv, rv, vbest, zr, dsr, dzr, zy, dsy, dzy, sy;
+    int ep, A, b, AA, tgt, ints, diag0, Linv, ytmp, total;
 };
 
 #if defined(__CUDACC__)
@@ -88,16 +88,14 @@ static inline GcsScratchLayout gcs_scratch_layout(int dcap, int mcap) {
     L.u = o; o += L.nucap;  L.dua = o; o += L.nucap;  L.du = o; o += L.nucap;
     L.gu = o; o += L.nucap; L.ru = o; o += L.nucap;  L.Pu = o; o += L.nucap;  L.qu = o; o += L.nucap;
     L.v = o; o += L.ncap;   L.dv = o; o += L.ncap;   L.rv = o; o += L.ncap;   L.vbest = o; o += L.ncap;
-    int nr = dcap * 2 * mcap * 2;
+    int nr = 4 * (dcap + 1) * mcap;            // one slot of mcap rows per family (block, point, kind); block dcap = core
     L.zr = o; o += nr;  L.dsr = o; o += nr;  L.dzr = o; o += nr;
-    int ncr = 2 * mcap * 2;
-    L.zc = o; o += ncr; L.dsc = o; o += ncr; L.dzc = o; o += ncr;
     L.zy = o; o += dcap + 1; L.dsy = o; o += dcap + 1; L.dzy = o; o += dcap + 1; L.sy = o; o += dcap + 1;
-    L.ep = o; o += GCS_EPP * 2 * dcap;
-    L.cp = o; o += 16;
+    L.ep = o; o += GCS_EPP * 4 * (dcap + 1);
     L.A = o; o += 2 * mcap; L.b = o; o += mcap; L.AA = o; o += 3 * mcap;
     L.tgt = o; o += 5 * dcap;
     L.ints = o; o += (3 * dcap + 1) / 2 + 1;   // int arrays out / prim / hid packed behind the doubles
+    L.diag0 = o; o += L.ncap; L.Linv = o; o += 15 * dcap; L.ytmp = o; o += L.ncap;
     L.total = o;
     return L;
 }
@@ -179,235 +177,124 @@ GCS_DEV void gcs_adjoint(const double *g, double *out, int d, int jstar, const i
     GCS_SYNC();
 }
 
-// H_u(a, b) from its structured pieces (a, b are u-space indices)
-GCS_DEV double gcs_hu(const double *M, const double *B, const double *C, int a, int b) {
-    if (a < GCS_NCORE && b < GCS_NCORE) return C[a * 10 + b];
-    if (a >= GCS_NCORE && b >= GCS_NCORE) {
-        int ja = (a - GCS_NCORE) / 5, jb = (b - GCS_NCORE) / 5;
-        if (ja != jb) return 0.0;
-        return M[25 * ja + 5 * (a - GCS_NCORE - 5 * ja) + (b - GCS_NCORE - 5 * jb)];
-    }
-    if (a > b) { int t = a; a = b; b = t; }   // a core, b block
-    if (a >= 4) return 0.0;                   // only x couples with the edge blocks (C4)
-    int jb = (b - GCS_NCORE) / 5;
-    return B[20 * jb + 5 * a + (b - GCS_NCORE - 5 * jb)];
-}
-// column p of N as up to three (u-index, coefficient) pairs; returns the count
-GCS_DEV int gcs_ncol(int p, int jstar, const int *prim, bool term, int *idx, double *cf) {
-    if (p < 4) {
-        idx[0] = GCS_UX + p; cf[0] = 1.0;
-        if (!term) return 1;
-        idx[1] = GCS_UZ + p; cf[1] = 1.0; idx[2] = gcs_uw(jstar) + p; cf[2] = 1.0;
-        return 3;
-    }
-    if (p == 4) { idx[0] = GCS_UT; cf[0] = 1.0; return 1; }
-    int jj = (p - 5) / 5, c = p - 5 - 5 * jj, j = jj < jstar ? jj : jj + 1;
-    idx[0] = gcs_uw(j) + c; cf[0] = 1.0;
-    idx[1] = gcs_uw(jstar) + c;
-    if (prim[j]) { cf[1] = -1.0; return 2; }
-    cf[1] = 1.0; idx[2] = GCS_UZ + c; cf[2] = 1.0;
-    return 3;
-}
+#ifdef GCS_EMULATE
+static inline double gcs_rcp(double x) { return 1.0 / x; }
+#else
+__device__ __forceinline__ double gcs_rcp(double x) { return __drcp_rn(x); }
+#endif
 
 // ---- one pass over the inequality rows ---------------------------------------------------------
-//   mode 0: Hessian pieces, gradient G'z into gout, gap (r1) and smallest complementarity product (r0)
-//   mode 1: predictor step ratio for direction dua (r0 = max(-ds/s, -dz/z))
-//   mode 2: corrector right-hand side  -G'(rc/s)  into gout        (rc uses dua and sigmu)
+// Every polytope row family has the form  s_k = h0 b_k - A_k . p  (k = 0..m-1):
+//   C3 (:434-436)  h0 = y_e^v      p = a_i             C1 (:420-422)  h0 = y_v      p = z_i
+//   C4 (:438-440)  h0 = 1 - y_e^v  p = x_i - a_i       C2 (:424-426)  h0 = 1 - y_v  p = x_i - z_i
+// One lane owns one family (block, point i, kind): 4 (d + 1) items (2 (d + 1) for 's'/'t', which have no
+// C2 / C4).  Each item leaves a record  [sum D AA'(3), sum D b A(2), sum D b^2, sum w A(2), sum w b]
+// (D = z/s; w = z in mode 0, rc/s in mode 2) that the assembly signs into M_j, B_j, C and the gradient.
+//   mode 0: records, gap (r1) and smallest complementarity product (r0); caches 1/s
+//   mode 1: predictor step ratio for direction dua (r0)
+//   mode 2: corrector right-hand side records (rc uses dua and sigmu)
 //   mode 3: corrector direction du: store ds, dz per row; r0 = max ratio
 //   mode 4: neighbourhood statistics for step alpha: r0 = min, r1 = sum of (s + a ds)(z + a dz)
 //   mode 5: z += alpha dz
-struct GcsRowsArgs { int mode; double sigmu, alpha; double *gout; };
+//   mode 6: initial slacks into the dual slots; r1 = their sum, r0 = their count
+struct GcsRowsArgs { int mode; double sigmu, alpha; };
+
+GCS_DEV int gcs_slot(int blk, int i, int fam) { return (blk * 2 + i) * 2 + fam; }
 
 GCS_DEV void gcs_rows(const GcsScratchLayout &L, double *S, int m, int d, bool term, const GcsRowsArgs &ar,
                       double &r0, double &r1, int lane) {
     const double *A = S + L.A, *b = S + L.b, *AA = S + L.AA;
     const double *u = S + L.u, *du = S + L.du, *dua = S + L.dua;
-    double *gout = ar.gout;
-    double acc_max = 0.0, acc_min = 1e300, acc_sum = 0.0;
+    double acc_max = 0.0, acc_min = 1e300, acc_sum = 0.0, acc_cnt = 0.0;
     const int mode = ar.mode;
     const bool need_p = (mode == 1 || mode == 2 || mode == 3), need_d = (mode == 3);
-    // ---- edge-point items (j, i): rows C3 (:434-436) and C4 (:438-440) of half-edge j, point i
-    GCS_LANE_LOOP(e, 2 * d) {
-        const int j = e >> 1, i = e & 1;
-        const int ao = gcs_uw(j) + 2 * i, yo = gcs_uw(j) + 4, xo = GCS_UX + 2 * i;
-        const double a0 = u[ao], a1 = u[ao + 1], y = u[yo], x0 = u[xo], x1 = u[xo + 1];
-        double da0 = 0, da1 = 0, dy = 0, dx0 = 0, dx1 = 0, pa0 = 0, pa1 = 0, py = 0, px0 = 0, px1 = 0;
-        if (need_d) { da0 = du[ao]; da1 = du[ao + 1]; dy = du[yo]; dx0 = du[xo]; dx1 = du[xo + 1]; }
-        if (need_p) { pa0 = dua[ao]; pa1 = dua[ao + 1]; py = dua[yo]; px0 = dua[xo]; px1 = dua[xo + 1]; }
-        double *zr = S + L.zr + e * m * 2, *dsr = S + L.dsr + e * m * 2, *dzr = S + L.dzr + e * m * 2;
-        double Maa0 = 0, Maa1 = 0, Maa2 = 0, May0 = 0, May1 = 0, Myy = 0, Bxa0 = 0, Bxa1 = 0, Bxa2 = 0, Bxy0 = 0, Bxy1 = 0;
-        double ga0 = 0, ga1 = 0, gy = 0, gx0 = 0, gx1 = 0;
+    const int nitems = term ? 2 * (d + 1) : 4 * (d + 1);
+    GCS_LANE_LOOP(it, nitems) {
+        int fam, i, blk;
+        if (term) { fam = 0; i = it & 1; blk = it >> 1; } else { fam = it & 1; i = (it >> 1) & 1; blk = it >> 2; }
+        const int po = (blk < d ? gcs_uw(blk) : GCS_UZ) + 2 * i, yo = blk < d ? gcs_uw(blk) + 4 : GCS_UYV, xo = GCS_UX + 2 * i;
+        const int slot = gcs_slot(blk, i, fam);
+        const double h0 = fam ? 1.0 - u[yo] : u[yo];
+        const double p0 = fam ? u[xo] - u[po] : u[po], p1 = fam ? u[xo + 1] - u[po + 1] : u[po + 1];
+        double ph = 0, pp0 = 0, pp1 = 0, dh = 0, dp0 = 0, dp1 = 0;
+        if (need_p) { ph = fam ? -dua[yo] : dua[yo]; pp0 = fam ? dua[xo] - dua[po] : dua[po]; pp1 = fam ? dua[xo + 1] - dua[po + 1] : dua[po + 1]; }
+        if (need_d) { dh = fam ? -du[yo] : du[yo]; dp0 = fam ? du[xo] - du[po] : du[po]; dp1 = fam ? du[xo + 1] - du[po + 1] : du[po + 1]; }
+        double *zr = S + L.zr + slot * m, *dsr = S + L.dsr + slot * m, *dzr = S + L.dzr + slot * m;
+        double s_aa0 = 0, s_aa1 = 0, s_aa2 = 0, s_ba0 = 0, s_ba1 = 0, s_bb = 0, w_a0 = 0, w_a1 = 0, w_b = 0;
         for (int k = 0; k < m; ++k) {
             const double A0 = A[2 * k], A1 = A[2 * k + 1], bk = b[k];
-            const double Aa = A0 * a0 + A1 * a1;
-            const double s3 = y * bk - Aa, z3 = zr[2 * k];
-            double s4 = 1.0, z4 = 0.0;
-            if (!term) { s4 = (1.0 - y) * bk - (A0 * x0 + A1 * x1) + Aa; z4 = zr[2 * k + 1]; }
+            const double sl = h0 * bk - (A0 * p0 + A1 * p1);
+            if (mode == 6) { zr[k] = sl; acc_sum += sl; acc_cnt += 1.0; continue; }
+            const double z = zr[k];
             if (mode == 0) {
-                const double D3 = z3 / s3, D4 = z4 / s4, Ds = D3 + D4;
-                Maa0 += Ds * AA[3 * k]; Maa1 += Ds * AA[3 * k + 1]; Maa2 += Ds * AA[3 * k + 2];
-                May0 -= Ds * bk * A0; May1 -= Ds * bk * A1; Myy += Ds * bk * bk;
-                Bxa0 -= D4 * AA[3 * k]; Bxa1 -= D4 * AA[3 * k + 1]; Bxa2 -= D4 * AA[3 * k + 2];
-                Bxy0 += D4 * bk * A0; Bxy1 += D4 * bk * A1;
-                const double zd = z3 - z4;
-                ga0 += A0 * zd; ga1 += A1 * zd; gy -= bk * zd; gx0 += A0 * z4; gx1 += A1 * z4;
-                const double p3 = s3 * z3;
-                acc_sum += p3; acc_min = fmin(acc_min, p3);
-                if (!term) { const double p4 = s4 * z4; acc_sum += p4; acc_min = fmin(acc_min, p4); }
+                const double rs = gcs_rcp(sl), D = z * rs;
+                dsr[k] = rs;                                  // cached 1/s for the other passes of this iteration
+                s_aa0 += D * AA[3 * k]; s_aa1 += D * AA[3 * k + 1]; s_aa2 += D * AA[3 * k + 2];
+                s_ba0 += D * bk * A0; s_ba1 += D * bk * A1; s_bb += D * bk * bk;
+                w_a0 += A0 * z; w_a1 += A1 * z; w_b += bk * z;
+                const double pr = sl * z;
+                acc_sum += pr; acc_min = fmin(acc_min, pr);
             } else if (need_p) {
-                // predictor quantities (rc = -s z):  ds = -g.dua,  dz = -z - z ds / s
-                const double pAa = A0 * pa0 + A1 * pa1;
-                const double ps3 = -(pAa - bk * py), ps4 = -((A0 * px0 + A1 * px1) - pAa + bk * py);
-                const double pz3 = -z3 - z3 * ps3 / s3, pz4 = -z4 - z4 * ps4 / s4;
+                const double rs = dsr[k];
+                const double ps = ph * bk - (A0 * pp0 + A1 * pp1);      // predictor ds
+                const double t = ps * rs;                                // ds / s
                 if (mode == 1) {
-                    acc_max = fmax(acc_max, fmax(-ps3 / s3, -pz3 / z3));
-                    if (!term) acc_max = fmax(acc_max, fmax(-ps4 / s4, -pz4 / z4));
+                    acc_max = fmax(acc_max, fmax(-t, 1.0 + t));          // -ds/s and -dz/z = 1 + ds/s  (dz = -z - z ds/s)
                 } else {
-                    const double rc3 = -s3 * z3 + ar.sigmu - ps3 * pz3, rc4 = -s4 * z4 + ar.sigmu - ps4 * pz4;
+                    const double pz = -z - z * t;
+                    const double rc = -sl * z + ar.sigmu - ps * pz;
                     if (mode == 2) {
-                        const double g3 = rc3 / s3, g4 = term ? 0.0 : rc4 / s4, gd = g3 - g4;
-                        ga0 -= A0 * gd; ga1 -= A1 * gd; gy += bk * gd; gx0 -= A0 * g4; gx1 -= A1 * g4;
+                        const double g = rc * rs;
+                        w_a0 += A0 * g; w_a1 += A1 * g; w_b += bk * g;
                     } else {
-                        const double dAa = A0 * da0 + A1 * da1;
-                        const double ds3 = -(dAa - bk * dy), dz3 = (rc3 - z3 * ds3) / s3;
-                        dsr[2 * k] = ds3; dzr[2 * k] = dz3;
-                        acc_max = fmax(acc_max, fmax(-ds3 / s3, -dz3 / z3));
-                        if (!term) {
-                            const double ds4 = -((A0 * dx0 + A1 * dx1) - dAa + bk * dy), dz4 = (rc4 - z4 * ds4) / s4;
-                            dsr[2 * k + 1] = ds4; dzr[2 * k + 1] = dz4;
-                            acc_max = fmax(acc_max, fmax(-ds4 / s4, -dz4 / z4));
-                        }
+                        const double ds = dh * bk - (A0 * dp0 + A1 * dp1);
+                        const double dz = (rc - z * ds) * rs;
+                        dsr[k] = ds; dzr[k] = dz;
+                        acc_max = fmax(acc_max, fmax(-ds * rs, -dz * gcs_rcp(z)));
                     }
                 }
             } else if (mode == 4) {
-                const double p3 = (s3 + ar.alpha * dsr[2 * k]) * (z3 + ar.alpha * dzr[2 * k]);
-                acc_sum += p3; acc_min = fmin(acc_min, p3);
-                if (!term) {
-                    const double p4 = (s4 + ar.alpha * dsr[2 * k + 1]) * (z4 + ar.alpha * dzr[2 * k + 1]);
-                    acc_sum += p4; acc_min = fmin(acc_min, p4);
-                }
+                const double pr = (sl + ar.alpha * dsr[k]) * (z + ar.alpha * dzr[k]);
+                acc_sum += pr; acc_min = fmin(acc_min, pr);
             } else {
-                zr[2 * k] = z3 + ar.alpha * dzr[2 * k];
-                if (!term) zr[2 * k + 1] = z4 + ar.alpha * dzr[2 * k + 1];
+                zr[k] = z + ar.alpha * dzr[k];
             }
         }
         if (mode == 0 || mode == 2) {
-            double *ep = S + L.ep + GCS_EPP * e;
-            if (mode == 0) {
-                ep[0] = Maa0; ep[1] = Maa1; ep[2] = Maa2; ep[3] = May0; ep[4] = May1; ep[5] = Myy;
-                ep[6] = Bxa0; ep[7] = Bxa1; ep[8] = Bxa2; ep[9] = Bxy0; ep[10] = Bxy1;
-            }
-            ep[11] = gy; ep[12] = gx0; ep[13] = gx1;
-            gout[ao] = ga0; gout[ao + 1] = ga1;          // exclusive slots
-        }
-    }
-    // ---- core items i: rows C1 (:420-422) and C2 (:424-426)
-    GCS_LANE_LOOP(i, 2) {
-        const int zo = GCS_UZ + 2 * i, xo = GCS_UX + 2 * i;
-        const double z0 = u[zo], z1 = u[zo + 1], yv = u[GCS_UYV], x0 = u[xo], x1 = u[xo + 1];
-        double dz0 = 0, dz1 = 0, dyv = 0, dx0 = 0, dx1 = 0, pz0 = 0, pz1 = 0, pyv = 0, px0 = 0, px1 = 0;
-        if (need_d) { dz0 = du[zo]; dz1 = du[zo + 1]; dyv = du[GCS_UYV]; dx0 = du[xo]; dx1 = du[xo + 1]; }
-        if (need_p) { pz0 = dua[zo]; pz1 = dua[zo + 1]; pyv = dua[GCS_UYV]; px0 = dua[xo]; px1 = dua[xo + 1]; }
-        double *zc = S + L.zc + i * m * 2, *dsc = S + L.dsc + i * m * 2, *dzc = S + L.dzc + i * m * 2;
-        double Zz0 = 0, Zz1 = 0, Zz2 = 0, Zy0 = 0, Zy1 = 0, Yy = 0, Xx0 = 0, Xx1 = 0, Xx2 = 0, Xy0 = 0, Xy1 = 0;
-        double gz0 = 0, gz1 = 0, gyv = 0, gx0 = 0, gx1 = 0;
-        for (int k = 0; k < m; ++k) {
-            const double A0 = A[2 * k], A1 = A[2 * k + 1], bk = b[k];
-            const double Az = A0 * z0 + A1 * z1;
-            const double s1 = yv * bk - Az, c1 = zc[2 * k];
-            double s2 = 1.0, c2 = 0.0;
-            if (!term) { s2 = (1.0 - yv) * bk - (A0 * x0 + A1 * x1) + Az; c2 = zc[2 * k + 1]; }
-            if (mode == 0) {
-                const double D1 = c1 / s1, D2 = c2 / s2, Ds = D1 + D2;
-                Zz0 += Ds * AA[3 * k]; Zz1 += Ds * AA[3 * k + 1]; Zz2 += Ds * AA[3 * k + 2];
-                Zy0 -= Ds * bk * A0; Zy1 -= Ds * bk * A1; Yy += Ds * bk * bk;
-                Xx0 += D2 * AA[3 * k]; Xx1 += D2 * AA[3 * k + 1]; Xx2 += D2 * AA[3 * k + 2];
-                Xy0 += D2 * bk * A0; Xy1 += D2 * bk * A1;
-                const double zd = c1 - c2;
-                gz0 += A0 * zd; gz1 += A1 * zd; gyv -= bk * zd; gx0 += A0 * c2; gx1 += A1 * c2;
-                const double p1 = s1 * c1;
-                acc_sum += p1; acc_min = fmin(acc_min, p1);
-                if (!term) { const double p2 = s2 * c2; acc_sum += p2; acc_min = fmin(acc_min, p2); }
-            } else if (need_p) {
-                const double pAz = A0 * pz0 + A1 * pz1;
-                const double ps1 = -(pAz - bk * pyv), ps2 = -((A0 * px0 + A1 * px1) - pAz + bk * pyv);
-                const double q1 = -c1 - c1 * ps1 / s1, q2 = -c2 - c2 * ps2 / s2;
-                if (mode == 1) {
-                    acc_max = fmax(acc_max, fmax(-ps1 / s1, -q1 / c1));
-                    if (!term) acc_max = fmax(acc_max, fmax(-ps2 / s2, -q2 / c2));
-                } else {
-                    const double rc1 = -s1 * c1 + ar.sigmu - ps1 * q1, rc2 = -s2 * c2 + ar.sigmu - ps2 * q2;
-                    if (mode == 2) {
-                        const double g1 = rc1 / s1, g2 = term ? 0.0 : rc2 / s2, gd = g1 - g2;
-                        gz0 -= A0 * gd; gz1 -= A1 * gd; gyv += bk * gd; gx0 -= A0 * g2; gx1 -= A1 * g2;
-                    } else {
-                        const double dAz = A0 * dz0 + A1 * dz1;
-                        const double ds1 = -(dAz - bk * dyv), dd1 = (rc1 - c1 * ds1) / s1;
-                        dsc[2 * k] = ds1; dzc[2 * k] = dd1;
-                        acc_max = fmax(acc_max, fmax(-ds1 / s1, -dd1 / c1));
-                        if (!term) {
-                            const double ds2 = -((A0 * dx0 + A1 * dx1) - dAz + bk * dyv), dd2 = (rc2 - c2 * ds2) / s2;
-                            dsc[2 * k + 1] = ds2; dzc[2 * k + 1] = dd2;
-                            acc_max = fmax(acc_max, fmax(-ds2 / s2, -dd2 / c2));
-                        }
-                    }
-                }
-            } else if (mode == 4) {
-                const double p1 = (s1 + ar.alpha * dsc[2 * k]) * (c1 + ar.alpha * dzc[2 * k]);
-                acc_sum += p1; acc_min = fmin(acc_min, p1);
-                if (!term) {
-                    const double p2 = (s2 + ar.alpha * dsc[2 * k + 1]) * (c2 + ar.alpha * dzc[2 * k + 1]);
-                    acc_sum += p2; acc_min = fmin(acc_min, p2);
-                }
-            } else {
-                zc[2 * k] = c1 + ar.alpha * dzc[2 * k];
-                if (!term) zc[2 * k + 1] = c2 + ar.alpha * dzc[2 * k + 1];
-            }
-        }
-        if (mode == 0) {   // point-exclusive entries of C (zero-filled by the caller)
-            double *c0 = S + L.C;
-            const int X = GCS_UX + 2 * i, Z = GCS_UZ + 2 * i, Y = GCS_UYV;
-            c0[Z * 10 + Z] = Zz0; c0[Z * 10 + Z + 1] = Zz1; c0[(Z + 1) * 10 + Z] = Zz1; c0[(Z + 1) * 10 + Z + 1] = Zz2;
-            c0[Z * 10 + Y] = Zy0; c0[Y * 10 + Z] = Zy0; c0[(Z + 1) * 10 + Y] = Zy1; c0[Y * 10 + Z + 1] = Zy1;
-            c0[X * 10 + X] = Xx0; c0[X * 10 + X + 1] = Xx1; c0[(X + 1) * 10 + X] = Xx1; c0[(X + 1) * 10 + X + 1] = Xx2;
-            c0[X * 10 + Y] = Xy0; c0[Y * 10 + X] = Xy0; c0[(X + 1) * 10 + Y] = Xy1; c0[Y * 10 + X + 1] = Xy1;
-            c0[X * 10 + Z] = -Xx0; c0[X * 10 + Z + 1] = -Xx1; c0[(X + 1) * 10 + Z] = -Xx1; c0[(X + 1) * 10 + Z + 1] = -Xx2;
-            c0[Z * 10 + X] = -Xx0; c0[(Z + 1) * 10 + X] = -Xx1; c0[Z * 10 + X + 1] = -Xx1; c0[(Z + 1) * 10 + X + 1] = -Xx2;
-        }
-        if (mode == 0 || mode == 2) {
-            gout[zo] = gz0; gout[zo + 1] = gz1;           // exclusive
-            double *cp = S + L.cp + 8 * i;
-            cp[0] = Yy; cp[1] = gyv; cp[2] = gx0; cp[3] = gx1;
+            double *rec = S + L.ep + GCS_EPP * slot;
+            if (mode == 0) { rec[0] = s_aa0; rec[1] = s_aa1; rec[2] = s_aa2; rec[3] = s_ba0; rec[4] = s_ba1; rec[5] = s_bb; }
+            rec[6] = w_a0; rec[7] = w_a1; rec[8] = w_b;
         }
     }
     // ---- singles: y_e >= 0 (:377) and y_v <= 1 (:366)
     GCS_LANE_LOOP(j, d + 1) {
-        if (j == d && term) continue;
+        double *zy = S + L.zy, *dsy = S + L.dsy, *dzy = S + L.dzy, *sy = S + L.sy;
+        if (j == d && term) { if (mode == 0 || mode == 2) sy[j] = 0.0; if (mode == 0) dsy[j] = 0.0; continue; }
         const int yo = j < d ? gcs_uw(j) + 4 : GCS_UYV;
         const double sgn = j < d ? 1.0 : -1.0;           // s = y   or   s = 1 - y_v ;  row g = -sgn on y
-        const double s = j < d ? u[yo] : 1.0 - u[yo];
-        double *zy = S + L.zy, *dsy = S + L.dsy, *dzy = S + L.dzy, *sy = S + L.sy;
+        const double sl = j < d ? u[yo] : 1.0 - u[yo];
+        if (mode == 6) { zy[j] = sl; acc_sum += sl; acc_cnt += 1.0; continue; }
         const double z = zy[j];
         if (mode == 0) {
-            const double p = s * z;
-            acc_sum += p; acc_min = fmin(acc_min, p);
-            dsy[j] = z / s;          // D, consumed by the assembly
+            const double pr = sl * z;
+            acc_sum += pr; acc_min = fmin(acc_min, pr);
+            dsy[j] = z / sl;         // D, consumed by the assembly
             sy[j] = -sgn * z;        // G'z contribution
         } else if (need_p) {
-            const double ps = sgn * dua[yo], pz = -z - z * ps / s;
-            if (mode == 1) acc_max = fmax(acc_max, fmax(-ps / s, -pz / z));
+            const double ps = sgn * dua[yo], pz = -z - z * ps / sl;
+            if (mode == 1) acc_max = fmax(acc_max, fmax(-ps / sl, -pz / z));
             else {
-                const double rc = -s * z + ar.sigmu - ps * pz;
-                if (mode == 2) sy[j] = sgn * rc / s;     // -G'(rc/s)
+                const double rc = -sl * z + ar.sigmu - ps * pz;
+                if (mode == 2) sy[j] = sgn * rc / sl;     // -G'(rc/s)
                 else {
-                    const double ds = sgn * du[yo], dz = (rc - z * ds) / s;
+                    const double ds = sgn * du[yo], dz = (rc - z * ds) / sl;
                     dsy[j] = ds; dzy[j] = dz;
-                    acc_max = fmax(acc_max, fmax(-ds / s, -dz / z));
+                    acc_max = fmax(acc_max, fmax(-ds / sl, -dz / z));
                 }
             }
         } else if (mode == 4) {
-            const double p = (s + ar.alpha * dsy[j]) * (z + ar.alpha * dzy[j]);
-            acc_sum += p; acc_min = fmin(acc_min, p);
+            const double pr = (sl + ar.alpha * dsy[j]) * (z + ar.alpha * dzy[j]);
+            acc_sum += pr; acc_min = fmin(acc_min, pr);
         } else {
             zy[j] = z + ar.alpha * dzy[j];
         }
@@ -415,65 +302,147 @@ GCS_DEV void gcs_rows(const GcsScratchLayout &L, double *S, int m, int d, bool t
     GCS_SYNC();
     if (mode == 1 || mode == 3) r0 = gcs_warp_max(acc_max);
     if (mode == 0 || mode == 4) { r0 = gcs_warp_min(acc_min); r1 = gcs_warp_sum(acc_sum); }
+    if (mode == 6) { r0 = gcs_warp_sum(acc_cnt); r1 = gcs_warp_sum(acc_sum); }
 }
 
-// folds the shared gradient slots (y_j, x_i, y_v) written as partials by gcs_rows (modes 0 / 2)
-GCS_DEV void gcs_fold(const GcsScratchLayout &L, double *S, int d, bool term, double *gout, int lane) {
-    const double *ep = S + L.ep, *cp = S + L.cp, *sy = S + L.sy;
-    GCS_LANE_LOOP(j, d) gout[gcs_uw(j) + 4] = ep[GCS_EPP * (2 * j) + 11] + ep[GCS_EPP * (2 * j + 1) + 11] + sy[j];
+// gradient-like vector from the records:  gout = sign * G'w (+ the singles' signed terms)
+//   a_i / z_i slots:  wA(C3|C1) - wA(C4|C2);   y / y_v slots:  -wb(C3|C1) + wb(C4|C2);   x_i: sum over blocks of wA(C4|C2)
+GCS_DEV void gcs_fold(const GcsScratchLayout &L, double *S, int d, bool term, double *gout, double sign, int lane) {
+    const double *ep = S + L.ep, *sy = S + L.sy;
+    GCS_LANE_LOOP(q, 4 * (d + 1)) {
+        const int blk = q >> 2, i = (q >> 1) & 1, c = q & 1;
+        const double *r3 = ep + GCS_EPP * gcs_slot(blk, i, 0);
+        const double v = r3[6 + c] - (term ? 0.0 : r3[GCS_EPP + 6 + c]);
+        gout[(blk < d ? gcs_uw(blk) : GCS_UZ) + 2 * i + c] = sign * v;
+    }
+    GCS_LANE_LOOP(blk, d + 1) {
+        const double *r = ep + GCS_EPP * gcs_slot(blk, 0, 0);
+        double v = -(r[8] + r[2 * GCS_EPP + 8]);
+        if (!term) v += r[GCS_EPP + 8] + r[3 * GCS_EPP + 8];
+        gout[blk < d ? gcs_uw(blk) + 4 : GCS_UYV] = sign * v + sy[blk];
+    }
     GCS_LANE_LOOP(q, 4) {
-        int i = q >> 1, c = q & 1;
-        double s = cp[8 * i + 2 + c];
-        for (int j = 0; j < d; ++j) s += ep[GCS_EPP * (2 * j + i) + 12 + c];
-        gout[GCS_UX + q] = s;
+        const int i = q >> 1, c = q & 1;
+        double v = 0.0;
+        if (!term) for (int blk = 0; blk <= d; ++blk) v += ep[GCS_EPP * gcs_slot(blk, i, 1) + 6 + c];
+        gout[GCS_UX + q] = sign * v;
     }
-    if (lane == 0) {
-        gout[GCS_UYV] = cp[1] + cp[8 + 1] + (term ? 0.0 : sy[d]);
-        gout[GCS_UT] = 0.0;
-    }
+    if (lane == 0) gout[GCS_UT] = 0.0;
     GCS_SYNC();
 }
 
-// in-place Cholesky of the n x n matrix H (row stride ldh, lower triangle) with pivot lifting:
-// a pivot that falls below the rounding noise of its own cancellation is lifted to that level.
-GCS_DEV void gcs_cholesky(double *H, int n, int ldh, double *piv, int lane) {
-    for (int j = 0; j < n; ++j) {
-        GCS_LANE_LOOP(i, n - j) {
-            const int r = j + i;
-            const double *hr = H + r * ldh, *hj = H + j * ldh;
-            double s = 0.0;
-            for (int k = 0; k < j; ++k) s += hr[k] * hj[k];
-            if (i == 0) {
-                double d0 = hr[j], dd = d0 - s, noise = 64.0 * 2.2e-16 * (fabs(d0) + s) + 1e-300;
-                if (!(dd > noise)) dd = noise;
-                piv[0] = sqrt(dd);
-            } else {
-                H[r * ldh + j] = hr[j] - s;
+#ifdef GCS_EMULATE
+static inline double gcs_rsqrt(double x) { return 1.0 / sqrt(x); }
+#else
+__device__ __forceinline__ double gcs_rsqrt(double x) { return rsqrt(x); }
+#endif
+
+// In-place blocked Cholesky (block size 5 = one half-edge block) of the n x n matrix H, n = 5 nb,
+// row stride ldh, lower triangle.  Pivot lifting: a pivot that falls below the rounding noise of its
+// own cancellation is lifted to that level (diag0 holds the diagonal before elimination).
+// Linv[b] receives the inverse of the b-th diagonal Cholesky block (15 doubles, row-major lower).
+GCS_DEV void gcs_cholesky(double *H, int nb, int ldh, const double *diag0, double *Linv, int lane) {
+    const int n = 5 * nb;
+    for (int b = 0; b < nb; ++b) {
+        const int o = 5 * b;
+        // (1) every lane factors the 5x5 diagonal block redundantly in registers
+        double l[15], li[15];
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) l[r * (r + 1) / 2 + c] = H[(o + r) * ldh + o + c];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const double d0 = diag0[o + j];
+            double dd = l[j * (j + 1) / 2 + j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) dd -= l[j * (j + 1) / 2 + k] * l[j * (j + 1) / 2 + k];
+            const double noise = 64.0 * 2.2e-16 * (fabs(d0) + fabs(d0 - dd)) + 1e-300;
+            if (!(dd > noise)) dd = noise;
+            const double rs = gcs_rsqrt(dd);
+            l[j * (j + 1) / 2 + j] = dd * rs;
+            li[j * (j + 1) / 2 + j] = rs;
+#pragma unroll
+            for (int r = j + 1; r < 5; ++r) {
+                double v = l[r * (r + 1) / 2 + j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) v -= l[r * (r + 1) / 2 + k] * l[j * (j + 1) / 2 + k];
+                l[r * (r + 1) / 2 + j] = v * rs;
             }
         }
+        // inverse of the lower-triangular block
+#pragma unroll
+        for (int c = 0; c < 5; ++c)
+#pragma unroll
+            for (int r = c + 1; r < 5; ++r) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = c; k < r; ++k) v -= l[r * (r + 1) / 2 + k] * li[k * (k + 1) / 2 + c];
+                li[r * (r + 1) / 2 + c] = v * li[r * (r + 1) / 2 + r];
+            }
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < 5; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) { H[(o + r) * ldh + o + c] = l[r * (r + 1) / 2 + c]; Linv[15 * b + r * (r + 1) / 2 + c] = li[r * (r + 1) / 2 + c]; }
+        }
+        // (2) panel: rows below the block,  L_panel = H_panel L_bb^-T
+        const int rem = n - o - 5;
+        GCS_LANE_LOOP(i, rem) {
+            double *hr = H + (o + 5 + i) * ldh + o;
+            const double x0 = hr[0], x1 = hr[1], x2 = hr[2], x3 = hr[3], x4 = hr[4];
+            hr[0] = x0 * li[0];
+            hr[1] = x0 * li[1] + x1 * li[2];
+            hr[2] = x0 * li[3] + x1 * li[4] + x2 * li[5];
+            hr[3] = x0 * li[6] + x1 * li[7] + x2 * li[8] + x3 * li[9];
+            hr[4] = x0 * li[10] + x1 * li[11] + x2 * li[12] + x3 * li[13] + x4 * li[14];
+        }
         GCS_SYNC();
-        const double sd = piv[0];
-        GCS_LANE_LOOP(i, n - j) {
-            const int r = j + i;
-            if (i == 0) H[r * ldh + j] = sd; else H[r * ldh + j] /= sd;
+        // (3) trailing update; long rows first so the last partial round holds the short ones
+        GCS_LANE_LOOP(i, rem) {
+            const int r = n - 1 - i;
+            const double *pr = H + r * ldh + o;
+            const double p0 = pr[0], p1 = pr[1], p2 = pr[2], p3 = pr[3], p4 = pr[4];
+            double *hrow = H + r * ldh;
+            for (int k = o + 5; k <= r; ++k) {
+                const double *pk = H + k * ldh + o;
+                hrow[k] -= p0 * pk[0] + p1 * pk[1] + p2 * pk[2] + p3 * pk[3] + p4 * pk[4];
+            }
         }
         GCS_SYNC();
     }
 }
-// x <- (L L')^-1 x
-GCS_DEV void gcs_chol_solve(const double *H, int n, int ldh, double *x, int lane) {
-    for (int j = 0; j < n; ++j) {
-        const double xj = x[j] / H[j * ldh + j];
-        GCS_SYNC();
-        if (lane == 0) x[j] = xj;
-        GCS_LANE_LOOP(i, n - j - 1) { const int r = j + 1 + i; x[r] -= H[r * ldh + j] * xj; }
+// x <- (L L')^-1 x   (y: scratch of n doubles)
+GCS_DEV void gcs_chol_solve(const double *H, int nb, int ldh, const double *Linv, double *x, double *y, int lane) {
+    const int n = 5 * nb;
+    for (int b = 0; b < nb; ++b) {          // forward: L y = x
+        const int o = 5 * b;
+        const double *li = Linv + 15 * b;
+        const double x0 = x[o], x1 = x[o + 1], x2 = x[o + 2], x3 = x[o + 3], x4 = x[o + 4];
+        const double y0 = x0 * li[0], y1 = x0 * li[1] + x1 * li[2], y2 = x0 * li[3] + x1 * li[4] + x2 * li[5];
+        const double y3 = x0 * li[6] + x1 * li[7] + x2 * li[8] + x3 * li[9];
+        const double y4 = x0 * li[10] + x1 * li[11] + x2 * li[12] + x3 * li[13] + x4 * li[14];
+        if (lane == 0) { y[o] = y0; y[o + 1] = y1; y[o + 2] = y2; y[o + 3] = y3; y[o + 4] = y4; }
+        GCS_LANE_LOOP(i, n - o - 5) {
+            const int r = o + 5 + i;
+            const double *hr = H + r * ldh + o;
+            x[r] -= hr[0] * y0 + hr[1] * y1 + hr[2] * y2 + hr[3] * y3 + hr[4] * y4;
+        }
         GCS_SYNC();
     }
-    for (int j = n - 1; j >= 0; --j) {
-        const double xj = x[j] / H[j * ldh + j];
-        GCS_SYNC();
-        if (lane == 0) x[j] = xj;
-        GCS_LANE_LOOP(r, j) x[r] -= H[j * ldh + r] * xj;
+    for (int b = nb - 1; b >= 0; --b) {     // backward: L' x = y
+        const int o = 5 * b;
+        const double *li = Linv + 15 * b;
+        const double y0 = y[o], y1 = y[o + 1], y2 = y[o + 2], y3 = y[o + 3], y4 = y[o + 4];
+        const double x4 = y4 * li[14];
+        const double x3 = y3 * li[9] + y4 * li[13];
+        const double x2 = y2 * li[5] + y3 * li[8] + y4 * li[12];
+        const double x1 = y1 * li[2] + y2 * li[4] + y3 * li[7] + y4 * li[11];
+        const double x0 = y0 * li[0] + y1 * li[1] + y2 * li[3] + y3 * li[6] + y4 * li[10];
+        if (lane == 0) { x[o] = x0; x[o + 1] = x1; x[o + 2] = x2; x[o + 3] = x3; x[o + 4] = x4; }
+        GCS_LANE_LOOP(q, o) {
+            y[q] -= H[o * ldh + q] * x0 + H[(o + 1) * ldh + q] * x1 + H[(o + 2) * ldh + q] * x2 + H[(o + 3) * ldh + q] * x3 + H[(o + 4) * ldh + q] * x4;
+        }
         GCS_SYNC();
     }
 }
@@ -522,42 +491,11 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
     // slacks -> centred duals  z = mu0 / s  with mu0 = mean slack
     double zq[3], sq[3];
     {
-        double part = 0.0; int cnt = 0;
-        GCS_LANE_LOOP(e, 2 * d) {
-            const int j = e >> 1, i = e & 1, ao = gcs_uw(j) + 2 * i, xo = GCS_UX + 2 * i;
-            const double y = u[gcs_uw(j) + 4];
-            double *zr = S + L.zr + e * m * 2;
-            for (int k = 0; k < m; ++k) {
-                const double Aa = A[2 * k] * u[ao] + A[2 * k + 1] * u[ao + 1];
-                const double s3 = y * b[k] - Aa;
-                zr[2 * k] = s3; part += s3; cnt++;
-                if (!term) { const double s4 = (1.0 - y) * b[k] - (A[2 * k] * u[xo] + A[2 * k + 1] * u[xo + 1]) + Aa; zr[2 * k + 1] = s4; part += s4; cnt++; }
-                else zr[2 * k + 1] = 1.0;
-            }
-        }
-        GCS_LANE_LOOP(i, 2) {
-            const int zo = GCS_UZ + 2 * i, xo = GCS_UX + 2 * i;
-            double *zc = S + L.zc + i * m * 2;
-            for (int k = 0; k < m; ++k) {
-                const double Az = A[2 * k] * u[zo] + A[2 * k + 1] * u[zo + 1];
-                const double s1 = u[GCS_UYV] * b[k] - Az;
-                zc[2 * k] = s1; part += s1; cnt++;
-                if (!term) { const double s2 = (1.0 - u[GCS_UYV]) * b[k] - (A[2 * k] * u[xo] + A[2 * k + 1] * u[xo + 1]) + Az; zc[2 * k + 1] = s2; part += s2; cnt++; }
-                else zc[2 * k + 1] = 1.0;
-            }
-        }
-        GCS_LANE_LOOP(j, d + 1) {
-            double *zy = S + L.zy;
-            if (j < d) { zy[j] = u[gcs_uw(j) + 4]; part += zy[j]; cnt++; }
-            else if (!term) { zy[j] = 1.0 - u[GCS_UYV]; part += zy[j]; cnt++; }
-            else zy[j] = 1.0;
-        }
-        GCS_SYNC();
-        const double tot = gcs_warp_sum(part), nrows = gcs_warp_sum((double)cnt);
-        const double mu0 = tot / nrows;
-        GCS_LANE_LOOP(q, 2 * d * m * 2) { double *zr = S + L.zr; zr[q] = mu0 / zr[q]; }
-        GCS_LANE_LOOP(q, 2 * m * 2) { double *zc = S + L.zc; zc[q] = mu0 / zc[q]; }
-        GCS_LANE_LOOP(j, d + 1) { double *zy = S + L.zy; zy[j] = mu0 / zy[j]; }
+        double cnt = 0.0, tot = 0.0;
+        { GcsRowsArgs ar; ar.mode = 6; ar.sigmu = 0; ar.alpha = 0; gcs_rows(L, S, m, d, term, ar, cnt, tot, lane); }
+        const double mu0 = tot / cnt;
+        GCS_LANE_LOOP(q, 4 * (d + 1) * m) { double *zr = S + L.zr; zr[q] = mu0 / zr[q]; }
+        GCS_LANE_LOOP(j, d + 1) { double *zy = S + L.zy; if (!(j == d && term)) zy[j] = mu0 / zy[j]; }
         sq[0] = u[GCS_UT]; sq[1] = u[GCS_UZ] - u[GCS_UZ + 2]; sq[2] = u[GCS_UZ + 1] - u[GCS_UZ + 3];
         const double det = gcs_jnorm2(sq[0], sq[1], sq[2]);
         zq[0] = mu0 * sq[0] / det; zq[1] = -mu0 * sq[1] / det; zq[2] = -mu0 * sq[2] / det;
@@ -583,8 +521,8 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
         GCS_LANE_LOOP(q, 100) C[q] = 0.0;
         GCS_SYNC();
         double minprod = 0.0, gap = 0.0;
-        { GcsRowsArgs ar; ar.mode = 0; ar.sigmu = 0; ar.alpha = 0; ar.gout = gu; gcs_rows(L, S, m, d, term, ar, minprod, gap, lane); }
-        gcs_fold(L, S, d, term, gu, lane);
+        { GcsRowsArgs ar; ar.mode = 0; ar.sigmu = 0; ar.alpha = 0; gcs_rows(L, S, m, d, term, ar, minprod, gap, lane); }
+        gcs_fold(L, S, d, term, gu, 1.0, lane);
         sq[0] = u[GCS_UT]; sq[1] = u[GCS_UZ] - u[GCS_UZ + 2]; sq[2] = u[GCS_UZ + 1] - u[GCS_UZ + 3];
         const double pq0 = sq[0] * zq[0] + sq[1] * zq[1] + sq[2] * zq[2];
         gap += pq0; minprod = fmin(minprod, pq0);
@@ -616,30 +554,48 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
         const double mu = gap / deg;
         GcsNT nt; gcs_nt_build(nt, sq, zq);
 
-        // ---- assemble the blocks of H_u ---------------------------------------------------------
-        GCS_LANE_LOOP(j, d) {
-            const double *e0 = S + L.ep + GCS_EPP * (2 * j), *e1 = e0 + GCS_EPP;
-            double *Mj = M + 25 * j, *Bj = B + 20 * j;
-            const int o = gcs_uw(j);
-            for (int q = 0; q < 25; ++q) Mj[q] = 0.0;
-            for (int q = 0; q < 20; ++q) Bj[q] = 0.0;
-            Mj[0] = e0[0] + Pu[o]; Mj[1] = Mj[5] = e0[1]; Mj[6] = e0[2] + Pu[o + 1];
-            Mj[12] = e1[0] + Pu[o + 2]; Mj[13] = Mj[17] = e1[1]; Mj[18] = e1[2] + Pu[o + 3];
-            Mj[4] = Mj[20] = e0[3]; Mj[9] = Mj[21] = e0[4]; Mj[14] = Mj[22] = e1[3]; Mj[19] = Mj[23] = e1[4];
-            Mj[24] = e0[5] + e1[5] + Pu[o + 4] + S[L.dsy + j];
-            // B_j: rows x(4), cols w_j(5):  x_i - a_i : Bxa (sym 2x2),  x_i - y : Bxy
-            Bj[0] = e0[6]; Bj[1] = e0[7]; Bj[5] = e0[7]; Bj[6] = e0[8]; Bj[4] = e0[9]; Bj[9] = e0[10];
-            Bj[12] = e1[6]; Bj[13] = e1[7]; Bj[17] = e1[7]; Bj[18] = e1[8]; Bj[14] = e1[9]; Bj[19] = e1[10];
+        // ---- assemble the blocks of H_u from the family records ---------------------------------
+        // block (a_i | z_i, y | y_v) gets  +S_AA, -S_bA, +S_bb  from both kinds; the x_i coupling comes from C4 | C2 only
+        GCS_LANE_LOOP(blk, d + 1) {
+            const double *r03 = S + L.ep + GCS_EPP * gcs_slot(blk, 0, 0), *r04 = r03 + GCS_EPP, *r13 = r03 + 2 * GCS_EPP, *r14 = r03 + 3 * GCS_EPP;
+            double aa0[3], aa1[3], ay0[2], ay1[2], yy, xa0[3], xa1[3], xy0[2], xy1[2];
+            for (int q = 0; q < 3; ++q) { aa0[q] = r03[q] + (term ? 0.0 : r04[q]); aa1[q] = r13[q] + (term ? 0.0 : r14[q]); xa0[q] = term ? 0.0 : -r04[q]; xa1[q] = term ? 0.0 : -r14[q]; }
+            for (int q = 0; q < 2; ++q) { ay0[q] = -(r03[3 + q] + (term ? 0.0 : r04[3 + q])); ay1[q] = -(r13[3 + q] + (term ? 0.0 : r14[3 + q])); xy0[q] = term ? 0.0 : r04[3 + q]; xy1[q] = term ? 0.0 : r14[3 + q]; }
+            yy = r03[5] + r13[5] + (term ? 0.0 : r04[5] + r14[5]) + S[L.dsy + blk];
+            if (blk < d) {
+                double *Mj = M + 25 * blk, *Bj = B + 20 * blk;
+                const int o = gcs_uw(blk);
+                for (int q = 0; q < 25; ++q) Mj[q] = 0.0;
+                for (int q = 0; q < 20; ++q) Bj[q] = 0.0;
+                Mj[0] = aa0[0] + Pu[o]; Mj[1] = Mj[5] = aa0[1]; Mj[6] = aa0[2] + Pu[o + 1];
+                Mj[12] = aa1[0] + Pu[o + 2]; Mj[13] = Mj[17] = aa1[1]; Mj[18] = aa1[2] + Pu[o + 3];
+                Mj[4] = Mj[20] = ay0[0]; Mj[9] = Mj[21] = ay0[1]; Mj[14] = Mj[22] = ay1[0]; Mj[19] = Mj[23] = ay1[1];
+                Mj[24] = yy + Pu[o + 4];
+                Bj[0] = xa0[0]; Bj[1] = xa0[1]; Bj[5] = xa0[1]; Bj[6] = xa0[2]; Bj[4] = xy0[0]; Bj[9] = xy0[1];
+                Bj[12] = xa1[0]; Bj[13] = xa1[1]; Bj[17] = xa1[1]; Bj[18] = xa1[2]; Bj[14] = xy1[0]; Bj[19] = xy1[1];
+            } else {    // core block: z_i plays a_i, y_v plays y
+                const int Z = GCS_UZ, Y = GCS_UYV, X = GCS_UX;
+                C[Z * 10 + Z] = aa0[0]; C[Z * 10 + Z + 1] = C[(Z + 1) * 10 + Z] = aa0[1]; C[(Z + 1) * 10 + Z + 1] = aa0[2];
+                C[(Z + 2) * 10 + Z + 2] = aa1[0]; C[(Z + 2) * 10 + Z + 3] = C[(Z + 3) * 10 + Z + 2] = aa1[1]; C[(Z + 3) * 10 + Z + 3] = aa1[2];
+                C[Z * 10 + Y] = C[Y * 10 + Z] = ay0[0]; C[(Z + 1) * 10 + Y] = C[Y * 10 + Z + 1] = ay0[1];
+                C[(Z + 2) * 10 + Y] = C[Y * 10 + Z + 2] = ay1[0]; C[(Z + 3) * 10 + Y] = C[Y * 10 + Z + 3] = ay1[1];
+                C[Y * 10 + Y] = yy;
+                C[X * 10 + Z] = C[Z * 10 + X] = xa0[0]; C[X * 10 + Z + 1] = C[(Z + 1) * 10 + X] = xa0[1];
+                C[(X + 1) * 10 + Z] = C[Z * 10 + X + 1] = xa0[1]; C[(X + 1) * 10 + Z + 1] = C[(Z + 1) * 10 + X + 1] = xa0[2];
+                C[(X + 2) * 10 + Z + 2] = C[(Z + 2) * 10 + X + 2] = xa1[0]; C[(X + 2) * 10 + Z + 3] = C[(Z + 3) * 10 + X + 2] = xa1[1];
+                C[(X + 3) * 10 + Z + 2] = C[(Z + 2) * 10 + X + 3] = xa1[1]; C[(X + 3) * 10 + Z + 3] = C[(Z + 3) * 10 + X + 3] = xa1[2];
+                C[X * 10 + Y] = C[Y * 10 + X] = xy0[0]; C[(X + 1) * 10 + Y] = C[Y * 10 + X + 1] = xy0[1];
+                C[(X + 2) * 10 + Y] = C[Y * 10 + X + 2] = xy1[0]; C[(X + 3) * 10 + Y] = C[Y * 10 + X + 3] = xy1[1];
+            }
         }
-        GCS_LANE_LOOP(i, 2) {     // x_i x_i gets every C4 row of point i:  sum_j D4 A A' = - sum_j Bxa
+        GCS_LANE_LOOP(i, 2) {     // x_i x_i collects every C4 | C2 family of point i:  sum D AA'
             const int X = GCS_UX + 2 * i;
             double s0 = 0, s1 = 0, s2 = 0;
-            for (int j = 0; j < d; ++j) { const double *e = S + L.ep + GCS_EPP * (2 * j + i); s0 -= e[6]; s1 -= e[7]; s2 -= e[8]; }
-            C[X * 10 + X] += s0; C[X * 10 + X + 1] += s1; C[(X + 1) * 10 + X] += s1; C[(X + 1) * 10 + X + 1] += s2;
+            if (!term) for (int blk = 0; blk <= d; ++blk) { const double *r = S + L.ep + GCS_EPP * gcs_slot(blk, i, 1); s0 += r[0]; s1 += r[1]; s2 += r[2]; }
+            C[X * 10 + X] = s0; C[X * 10 + X + 1] = s1; C[(X + 1) * 10 + X] = s1; C[(X + 1) * 10 + X + 1] = s2;
         }
         GCS_SYNC();
         if (lane == 0) {
-            C[GCS_UYV * 10 + GCS_UYV] = S[L.cp + 0] + S[L.cp + 8] + (term ? 0.0 : S[L.dsy + d]);
             // second-order cone block  B' W^-2 B  on (t, z1 - z2); a few ulps of its trace keep it PSD
             double Wi2[3][3];
             for (int c = 0; c < 3; ++c) {
@@ -658,27 +614,58 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
                 }
         }
         GCS_SYNC();
-        // ---- H_v = N' H_u N (lower triangle), then factor ------------------------------------
-        GCS_LANE_LOOP(idx, n * n) {
-            const int p = idx / n, q = idx - p * n;
-            if (q > p) continue;
-            int ip[3], iq[3]; double cp_[3], cq_[3];
-            const int np_ = gcs_ncol(p, jstar, prim, term, ip, cp_), nq_ = gcs_ncol(q, jstar, prim, term, iq, cq_);
-            double s = 0.0;
-            for (int a = 0; a < np_; ++a) for (int c = 0; c < nq_; ++c) s += cp_[a] * cq_[c] * gcs_hu(M, B, C, ip[a], iq[c]);
-            H[p * ldh + q] = s + (p == q ? 1e-14 : 0.0);
+        // ---- H_v = N' H_u N (lower triangle) from the structured pieces, then factor ----------
+        //   w_j rows/cols:  delta_jk M_j + cs_j cs_k M_* + cz_j cz_k C_zz        (cs = -1 primary, +1 secondary; cz = secondary)
+        //   x cols        :  B_j + cs_j B_* + cz_j C_xz (+ cs_j M_* for 's'/'t', where x also feeds z and w_*)
+        //   t col         :  cz_j C_tz
+        {
+            const double *Ms = M + 25 * jstar, *Bs = B + 20 * jstar;
+            for (int jj = 0; jj < d - 1; ++jj) {
+                const int j = jj < jstar ? jj : jj + 1;
+                const double csj = prim[j] ? -1.0 : 1.0, czj = prim[j] ? 0.0 : 1.0;
+                GCS_LANE_LOOP(e, 25 * (jj + 1)) {
+                    const int kk = e / 25, ab = e - 25 * kk, a = ab / 5, c = ab - 5 * a;
+                    const int k = kk < jstar ? kk : kk + 1;
+                    const double csk = prim[k] ? -1.0 : 1.0, czk = prim[k] ? 0.0 : 1.0;
+                    double sv = csj * csk * Ms[5 * a + c] + czj * czk * C[(GCS_UZ + a) * 10 + GCS_UZ + c];
+                    if (kk == jj) sv += M[25 * j + 5 * a + c] + (a == c ? 1e-14 : 0.0);
+                    H[(5 + 5 * jj + a) * ldh + 5 + 5 * kk + c] = sv;
+                }
+            }
+            GCS_LANE_LOOP(e, 25 * (d - 1)) {
+                const int r = e / 5, c = e - 5 * r, jj = r / 5, a = r - 5 * jj, j = jj < jstar ? jj : jj + 1;
+                const double csj = prim[j] ? -1.0 : 1.0, czj = prim[j] ? 0.0 : 1.0;
+                double sv;
+                if (c < 4) sv = B[20 * j + 5 * c + a] + csj * Bs[5 * c + a] + czj * C[c * 10 + GCS_UZ + a] + (term ? csj * Ms[5 * a + c] : 0.0);
+                else sv = czj * C[GCS_UT * 10 + GCS_UZ + a];
+                H[(5 + r) * ldh + c] = sv;
+            }
+            GCS_LANE_LOOP(e, 25) {
+                const int p = e / 5, q = e - 5 * p;
+                if (q <= p) {
+                    double sv;
+                    if (p < 4) {
+                        sv = C[p * 10 + q];
+                        if (term) sv += C[p * 10 + GCS_UZ + q] + C[(GCS_UZ + p) * 10 + q] + C[(GCS_UZ + p) * 10 + GCS_UZ + q] + Ms[5 * p + q] + Bs[5 * p + q] + Bs[5 * q + p];
+                    } else if (q < 4) sv = C[GCS_UT * 10 + q] + (term ? C[GCS_UT * 10 + GCS_UZ + q] : 0.0);
+                    else sv = C[GCS_UT * 10 + GCS_UT];
+                    H[p * ldh + q] = sv + (p == q ? 1e-14 : 0.0);
+                }
+            }
+            GCS_SYNC();
+            GCS_LANE_LOOP(q, n) S[L.diag0 + q] = H[q * ldh + q];
+            GCS_SYNC();
         }
-        GCS_SYNC();
-        gcs_cholesky(H, n, ldh, S + L.cp + 4, lane);
+        gcs_cholesky(H, d, ldh, S + L.diag0, S + L.Linv, lane);
 
         // ---- predictor:  rhs = -N'(P u + q) -----------------------------------------------------
         GCS_LANE_LOOP(q, nu) ru[q] = -(Pu[q] * u[q] + qu[q]);
         GCS_SYNC();
         gcs_adjoint(ru, dv, d, jstar, prim, term, lane);
-        gcs_chol_solve(H, n, ldh, dv, lane);
+        gcs_chol_solve(H, d, ldh, S + L.Linv, dv, S + L.ytmp, lane);
         gcs_forward(dv, dua, d, jstar, prim, term, false, lane);
         double tmax = 0.0, dummy = 0.0;
-        { GcsRowsArgs ar; ar.mode = 1; ar.sigmu = 0; ar.alpha = 0; ar.gout = 0; gcs_rows(L, S, m, d, term, ar, tmax, dummy, lane); }
+        { GcsRowsArgs ar; ar.mode = 1; ar.sigmu = 0; ar.alpha = 0; gcs_rows(L, S, m, d, term, ar, tmax, dummy, lane); }
         double dsq_a[3], dzq_a[3];
         gcs_nt_apply(nt, dua[GCS_UT], dua[GCS_UZ] - dua[GCS_UZ + 2], dua[GCS_UZ + 1] - dua[GCS_UZ + 3], true, dsq_a[0], dsq_a[1], dsq_a[2]);
         dzq_a[0] = -nt.l0 - dsq_a[0]; dzq_a[1] = -nt.l1 - dsq_a[1]; dzq_a[2] = -nt.l2 - dsq_a[2];
@@ -690,8 +677,8 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
             sigma = fmax(sigma, GCS_LOQO_C * c * c * c);
         }
         // ---- corrector --------------------------------------------------------------------------
-        { GcsRowsArgs ar; ar.mode = 2; ar.sigmu = sigma * mu; ar.alpha = 0; ar.gout = ru; gcs_rows(L, S, m, d, term, ar, dummy, dummy, lane); }
-        gcs_fold(L, S, d, term, ru, lane);
+        { GcsRowsArgs ar; ar.mode = 2; ar.sigmu = sigma * mu; ar.alpha = 0; gcs_rows(L, S, m, d, term, ar, dummy, dummy, lane); }
+        gcs_fold(L, S, d, term, ru, -1.0, lane);
         double tq[3];
         {
             double dsoc[3];
@@ -713,9 +700,9 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
             GCS_SYNC();
         }
         gcs_adjoint(ru, dv, d, jstar, prim, term, lane);
-        gcs_chol_solve(H, n, ldh, dv, lane);
+        gcs_chol_solve(H, d, ldh, S + L.Linv, dv, S + L.ytmp, lane);
         gcs_forward(dv, du, d, jstar, prim, term, false, lane);
-        { GcsRowsArgs ar; ar.mode = 3; ar.sigmu = sigma * mu; ar.alpha = 0; ar.gout = 0; gcs_rows(L, S, m, d, term, ar, tmax, dummy, lane); }
+        { GcsRowsArgs ar; ar.mode = 3; ar.sigmu = sigma * mu; ar.alpha = 0; gcs_rows(L, S, m, d, term, ar, tmax, dummy, lane); }
         double dsq_s[3], dzq_s[3];
         gcs_nt_apply(nt, du[GCS_UT], du[GCS_UZ] - du[GCS_UZ + 2], du[GCS_UZ + 1] - du[GCS_UZ + 3], true, dsq_s[0], dsq_s[1], dsq_s[2]);
         dzq_s[0] = tq[0] - dsq_s[0]; dzq_s[1] = tq[1] - dsq_s[1]; dzq_s[2] = tq[2] - dsq_s[2];
@@ -726,7 +713,7 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
         gcs_nt_apply(nt, dsq_s[0], dsq_s[1], dsq_s[2], false, dsq[0], dsq[1], dsq[2]);
         for (int bt = 0; bt < 30; ++bt) {    // wide-neighbourhood safeguard
             double mn = 0.0, sum = 0.0;
-            { GcsRowsArgs ar; ar.mode = 4; ar.sigmu = 0; ar.alpha = alpha; ar.gout = 0; gcs_rows(L, S, m, d, term, ar, mn, sum, lane); }
+            { GcsRowsArgs ar; ar.mode = 4; ar.sigmu = 0; ar.alpha = alpha; gcs_rows(L, S, m, d, term, ar, mn, sum, lane); }
             double pq = 0.0;
             for (int k = 0; k < 3; ++k) pq += (sq[k] + alpha * dsq[k]) * (zq[k] + alpha * dzq[k]);
             sum += pq; mn = fmin(mn, pq);
@@ -740,7 +727,7 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
             if (bad > 0.0 || !(alpha == alpha)) { res.status = 2; break; }
         }
         GCS_LANE_LOOP(q, n) v[q] += alpha * dv[q];
-        { GcsRowsArgs ar; ar.mode = 5; ar.sigmu = 0; ar.alpha = alpha; ar.gout = 0; gcs_rows(L, S, m, d, term, ar, dummy, dummy, lane); }
+        { GcsRowsArgs ar; ar.mode = 5; ar.sigmu = 0; ar.alpha = alpha; gcs_rows(L, S, m, d, term, ar, dummy, dummy, lane); }
         zq[0] += alpha * dzq[0]; zq[1] += alpha * dzq[1]; zq[2] += alpha * dzq[2];
         GCS_SYNC();
         gcs_forward(v, u, d, jstar, prim, term, true, lane);
