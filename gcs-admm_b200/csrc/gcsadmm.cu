@@ -18,7 +18,7 @@
 #include "vertex_update.cuh"
 
 #define GCS_VERSION "gcsadmm 0.1.0 (sm_100a)"
-#define K1_MAX_WARPS 8   // 254 registers/thread: 8 warps fill the register file of one SM
+#define K1_MAX_WARPS 12  // __launch_bounds__(320): <= 204 registers/thread, 10 warps fill the register file of one SM
 #define EDGE_THREADS 256
 #define NSUMS 8   // r2, dz2, x2, z2, mu2(pre-scale), nonfinite, spare, spare
 
@@ -273,13 +273,11 @@ extern "C" int gcsadmm_create(const GcsGraph *g, const GcsParams *p, int device,
             return set_err(GCS_E_INVALID, "vertex program too large for shared memory (max live degree / polytope rows too high)%s", "");
         }
         if (w > K1_MAX_WARPS) w = K1_MAX_WARPS;
-        // prefer two resident blocks per SM when that keeps more warps in flight
-        const int w2 = (int)((prop.sharedMemPerMultiprocessor / 2 - 1024) / per_warp);
-        if (w2 >= 2 && 2 * (w2 > K1_MAX_WARPS / 2 ? K1_MAX_WARPS / 2 : w2) >= w) w = w2 > K1_MAX_WARPS / 2 ? K1_MAX_WARPS / 2 : w2;
         h->k1_warps = w;
         h->k1_smem = (int)(w * per_warp);
     }
     CK(cudaFuncSetAttribute(vertex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k1_smem));
+    CK(cudaFuncSetAttribute(vertex_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     h->k1_blocks = (g->nV + h->k1_warps - 1) / h->k1_warps;
     int eb = (g->nE + EDGE_THREADS - 1) / EDGE_THREADS;
     int cap = prop.multiProcessorCount * 8;

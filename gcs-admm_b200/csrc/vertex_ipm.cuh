@@ -61,12 +61,13 @@ __device__ __forceinline__ double gcs_warp_min(double x) {
 #define GCS_EPP 9              // doubles per row-family record
 #define GCS_NB_GAMMA 1e-5      // width of the central-path neighbourhood
 #define GCS_LOQO_C 0.02        // weight of the centrality-aware floor on sigma
+#define GCS_QN 21               // doubles per compact Hessian block: aa0(3) aa1(3) ay0(2) ay1(2) yy xa0(3) xa1(3) xy0(2) xy1(2)
 
 // Scratch layout (offsets in doubles) of one warp, for <= dcap live half-edges and <= mcap polytope rows.
 struct GcsScratchLayout {
-    int dcap, mcap, ncap, nucap, ldh;
-    int H, M, B, C, u, dua, du, gu, ru, Pu, qu, v, dv, rv, vbest, zr, dsr, dzr, zy, dsy, dzy, sy;
-    int ep, A, b, AA, tgt, ints, diag0, Linv, ytmp, total;
+    int dcap, mcap, ncap, nucap;
+    int H, C, u, gu, Pu, qu, dua, du, ru, dv, rv, ytmp, Q, v, vbest, zr, wr, zy, dsy, dzy, sy;
+    int ep, A, b, AA, tgt, ints, diag0, Linv, total;
 };
 
 #if defined(__CUDACC__)
@@ -79,23 +80,23 @@ static inline GcsScratchLayout gcs_scratch_layout(int dcap, int mcap) {
     L.dcap = dcap; L.mcap = mcap;
     L.ncap = 5 * dcap;            // v-space: 5 + 5 (d - 1)
     L.nucap = GCS_NCORE + 5 * dcap;
-    L.ldh = L.ncap | 1;           // odd row stride: fewer shared-memory bank conflicts
     int o = 0;
-    L.H = o; o += L.ncap * L.ldh;
-    L.M = o; o += 25 * dcap;
-    L.B = o; o += 20 * dcap;
+    L.H = o; o += L.ncap * (L.ncap + 1) / 2;     // packed lower triangle, row r starts at r (r + 1) / 2
     L.C = o; o += 100;
-    L.u = o; o += L.nucap;  L.dua = o; o += L.nucap;  L.du = o; o += L.nucap;
-    L.gu = o; o += L.nucap; L.ru = o; o += L.nucap;  L.Pu = o; o += L.nucap;  L.qu = o; o += L.nucap;
-    L.v = o; o += L.ncap;   L.dv = o; o += L.ncap;   L.rv = o; o += L.ncap;   L.vbest = o; o += L.ncap;
+    L.u = o; o += L.nucap;  L.gu = o; o += L.nucap;  L.Pu = o; o += L.nucap;  L.qu = o; o += L.nucap;
+    // direction / right-hand-side vectors; between the residual check and the factorisation they are
+    // free and hold Q, the compact Hessian blocks (21 doubles per half-edge block)
+    L.dua = o; L.Q = o; o += L.nucap;  L.du = o; o += L.nucap;  L.ru = o; o += L.nucap;
+    L.dv = o; o += L.ncap;   L.rv = o; o += L.ncap;   L.ytmp = o; o += L.ncap;
+    L.v = o; o += L.ncap;    L.vbest = o; o += L.ncap;
     int nr = 4 * (dcap + 1) * mcap;            // one slot of mcap rows per family (block, point, kind); block dcap = core
-    L.zr = o; o += nr;  L.dsr = o; o += nr;  L.dzr = o; o += nr;
+    L.zr = o; o += nr;  L.wr = o; o += nr;      // duals; work array (1/s, then dz)
     L.zy = o; o += dcap + 1; L.dsy = o; o += dcap + 1; L.dzy = o; o += dcap + 1; L.sy = o; o += dcap + 1;
     L.ep = o; o += GCS_EPP * 4 * (dcap + 1);
     L.A = o; o += 2 * mcap; L.b = o; o += mcap; L.AA = o; o += 3 * mcap;
     L.tgt = o; o += 5 * dcap;
     L.ints = o; o += (3 * dcap + 1) / 2 + 1;   // int arrays out / prim / hid packed behind the doubles
-    L.diag0 = o; o += L.ncap; L.Linv = o; o += 15 * dcap; L.ytmp = o; o += L.ncap;
+    L.diag0 = o; o += L.ncap; L.Linv = o; o += 15 * dcap;
     L.total = o;
     return L;
 }
@@ -207,7 +208,7 @@ GCS_DEV void gcs_rows(const GcsScratchLayout &L, double *S, int m, int d, bool t
     const double *u = S + L.u, *du = S + L.du, *dua = S + L.dua;
     double acc_max = 0.0, acc_min = 1e300, acc_sum = 0.0, acc_cnt = 0.0;
     const int mode = ar.mode;
-    const bool need_p = (mode == 1 || mode == 2 || mode == 3), need_d = (mode == 3);
+    const bool need_p = (mode == 1 || mode == 2 || mode == 3), need_d = (mode == 3 || mode == 4);
     const int nitems = term ? 2 * (d + 1) : 4 * (d + 1);
     GCS_LANE_LOOP(it, nitems) {
         int fam, i, blk;
@@ -219,7 +220,7 @@ GCS_DEV void gcs_rows(const GcsScratchLayout &L, double *S, int m, int d, bool t
         double ph = 0, pp0 = 0, pp1 = 0, dh = 0, dp0 = 0, dp1 = 0;
         if (need_p) { ph = fam ? -dua[yo] : dua[yo]; pp0 = fam ? dua[xo] - dua[po] : dua[po]; pp1 = fam ? dua[xo + 1] - dua[po + 1] : dua[po + 1]; }
         if (need_d) { dh = fam ? -du[yo] : du[yo]; dp0 = fam ? du[xo] - du[po] : du[po]; dp1 = fam ? du[xo + 1] - du[po + 1] : du[po + 1]; }
-        double *zr = S + L.zr + slot * m, *dsr = S + L.dsr + slot * m, *dzr = S + L.dzr + slot * m;
+        double *zr = S + L.zr + slot * m, *wr = S + L.wr + slot * m;
         double s_aa0 = 0, s_aa1 = 0, s_aa2 = 0, s_ba0 = 0, s_ba1 = 0, s_bb = 0, w_a0 = 0, w_a1 = 0, w_b = 0;
         for (int k = 0; k < m; ++k) {
             const double A0 = A[2 * k], A1 = A[2 * k + 1], bk = b[k];
@@ -228,14 +229,14 @@ GCS_DEV void gcs_rows(const GcsScratchLayout &L, double *S, int m, int d, bool t
             const double z = zr[k];
             if (mode == 0) {
                 const double rs = gcs_rcp(sl), D = z * rs;
-                dsr[k] = rs;                                  // cached 1/s for the other passes of this iteration
+                wr[k] = rs;                                   // cached 1/s for the other passes of this iteration
                 s_aa0 += D * AA[3 * k]; s_aa1 += D * AA[3 * k + 1]; s_aa2 += D * AA[3 * k + 2];
                 s_ba0 += D * bk * A0; s_ba1 += D * bk * A1; s_bb += D * bk * bk;
                 w_a0 += A0 * z; w_a1 += A1 * z; w_b += bk * z;
                 const double pr = sl * z;
                 acc_sum += pr; acc_min = fmin(acc_min, pr);
             } else if (need_p) {
-                const double rs = dsr[k];
+                const double rs = wr[k];
                 const double ps = ph * bk - (A0 * pp0 + A1 * pp1);      // predictor ds
                 const double t = ps * rs;                                // ds / s
                 if (mode == 1) {
@@ -249,15 +250,16 @@ GCS_DEV void gcs_rows(const GcsScratchLayout &L, double *S, int m, int d, bool t
                     } else {
                         const double ds = dh * bk - (A0 * dp0 + A1 * dp1);
                         const double dz = (rc - z * ds) * rs;
-                        dsr[k] = ds; dzr[k] = dz;
+                        wr[k] = dz;                           // 1/s is not needed after this pass
                         acc_max = fmax(acc_max, fmax(-ds * rs, -dz * gcs_rcp(z)));
                     }
                 }
             } else if (mode == 4) {
-                const double pr = (sl + ar.alpha * dsr[k]) * (z + ar.alpha * dzr[k]);
+                const double ds = dh * bk - (A0 * dp0 + A1 * dp1);
+                const double pr = (sl + ar.alpha * ds) * (z + ar.alpha * wr[k]);
                 acc_sum += pr; acc_min = fmin(acc_min, pr);
             } else {
-                zr[k] = z + ar.alpha * dzr[k];
+                zr[k] = z + ar.alpha * wr[k];
             }
         }
         if (mode == 0 || mode == 2) {
@@ -341,7 +343,9 @@ __device__ __forceinline__ double gcs_rsqrt(double x) { return rsqrt(x); }
 // row stride ldh, lower triangle.  Pivot lifting: a pivot that falls below the rounding noise of its
 // own cancellation is lifted to that level (diag0 holds the diagonal before elimination).
 // Linv[b] receives the inverse of the b-th diagonal Cholesky block (15 doubles, row-major lower).
-GCS_DEV void gcs_cholesky(double *H, int nb, int ldh, const double *diag0, double *Linv, int lane) {
+GCS_DEV int gcs_tri(int r) { return (r * (r + 1)) >> 1; }   // start of row r in the packed lower triangle
+
+GCS_DEV void gcs_cholesky(double *H, int nb, const double *diag0, double *Linv, int lane) {
     const int n = 5 * nb;
     for (int b = 0; b < nb; ++b) {
         const int o = 5 * b;
@@ -350,7 +354,7 @@ GCS_DEV void gcs_cholesky(double *H, int nb, int ldh, const double *diag0, doubl
 #pragma unroll
         for (int r = 0; r < 5; ++r)
 #pragma unroll
-            for (int c = 0; c <= r; ++c) l[r * (r + 1) / 2 + c] = H[(o + r) * ldh + o + c];
+            for (int c = 0; c <= r; ++c) l[r * (r + 1) / 2 + c] = H[gcs_tri(o + r) + o + c];
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
             const double d0 = diag0[o + j];
@@ -384,12 +388,12 @@ GCS_DEV void gcs_cholesky(double *H, int nb, int ldh, const double *diag0, doubl
 #pragma unroll
             for (int r = 0; r < 5; ++r)
 #pragma unroll
-                for (int c = 0; c <= r; ++c) { H[(o + r) * ldh + o + c] = l[r * (r + 1) / 2 + c]; Linv[15 * b + r * (r + 1) / 2 + c] = li[r * (r + 1) / 2 + c]; }
+                for (int c = 0; c <= r; ++c) { H[gcs_tri(o + r) + o + c] = l[r * (r + 1) / 2 + c]; Linv[15 * b + r * (r + 1) / 2 + c] = li[r * (r + 1) / 2 + c]; }
         }
         // (2) panel: rows below the block,  L_panel = H_panel L_bb^-T
         const int rem = n - o - 5;
         GCS_LANE_LOOP(i, rem) {
-            double *hr = H + (o + 5 + i) * ldh + o;
+            double *hr = H + gcs_tri(o + 5 + i) + o;
             const double x0 = hr[0], x1 = hr[1], x2 = hr[2], x3 = hr[3], x4 = hr[4];
             hr[0] = x0 * li[0];
             hr[1] = x0 * li[1] + x1 * li[2];
@@ -401,11 +405,11 @@ GCS_DEV void gcs_cholesky(double *H, int nb, int ldh, const double *diag0, doubl
         // (3) trailing update; long rows first so the last partial round holds the short ones
         GCS_LANE_LOOP(i, rem) {
             const int r = n - 1 - i;
-            const double *pr = H + r * ldh + o;
+            const double *pr = H + gcs_tri(r) + o;
             const double p0 = pr[0], p1 = pr[1], p2 = pr[2], p3 = pr[3], p4 = pr[4];
-            double *hrow = H + r * ldh;
+            double *hrow = H + gcs_tri(r);
             for (int k = o + 5; k <= r; ++k) {
-                const double *pk = H + k * ldh + o;
+                const double *pk = H + gcs_tri(k) + o;
                 hrow[k] -= p0 * pk[0] + p1 * pk[1] + p2 * pk[2] + p3 * pk[3] + p4 * pk[4];
             }
         }
@@ -413,7 +417,7 @@ GCS_DEV void gcs_cholesky(double *H, int nb, int ldh, const double *diag0, doubl
     }
 }
 // x <- (L L')^-1 x   (y: scratch of n doubles)
-GCS_DEV void gcs_chol_solve(const double *H, int nb, int ldh, const double *Linv, double *x, double *y, int lane) {
+GCS_DEV void gcs_chol_solve(const double *H, int nb, const double *Linv, double *x, double *y, int lane) {
     const int n = 5 * nb;
     for (int b = 0; b < nb; ++b) {          // forward: L y = x
         const int o = 5 * b;
@@ -425,7 +429,7 @@ GCS_DEV void gcs_chol_solve(const double *H, int nb, int ldh, const double *Linv
         if (lane == 0) { y[o] = y0; y[o + 1] = y1; y[o + 2] = y2; y[o + 3] = y3; y[o + 4] = y4; }
         GCS_LANE_LOOP(i, n - o - 5) {
             const int r = o + 5 + i;
-            const double *hr = H + r * ldh + o;
+            const double *hr = H + gcs_tri(r) + o;
             x[r] -= hr[0] * y0 + hr[1] * y1 + hr[2] * y2 + hr[3] * y3 + hr[4] * y4;
         }
         GCS_SYNC();
@@ -441,10 +445,24 @@ GCS_DEV void gcs_chol_solve(const double *H, int nb, int ldh, const double *Linv
         const double x0 = y0 * li[0] + y1 * li[1] + y2 * li[3] + y3 * li[6] + y4 * li[10];
         if (lane == 0) { x[o] = x0; x[o + 1] = x1; x[o + 2] = x2; x[o + 3] = x3; x[o + 4] = x4; }
         GCS_LANE_LOOP(q, o) {
-            y[q] -= H[o * ldh + q] * x0 + H[(o + 1) * ldh + q] * x1 + H[(o + 2) * ldh + q] * x2 + H[(o + 3) * ldh + q] * x3 + H[(o + 4) * ldh + q] * x4;
+            y[q] -= H[gcs_tri(o) + q] * x0 + H[gcs_tri(o + 1) + q] * x1 + H[gcs_tri(o + 2) + q] * x2 + H[gcs_tri(o + 3) + q] * x3 + H[gcs_tri(o + 4) + q] * x4;
         }
         GCS_SYNC();
     }
+}
+
+// compact Hessian block Q[21] = aa0(3) aa1(3) ay0(2) ay1(2) yy xa0(3) xa1(3) xy0(2) xy1(2)
+//   M(a, c): the block's own 5x5 (a1 a2 y);   B(xr, c): its coupling to x (rows x1 x2)
+GCS_DEV double gcs_qM(const double *Qj, int a, int c) {
+    if (a == 4 && c == 4) return Qj[10];
+    if (a == 4 || c == 4) return Qj[6 + (a < c ? a : c)];
+    if ((a >> 1) != (c >> 1)) return 0.0;
+    return Qj[3 * (a >> 1) + (a & 1) + (c & 1)];
+}
+GCS_DEV double gcs_qB(const double *Qj, int xr, int c) {
+    if (c == 4) return Qj[17 + xr];
+    if ((xr >> 1) != (c >> 1)) return 0.0;
+    return Qj[11 + 3 * (xr >> 1) + (xr & 1) + (c & 1)];
 }
 
 // Solves one vertex program.  Scratch S must already hold: A, b (L.A, L.b), targets (L.tgt, edge-canonical
@@ -452,12 +470,12 @@ GCS_DEV void gcs_chol_solve(const double *H, int nb, int ldh, const double *Linv
 GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, const GcsVertexIn &in, int lane) {
     const int m = in.m, d = in.d;
     const bool term = in.type != 0;
-    const int n = 5 * d, nu = GCS_NCORE + 5 * d, ldh = L.ldh;
+    const int n = 5 * d, nu = GCS_NCORE + 5 * d;
     int *out = (int *)(S + L.ints), *prim = out + L.dcap;
     double *A = S + L.A, *b = S + L.b, *AA = S + L.AA, *tgt = S + L.tgt;
     double *u = S + L.u, *dua = S + L.dua, *du = S + L.du, *gu = S + L.gu, *ru = S + L.ru, *Pu = S + L.Pu, *qu = S + L.qu;
     double *v = S + L.v, *dv = S + L.dv, *rv = S + L.rv, *vbest = S + L.vbest;
-    double *H = S + L.H, *M = S + L.M, *B = S + L.B, *C = S + L.C;
+    double *H = S + L.H, *Q = S + L.Q, *C = S + L.C;
     GcsVertexOut res; res.iters = 0; res.status = 1; res.gap = 0; res.dres = 0;
 
     // ---- setup ----------------------------------------------------------------------------------
@@ -493,7 +511,10 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
     {
         double cnt = 0.0, tot = 0.0;
         { GcsRowsArgs ar; ar.mode = 6; ar.sigmu = 0; ar.alpha = 0; gcs_rows(L, S, m, d, term, ar, cnt, tot, lane); }
-        const double mu0 = tot / cnt;
+        double mu0 = tot / cnt;
+#ifdef GCS_EMULATE
+        if (getenv("GCSEMU_MU0")) mu0 *= atof(getenv("GCSEMU_MU0"));
+#endif
         GCS_LANE_LOOP(q, 4 * (d + 1) * m) { double *zr = S + L.zr; zr[q] = mu0 / zr[q]; }
         GCS_LANE_LOOP(j, d + 1) { double *zy = S + L.zy; if (!(j == d && term)) zy[j] = mu0 / zy[j]; }
         sq[0] = u[GCS_UT]; sq[1] = u[GCS_UZ] - u[GCS_UZ + 2]; sq[2] = u[GCS_UZ + 1] - u[GCS_UZ + 3];
@@ -563,16 +584,14 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
             for (int q = 0; q < 2; ++q) { ay0[q] = -(r03[3 + q] + (term ? 0.0 : r04[3 + q])); ay1[q] = -(r13[3 + q] + (term ? 0.0 : r14[3 + q])); xy0[q] = term ? 0.0 : r04[3 + q]; xy1[q] = term ? 0.0 : r14[3 + q]; }
             yy = r03[5] + r13[5] + (term ? 0.0 : r04[5] + r14[5]) + S[L.dsy + blk];
             if (blk < d) {
-                double *Mj = M + 25 * blk, *Bj = B + 20 * blk;
+                double *Qj = Q + GCS_QN * blk;
                 const int o = gcs_uw(blk);
-                for (int q = 0; q < 25; ++q) Mj[q] = 0.0;
-                for (int q = 0; q < 20; ++q) Bj[q] = 0.0;
-                Mj[0] = aa0[0] + Pu[o]; Mj[1] = Mj[5] = aa0[1]; Mj[6] = aa0[2] + Pu[o + 1];
-                Mj[12] = aa1[0] + Pu[o + 2]; Mj[13] = Mj[17] = aa1[1]; Mj[18] = aa1[2] + Pu[o + 3];
-                Mj[4] = Mj[20] = ay0[0]; Mj[9] = Mj[21] = ay0[1]; Mj[14] = Mj[22] = ay1[0]; Mj[19] = Mj[23] = ay1[1];
-                Mj[24] = yy + Pu[o + 4];
-                Bj[0] = xa0[0]; Bj[1] = xa0[1]; Bj[5] = xa0[1]; Bj[6] = xa0[2]; Bj[4] = xy0[0]; Bj[9] = xy0[1];
-                Bj[12] = xa1[0]; Bj[13] = xa1[1]; Bj[17] = xa1[1]; Bj[18] = xa1[2]; Bj[14] = xy1[0]; Bj[19] = xy1[1];
+                Qj[0] = aa0[0] + Pu[o]; Qj[1] = aa0[1]; Qj[2] = aa0[2] + Pu[o + 1];
+                Qj[3] = aa1[0] + Pu[o + 2]; Qj[4] = aa1[1]; Qj[5] = aa1[2] + Pu[o + 3];
+                Qj[6] = ay0[0]; Qj[7] = ay0[1]; Qj[8] = ay1[0]; Qj[9] = ay1[1];
+                Qj[10] = yy + Pu[o + 4];
+                Qj[11] = xa0[0]; Qj[12] = xa0[1]; Qj[13] = xa0[2]; Qj[14] = xa1[0]; Qj[15] = xa1[1]; Qj[16] = xa1[2];
+                Qj[17] = xy0[0]; Qj[18] = xy0[1]; Qj[19] = xy1[0]; Qj[20] = xy1[1];
             } else {    // core block: z_i plays a_i, y_v plays y
                 const int Z = GCS_UZ, Y = GCS_UYV, X = GCS_UX;
                 C[Z * 10 + Z] = aa0[0]; C[Z * 10 + Z + 1] = C[(Z + 1) * 10 + Z] = aa0[1]; C[(Z + 1) * 10 + Z + 1] = aa0[2];
@@ -619,26 +638,28 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
         //   x cols        :  B_j + cs_j B_* + cz_j C_xz (+ cs_j M_* for 's'/'t', where x also feeds z and w_*)
         //   t col         :  cz_j C_tz
         {
-            const double *Ms = M + 25 * jstar, *Bs = B + 20 * jstar;
+            const double *Qs = Q + GCS_QN * jstar;
             for (int jj = 0; jj < d - 1; ++jj) {
                 const int j = jj < jstar ? jj : jj + 1;
                 const double csj = prim[j] ? -1.0 : 1.0, czj = prim[j] ? 0.0 : 1.0;
+                const double *Qj = Q + GCS_QN * j;
                 GCS_LANE_LOOP(e, 25 * (jj + 1)) {
                     const int kk = e / 25, ab = e - 25 * kk, a = ab / 5, c = ab - 5 * a;
+                    if (kk == jj && c > a) continue;                       // packed storage: lower triangle only
                     const int k = kk < jstar ? kk : kk + 1;
                     const double csk = prim[k] ? -1.0 : 1.0, czk = prim[k] ? 0.0 : 1.0;
-                    double sv = csj * csk * Ms[5 * a + c] + czj * czk * C[(GCS_UZ + a) * 10 + GCS_UZ + c];
-                    if (kk == jj) sv += M[25 * j + 5 * a + c] + (a == c ? 1e-14 : 0.0);
-                    H[(5 + 5 * jj + a) * ldh + 5 + 5 * kk + c] = sv;
+                    double sv = csj * csk * gcs_qM(Qs, a, c) + czj * czk * C[(GCS_UZ + a) * 10 + GCS_UZ + c];
+                    if (kk == jj) sv += gcs_qM(Qj, a, c) + (a == c ? 1e-14 : 0.0);
+                    H[gcs_tri(5 + 5 * jj + a) + 5 + 5 * kk + c] = sv;
                 }
             }
             GCS_LANE_LOOP(e, 25 * (d - 1)) {
                 const int r = e / 5, c = e - 5 * r, jj = r / 5, a = r - 5 * jj, j = jj < jstar ? jj : jj + 1;
                 const double csj = prim[j] ? -1.0 : 1.0, czj = prim[j] ? 0.0 : 1.0;
                 double sv;
-                if (c < 4) sv = B[20 * j + 5 * c + a] + csj * Bs[5 * c + a] + czj * C[c * 10 + GCS_UZ + a] + (term ? csj * Ms[5 * a + c] : 0.0);
+                if (c < 4) sv = gcs_qB(Q + GCS_QN * j, c, a) + csj * gcs_qB(Qs, c, a) + czj * C[c * 10 + GCS_UZ + a] + (term ? csj * gcs_qM(Qs, a, c) : 0.0);
                 else sv = czj * C[GCS_UT * 10 + GCS_UZ + a];
-                H[(5 + r) * ldh + c] = sv;
+                H[gcs_tri(5 + r) + c] = sv;
             }
             GCS_LANE_LOOP(e, 25) {
                 const int p = e / 5, q = e - 5 * p;
@@ -646,23 +667,23 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
                     double sv;
                     if (p < 4) {
                         sv = C[p * 10 + q];
-                        if (term) sv += C[p * 10 + GCS_UZ + q] + C[(GCS_UZ + p) * 10 + q] + C[(GCS_UZ + p) * 10 + GCS_UZ + q] + Ms[5 * p + q] + Bs[5 * p + q] + Bs[5 * q + p];
+                        if (term) sv += C[p * 10 + GCS_UZ + q] + C[(GCS_UZ + p) * 10 + q] + C[(GCS_UZ + p) * 10 + GCS_UZ + q] + gcs_qM(Qs, p, q) + gcs_qB(Qs, p, q) + gcs_qB(Qs, q, p);
                     } else if (q < 4) sv = C[GCS_UT * 10 + q] + (term ? C[GCS_UT * 10 + GCS_UZ + q] : 0.0);
                     else sv = C[GCS_UT * 10 + GCS_UT];
-                    H[p * ldh + q] = sv + (p == q ? 1e-14 : 0.0);
+                    H[gcs_tri(p) + q] = sv + (p == q ? 1e-14 : 0.0);
                 }
             }
             GCS_SYNC();
-            GCS_LANE_LOOP(q, n) S[L.diag0 + q] = H[q * ldh + q];
+            GCS_LANE_LOOP(q, n) S[L.diag0 + q] = H[gcs_tri(q) + q];
             GCS_SYNC();
         }
-        gcs_cholesky(H, d, ldh, S + L.diag0, S + L.Linv, lane);
+        gcs_cholesky(H, d, S + L.diag0, S + L.Linv, lane);
 
         // ---- predictor:  rhs = -N'(P u + q) -----------------------------------------------------
         GCS_LANE_LOOP(q, nu) ru[q] = -(Pu[q] * u[q] + qu[q]);
         GCS_SYNC();
         gcs_adjoint(ru, dv, d, jstar, prim, term, lane);
-        gcs_chol_solve(H, d, ldh, S + L.Linv, dv, S + L.ytmp, lane);
+        gcs_chol_solve(H, d, S + L.Linv, dv, S + L.ytmp, lane);
         gcs_forward(dv, dua, d, jstar, prim, term, false, lane);
         double tmax = 0.0, dummy = 0.0;
         { GcsRowsArgs ar; ar.mode = 1; ar.sigmu = 0; ar.alpha = 0; gcs_rows(L, S, m, d, term, ar, tmax, dummy, lane); }
@@ -700,7 +721,7 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
             GCS_SYNC();
         }
         gcs_adjoint(ru, dv, d, jstar, prim, term, lane);
-        gcs_chol_solve(H, d, ldh, S + L.Linv, dv, S + L.ytmp, lane);
+        gcs_chol_solve(H, d, S + L.Linv, dv, S + L.ytmp, lane);
         gcs_forward(dv, du, d, jstar, prim, term, false, lane);
         { GcsRowsArgs ar; ar.mode = 3; ar.sigmu = sigma * mu; ar.alpha = 0; gcs_rows(L, S, m, d, term, ar, tmax, dummy, lane); }
         double dsq_s[3], dzq_s[3];
