@@ -308,9 +308,11 @@ extern "C" int gcsadmm_create(const GcsGraph *g, const GcsParams *p, int device,
     return 0;
 }
 
-extern "C" int gcsadmm_set_stream(GcsHandle *h, void *s) {
+extern "C" int gcsadmm_set_stream(GcsHandle *h, void *s, int external) {
     if (!h) return set_err(GCS_E_INVALID, "null handle%s", "");
-    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    h->stream = external ? (cudaStream_t)s : h->own_stream;   // a NULL external stream is the legacy default stream
     return 0;
 }
 

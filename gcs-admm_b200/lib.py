@@ -71,7 +71,7 @@ def load():
     L.gcsadmm_default_params.restype = None
     L.gcsadmm_create.argtypes = [C.POINTER(GcsGraph), C.POINTER(GcsParams), C.c_int, C.POINTER(C.c_void_p)]
     L.gcsadmm_destroy.argtypes = [C.c_void_p]
-    L.gcsadmm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.gcsadmm_set_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.gcsadmm_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(GcsStatus)]
     L.gcsadmm_step.argtypes = [C.c_void_p, C.c_int]
     L.gcsadmm_get_status.argtypes = [C.c_void_p, C.POINTER(GcsStatus)]
@@ -164,8 +164,8 @@ class Solver:
 
     __del__ = close
 
-    def set_stream(self, stream_ptr):
-        _check(load().gcsadmm_set_stream(self._h, C.c_void_p(stream_ptr)))
+    def set_stream(self, stream_ptr, external=True):
+        _check(load().gcsadmm_set_stream(self._h, C.c_void_p(stream_ptr), int(external)))
 
     def run(self, max_iters=None):
         st = GcsStatus()

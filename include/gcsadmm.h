@@ -100,8 +100,9 @@ void gcsadmm_default_params(GcsParams *p);
 
 int gcsadmm_create(const GcsGraph *g, const GcsParams *p, int device, GcsHandle **out);
 int gcsadmm_destroy(GcsHandle *h);
-/* run on an externally owned CUDA stream (e.g. torch's current stream); NULL restores the handle's own */
-int gcsadmm_set_stream(GcsHandle *h, void *cuda_stream);
+/* external != 0: enqueue on the caller's CUDA stream (e.g. torch's current stream; NULL = the legacy default
+ * stream); external == 0: back to the handle's own stream */
+int gcsadmm_set_stream(GcsHandle *h, void *cuda_stream, int external);
 
 /* whole iterations */
 int gcsadmm_run(GcsHandle *h, int max_iters, GcsStatus *st);   /* until the stop rule fires or max_iters passes */
