@@ -12,9 +12,9 @@ extern "C" int gcsemu_vertex_update_all(int nV, int nE, const int *poly_off, con
                                         const int *he_off, const int *he_edge, const unsigned char *he_flags,
                                         const unsigned char *vtype, const double *cent, double *xc, const double *mu,
                                         const double *z, double *x_v, double *z_v, double *y_v, double rho, double mu_scale,
-                                        double tol, int max_iter, int dcap, int mcap, long *total_iters) {
+                                        double tol, int max_iter, int dcap, int mcap, long *total_iters, double *ws, double theta) {
     GcsGraphView G = {nV, nE, poly_off, polyA, polyb, he_off, he_edge, he_flags, vtype, cent};
-    GcsStateView St = {xc, mu, z, x_v, z_v, y_v};
+    GcsStateView St = {xc, mu, z, x_v, z_v, y_v, ws, theta};
     GcsScratchLayout L = gcs_scratch_layout(dcap, mcap);
     double *S = (double *)malloc(sizeof(double) * L.total);
     int fails = 0;
@@ -30,3 +30,4 @@ extern "C" int gcsemu_vertex_update_all(int nV, int nE, const int *poly_off, con
     return fails;
 }
 extern "C" int gcsemu_scratch_doubles(int dcap, int mcap) { return gcs_scratch_layout(dcap, mcap).total; }
+extern "C" int gcsemu_ws_stride(int dcap, int mcap) { return gcs_ws_stride(gcs_scratch_layout(dcap, mcap)); }

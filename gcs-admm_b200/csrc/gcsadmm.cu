@@ -55,6 +55,7 @@ struct GcsHandle {
     double *polyA, *polyb, *cent;
     unsigned char *he_flags, *vtype, *edge_counted;
     double *xc, *mu, *z, *x_v, *z_v, *y_v;
+    double *ws;         // [nV][gcs_ws_stride] interior-point warm-start records (null when warm_theta == 0)
     double *partials;   // [edge_blocks][NSUMS]
     double *hist;       // [3][hist_cap]
     int hist_cap;
@@ -191,8 +192,8 @@ extern "C" int gcsadmm_device_count(void) {
 }
 extern "C" void gcsadmm_default_params(GcsParams *p) {
     p->rho0 = 1.0; p->tau_incr = 2.0; p->tau_decr = 2.0; p->nu = 10.0; p->frac = 0.1;
-    p->eps_abs = 1e-4; p->eps_rel = 1e-3; p->max_it = 1000; p->inner_tol = 1e-9; p->inner_max_iter = 60;
-    p->check_every = 8; p->abs_stop = 0; p->abs_tol = 1e-4;
+    p->eps_abs = 1e-4; p->eps_rel = 1e-3; p->max_it = 1000; p->inner_tol = 1e-8; p->inner_max_iter = 60;
+    p->check_every = 8; p->abs_stop = 0; p->abs_tol = 1e-4; p->warm_theta = 1e-3;
 }
 extern "C" int gcsadmm_scratch_bytes(int max_live_degree, int max_rows) {
     return (int)(gcs_scratch_layout(max_live_degree, max_rows).total * sizeof(double));
@@ -222,7 +223,7 @@ extern "C" int gcsadmm_destroy(GcsHandle *h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     void *ptrs[] = {h->poly_off, h->he_off, h->he_edge, h->edge_he_tail, h->edge_he_head, h->polyA, h->polyb, h->cent,
-                    h->he_flags, h->vtype, h->edge_counted, h->xc, h->mu, h->z, h->x_v, h->z_v, h->y_v, h->partials, h->hist, h->ctrl};
+                    h->he_flags, h->vtype, h->edge_counted, h->xc, h->mu, h->z, h->x_v, h->z_v, h->y_v, h->ws, h->partials, h->hist, h->ctrl};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
     if (h->flush_buf) cudaFree(h->flush_buf);
@@ -294,6 +295,7 @@ extern "C" int gcsadmm_create(const GcsGraph *g, const GcsParams *p, int device,
     if (g->edge_counted) UP(edge_counted, g->edge_counted, g->nE);
     UP(xc, (const double *)nullptr, 5 * Hall); UP(mu, (const double *)nullptr, 5 * (size_t)g->nH_own); UP(z, (const double *)nullptr, 5 * (size_t)g->nE);
     UP(x_v, (const double *)nullptr, 4 * (size_t)g->nV); UP(z_v, (const double *)nullptr, 4 * (size_t)g->nV); UP(y_v, (const double *)nullptr, g->nV);
+    if (h->p.warm_theta > 0.0) UP(ws, (const double *)nullptr, (size_t)g->nV * gcs_ws_stride(h->L));
     UP(partials, (const double *)nullptr, (size_t)h->edge_blocks * NSUMS);
     h->hist_cap = h->p.max_it + 2;
     UP(hist, (const double *)nullptr, 3 * (size_t)h->hist_cap);
@@ -323,6 +325,7 @@ static GcsGraphView graph_view(const GcsHandle *h) {
 }
 static GcsStateView state_view(const GcsHandle *h) {
     GcsStateView S; S.xc = h->xc; S.mu = h->mu; S.z = h->z; S.x_v = h->x_v; S.z_v = h->z_v; S.y_v = h->y_v;
+    S.ws = h->ws; S.theta = h->p.warm_theta;
     return S;
 }
 static int launch_k1(GcsHandle *h) {

@@ -108,7 +108,15 @@ struct GcsVertexIn {
     double cx, cy;         // strictly interior point of the polytope
     double rho;
     double tol; int max_iter;
+    double *ws;            // warm-start record of this vertex in global memory (gcs_ws_stride doubles) or null
+    double theta;          // warm-start mixing weight towards the analytic centre (0 = cold start)
 };
+
+// warm-start record: [valid][v (ncap)][row duals (4 (dcap+1) mcap)][single duals (dcap+1)][cone dual (3)]
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline int gcs_ws_stride(const GcsScratchLayout &L) { return 1 + L.ncap + 4 * (L.dcap + 1) * L.mcap + (L.dcap + 1) + 3; }
 
 struct GcsVertexOut { int iters; int status; double gap, dres; };
 
@@ -506,20 +514,39 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
     }
     GCS_SYNC();
     gcs_forward(v, u, d, jstar, prim, term, true, lane);
-    // slacks -> centred duals  z = mu0 / s  with mu0 = mean slack
+    // slacks -> centred duals  z = mu0 / s  with mu0 = mean slack.
+    // Warm start (the feasible set does not change between ADMM iterations, only the targets do): pull the
+    // previous optimum a fraction theta towards the analytic centre — strictly feasible by convexity — keep
+    // its duals and add the centring term  theta * mean-slack / s  so every complementarity product is positive.
     double zq[3], sq[3];
     {
+        const int nrw = 4 * (L.dcap + 1) * L.mcap;
+        const bool warm = in.ws != 0 && in.theta > 0.0 && in.ws[0] == 1.0;
+        const double *wv = in.ws + 1, *wz = in.ws + 1 + L.ncap, *wy = wz + nrw, *wq = wy + L.dcap + 1;
+        if (warm) {
+            GCS_LANE_LOOP(q, n) v[q] = wv[q] + in.theta * (v[q] - wv[q]);
+            GCS_SYNC();
+            gcs_forward(v, u, d, jstar, prim, term, true, lane);
+        }
         double cnt = 0.0, tot = 0.0;
         { GcsRowsArgs ar; ar.mode = 6; ar.sigmu = 0; ar.alpha = 0; gcs_rows(L, S, m, d, term, ar, cnt, tot, lane); }
         double mu0 = tot / cnt;
 #ifdef GCS_EMULATE
         if (getenv("GCSEMU_MU0")) mu0 *= atof(getenv("GCSEMU_MU0"));
 #endif
-        GCS_LANE_LOOP(q, 4 * (d + 1) * m) { double *zr = S + L.zr; zr[q] = mu0 / zr[q]; }
-        GCS_LANE_LOOP(j, d + 1) { double *zy = S + L.zy; if (!(j == d && term)) zy[j] = mu0 / zy[j]; }
+        if (warm) mu0 *= in.theta;
+        const int nfam = term ? 1 : 2;
+        GCS_LANE_LOOP(q, 4 * (d + 1) * m) {
+            double *zr = S + L.zr;
+            // slot-major layout with stride m; the record uses the same (slot * m + k) indexing
+            zr[q] = mu0 / zr[q] + (warm ? wz[q] : 0.0);
+        }
+        (void)nfam;
+        GCS_LANE_LOOP(j, d + 1) { double *zy = S + L.zy; if (!(j == d && term)) zy[j] = mu0 / zy[j] + (warm ? wy[j] : 0.0); }
         sq[0] = u[GCS_UT]; sq[1] = u[GCS_UZ] - u[GCS_UZ + 2]; sq[2] = u[GCS_UZ + 1] - u[GCS_UZ + 3];
         const double det = gcs_jnorm2(sq[0], sq[1], sq[2]);
         zq[0] = mu0 * sq[0] / det; zq[1] = -mu0 * sq[1] / det; zq[2] = -mu0 * sq[2] / det;
+        if (warm) { zq[0] += wq[0]; zq[1] += wq[1]; zq[2] += wq[2]; }
         GCS_SYNC();
     }
     const int nrows_lp = (term ? 1 : 2) * (2 * d * m + 2 * m) + d + (term ? 0 : 1);
@@ -752,6 +779,16 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
         zq[0] += alpha * dzq[0]; zq[1] += alpha * dzq[1]; zq[2] += alpha * dzq[2];
         GCS_SYNC();
         gcs_forward(v, u, d, jstar, prim, term, true, lane);
+    }
+    if (in.ws != 0) {   // warm-start record for the next ADMM iteration (only a converged primal-dual pair is reused)
+        const int nrw = 4 * (L.dcap + 1) * L.mcap;
+        double *wv = in.ws + 1, *wz = in.ws + 1 + L.ncap, *wy = wz + nrw, *wq = wy + L.dcap + 1;
+        if (res.status == 0) {
+            GCS_LANE_LOOP(q, n) wv[q] = v[q];
+            GCS_LANE_LOOP(q, 4 * (d + 1) * m) wz[q] = S[L.zr + q];
+            GCS_LANE_LOOP(j, d + 1) wy[j] = S[L.zy + j];
+            if (lane == 0) { wq[0] = zq[0]; wq[1] = zq[1]; wq[2] = zq[2]; in.ws[0] = 1.0; }
+        } else if (lane == 0) in.ws[0] = 0.0;
     }
     if (res.status != 0) {
         GCS_LANE_LOOP(q, n) v[q] = vbest[q];

@@ -22,6 +22,8 @@ struct GcsStateView {
     const double *mu;    // [H][5]  scaled duals
     const double *z;     // [E][5]  edge variables
     double *x_v, *z_v, *y_v;   // [nV][4], [nV][4], [nV]
+    double *ws;                // [nV][gcs_ws_stride] warm-start records, or null
+    double theta;
 };
 
 // returns the interior-point iteration count (lane-uniform); *status receives the solve status
@@ -68,9 +70,27 @@ GCS_DEV int gcs_vertex_update(const GcsGraphView &G, const GcsStateView &St, int
         S[L.tgt + q] = St.z[5 * (size_t)e + c] + mu_scale * St.mu[5 * (size_t)h + c];
     }
     GCS_SYNC();
+    if (type == GCS_VT_GENERIC) {
+        // all consensus targets exactly zero (untouched region of a cold start): the program's optimum is the
+        // origin (cost t + eps y + rho/2 |.|^2 >= 0, attained at a = 0, y = 0, t = 0), no solve needed
+        double nz = 0.0;
+        GCS_LANE_LOOP(q, 5 * d) nz = fmax(nz, fabs(S[L.tgt + q]));
+        nz = gcs_warp_max(nz);
+        if (nz == 0.0) {
+            GCS_LANE_LOOP(q, 5 * d) { const int j = q / 5; St.xc[5 * (size_t)hid[j] + (q - 5 * j)] = 0.0; }
+            if (lane == 0) {
+                for (int k = 0; k < 4; ++k) { St.z_v[4 * (size_t)v + k] = 0.0; St.x_v[4 * (size_t)v + k] = G.cent[2 * (size_t)v + (k & 1)]; }
+                St.y_v[v] = 0.0;
+                if (St.ws) St.ws[(size_t)v * gcs_ws_stride(L)] = 0.0;
+            }
+            GCS_SYNC();
+            return 0;
+        }
+    }
     GcsVertexIn in;
     in.m = m; in.d = d; in.type = type; in.cx = G.cent[2 * (size_t)v]; in.cy = G.cent[2 * (size_t)v + 1];
     in.rho = rho; in.tol = tol; in.max_iter = max_iter;
+    in.ws = St.ws ? St.ws + (size_t)v * gcs_ws_stride(L) : 0; in.theta = St.theta;
     GcsVertexOut r = gcs_vertex_solve(L, S, in, lane);
     *status = r.status;
     const double *u = S + L.u, *tgt = S + L.tgt;

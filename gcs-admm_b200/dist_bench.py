@@ -24,12 +24,13 @@ def main(args):
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     W = max(3, args.warmup)
+    burn = max(W, args.grid + 10 if args.burn_in < 0 else args.burn_in)
     g = grid_packed_graph(args.grid)
     lp = split_graph(g, partition_vertices(g, world), world)[rank]
     t_create = time.perf_counter()
-    be = CudaBackend(lp, local_rank, max_it=max(1000, args.steps + W + 8))
+    be = CudaBackend(lp, local_rank, max_it=max(1000, args.steps + burn + 8), eps_abs=0.0, eps_rel=0.0)
     drv = DistributedADMM(lp, be)
-    drv.iterate(W)
+    drv.iterate(burn)
     torch.cuda.synchronize()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=be.device)
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -58,9 +59,10 @@ def main(args):
     # end to end: local graph upload + K iterations + local solution download, wall clock, max over ranks
     dist.barrier()
     t0 = time.perf_counter()
-    be2 = CudaBackend(lp, local_rank, max_it=max(1000, args.steps + 8), eps_abs=0.0, eps_rel=0.0)
+    n_e2e = burn + args.steps
+    be2 = CudaBackend(lp, local_rank, max_it=max(1000, n_e2e + 8), eps_abs=0.0, eps_rel=0.0)
     drv2 = DistributedADMM(lp, be2)
-    drv2.iterate(args.steps)
+    drv2.iterate(n_e2e)
     sol = be2.solution()
     hist = be2.history()
     e2e = time.perf_counter() - t0
@@ -84,11 +86,11 @@ def main(args):
         line = {"metric": bench.METRIC, "value": 1e3 / per, "unit": bench.UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": per, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"grid{args.grid}x{args.grid} 2-D GCS: {g.nV} vertices, {g.nE} directed edges, strips over {world} GPUs",
-                           "mode": "parity (vertex programs solved to 1e-9)", "l2": "flushed (256 MiB) before every timed iteration",
+                           "mode": "parity (every vertex program solved to 1e-8 by the interior-point kernel)", "l2": "flushed (256 MiB) before every timed iteration", "burn_in_iterations": burn,
                            "halo_half_edges_rank0": int(lp.nH_ghost), "collectives": "all_to_all_single(halo) + all_reduce(8 doubles) per iteration, NCCL"},
                 "clocks": clocks,
-                "e2e": {"value": args.steps / e2e, "unit": bench.UNIT, "h2d_bytes_per_step": gs_bytes / args.steps,
-                        "d2h_bytes_per_step": out_bytes / args.steps, "note": "per rank: local graph upload + K iterations + solution download; max over ranks"},
+                "e2e": {"value": n_e2e / e2e, "unit": bench.UNIT, "h2d_bytes_per_step": gs_bytes / n_e2e,
+                        "d2h_bytes_per_step": out_bytes / n_e2e, "note": "per rank, from a cold start: local graph upload + (burn_in + K) iterations + solution download; max over ranks"},
                 "gpu_launches": 4 * args.steps,
                 "roofline": {"bound": "hbm", "achieved": (k1b + k2b) / world / (per * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": (k1b + k2b) / world / (per * 1e-3) / 1e9 / peak, "traffic": None,

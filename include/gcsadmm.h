@@ -77,11 +77,13 @@ typedef struct GcsParams {       /* literals of admm_solver_v3.py:621-651 */
     double frac;                 /* 0.1: rho adapts only while it < frac * max_it */
     double eps_abs, eps_rel;     /* 1e-4, 1e-3 */
     int32_t max_it;              /* 1000 */
-    double inner_tol;            /* interior-point tolerance of the vertex programs (1e-9) */
+    double inner_tol;            /* interior-point tolerance of the vertex programs (1e-8: gap and 10x that on the dual residual; MOSEK's default is 1e-8) */
     int32_t inner_max_iter;      /* 60 */
     int32_t check_every;         /* host polls the stop flag every this many iterations (8) */
     int32_t abs_stop;            /* 0: reference stop rule; 1: stop when max(pri, dual) < abs_tol */
     double abs_tol;              /* 1e-4 (metric "time to residual 1e-4") */
+    double warm_theta;           /* interior-point warm start: previous optimum pulled this fraction towards the
+                                    analytic centre (1e-3); 0 = cold start every iteration */
 } GcsParams;
 
 typedef struct GcsStatus {

@@ -25,11 +25,12 @@ def emu():
     lib.gcsemu_vertex_update_all.restype = C.c_int
     lib.gcsemu_vertex_update_all.argtypes = [C.c_int, C.c_int, _ip, _dp, _dp, _ip, _ip, _bp, _bp, _dp, _dp, _dp, _dp,
                                              _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
-                                             C.c_int, C.POINTER(C.c_long)]
+                                             C.c_int, C.POINTER(C.c_long), C.c_void_p, C.c_double]
+    lib.gcsemu_ws_stride.restype = C.c_int
     return lib
 
 
-def emu_vertex_update(lib, g, mu, z, rho, tol=1e-9, max_iter=60):
+def emu_vertex_update(lib, g, mu, z, rho, tol=1e-9, max_iter=60, ws=None, theta=0.0):
     xc = np.zeros((g.H, 5))
     x_v, z_v, y_v = np.zeros((g.nV, 4)), np.zeros((g.nV, 4)), np.zeros(g.nV)
     iters = C.c_long()
@@ -38,7 +39,8 @@ def emu_vertex_update(lib, g, mu, z, rho, tol=1e-9, max_iter=60):
                                          g.he_flags, g.vtype, cent.reshape(-1), xc.reshape(-1),
                                          np.ascontiguousarray(mu).reshape(-1), np.ascontiguousarray(z).reshape(-1),
                                          x_v.reshape(-1), z_v.reshape(-1), y_v, rho, 1.0, tol, max_iter,
-                                         max(1, g.max_live_degree), max(1, g.max_rows), C.byref(iters))
+                                         max(1, g.max_live_degree), max(1, g.max_rows), C.byref(iters),
+                                         ws.ctypes.data_as(C.c_void_p) if ws is not None else None, theta)
     return xc, x_v, z_v, y_v, fails, iters.value
 
 
