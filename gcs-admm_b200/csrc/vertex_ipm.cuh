@@ -212,8 +212,8 @@ GCS_DEV int gcs_slot(int blk, int i, int fam) { return (blk * 2 + i) * 2 + fam; 
 
 GCS_DEV void gcs_rows(const GcsScratchLayout &L, double *S, int m, int d, bool term, const GcsRowsArgs &ar,
                       double &r0, double &r1, int lane) {
-    const double *A = S + L.A, *b = S + L.b, *AA = S + L.AA;
-    const double *u = S + L.u, *du = S + L.du, *dua = S + L.dua;
+    const double *__restrict__ A = S + L.A, *__restrict__ b = S + L.b, *__restrict__ AA = S + L.AA;
+    const double *__restrict__ u = S + L.u, *__restrict__ du = S + L.du, *__restrict__ dua = S + L.dua;
     double acc_max = 0.0, acc_min = 1e300, acc_sum = 0.0, acc_cnt = 0.0;
     const int mode = ar.mode;
     const bool need_p = (mode == 1 || mode == 2 || mode == 3), need_d = (mode == 3 || mode == 4);
@@ -228,7 +228,7 @@ GCS_DEV void gcs_rows(const GcsScratchLayout &L, double *S, int m, int d, bool t
         double ph = 0, pp0 = 0, pp1 = 0, dh = 0, dp0 = 0, dp1 = 0;
         if (need_p) { ph = fam ? -dua[yo] : dua[yo]; pp0 = fam ? dua[xo] - dua[po] : dua[po]; pp1 = fam ? dua[xo + 1] - dua[po + 1] : dua[po + 1]; }
         if (need_d) { dh = fam ? -du[yo] : du[yo]; dp0 = fam ? du[xo] - du[po] : du[po]; dp1 = fam ? du[xo + 1] - du[po + 1] : du[po + 1]; }
-        double *zr = S + L.zr + slot * m, *wr = S + L.wr + slot * m;
+        double *__restrict__ zr = S + L.zr + slot * m, *__restrict__ wr = S + L.wr + slot * m;
         double s_aa0 = 0, s_aa1 = 0, s_aa2 = 0, s_ba0 = 0, s_ba1 = 0, s_bb = 0, w_a0 = 0, w_a1 = 0, w_b = 0;
         for (int k = 0; k < m; ++k) {
             const double A0 = A[2 * k], A1 = A[2 * k + 1], bk = b[k];
@@ -410,13 +410,25 @@ GCS_DEV void gcs_cholesky(double *H, int nb, const double *diag0, double *Linv, 
             hr[4] = x0 * li[10] + x1 * li[11] + x2 * li[12] + x3 * li[13] + x4 * li[14];
         }
         GCS_SYNC();
-        // (3) trailing update; long rows first so the last partial round holds the short ones
+        // (3) trailing update; long rows first so the last partial round holds the short ones.
+        //     Row r only writes its own entries and only reads the (already final) panel columns, so the loads
+        //     of four steps are issued before the four stores.
         GCS_LANE_LOOP(i, rem) {
             const int r = n - 1 - i;
             const double *pr = H + gcs_tri(r) + o;
             const double p0 = pr[0], p1 = pr[1], p2 = pr[2], p3 = pr[3], p4 = pr[4];
             double *hrow = H + gcs_tri(r);
-            for (int k = o + 5; k <= r; ++k) {
+            int k = o + 5;
+            for (; k + 3 <= r; k += 4) {
+                const double *q0 = H + gcs_tri(k) + o, *q1 = H + gcs_tri(k + 1) + o, *q2 = H + gcs_tri(k + 2) + o, *q3 = H + gcs_tri(k + 3) + o;
+                const double s0 = p0 * q0[0] + p1 * q0[1] + p2 * q0[2] + p3 * q0[3] + p4 * q0[4];
+                const double s1 = p0 * q1[0] + p1 * q1[1] + p2 * q1[2] + p3 * q1[3] + p4 * q1[4];
+                const double s2 = p0 * q2[0] + p1 * q2[1] + p2 * q2[2] + p3 * q2[3] + p4 * q2[4];
+                const double s3 = p0 * q3[0] + p1 * q3[1] + p2 * q3[2] + p3 * q3[3] + p4 * q3[4];
+                const double h0 = hrow[k], h1 = hrow[k + 1], h2 = hrow[k + 2], h3 = hrow[k + 3];
+                hrow[k] = h0 - s0; hrow[k + 1] = h1 - s1; hrow[k + 2] = h2 - s2; hrow[k + 3] = h3 - s3;
+            }
+            for (; k <= r; ++k) {
                 const double *pk = H + gcs_tri(k) + o;
                 hrow[k] -= p0 * pk[0] + p1 * pk[1] + p2 * pk[2] + p3 * pk[3] + p4 * pk[4];
             }
@@ -425,7 +437,7 @@ GCS_DEV void gcs_cholesky(double *H, int nb, const double *diag0, double *Linv, 
     }
 }
 // x <- (L L')^-1 x   (y: scratch of n doubles)
-GCS_DEV void gcs_chol_solve(const double *H, int nb, const double *Linv, double *x, double *y, int lane) {
+GCS_DEV void gcs_chol_solve(const double *__restrict__ H, int nb, const double *__restrict__ Linv, double *__restrict__ x, double *__restrict__ y, int lane) {
     const int n = 5 * nb;
     for (int b = 0; b < nb; ++b) {          // forward: L y = x
         const int o = 5 * b;

@@ -1,0 +1,85 @@
+"""GPU: the public entry points (solve(), the CLI) and size-independent properties at BASELINE sizes."""
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_solve_entry_point_benchmark1():
+    from gcs_admm_b200.solver import solve
+    As, bs, n, d, keys = load_golden("benchmark1")
+    res = solve(As, bs, n, seed=0)
+    assert res["iterations"] == 39 and res["converged"]
+    assert abs(res["cost"] - float(d["v3_cost"])) <= 1e-4 * float(d["v3_cost"])
+    assert len(res["pri_res_seq"]) == 40 and res["pri_res_seq"][0] == 0.0 and res["rho_seq"][0] == 1.0
+    assert res["path"][0] == "s" and res["path"][-1] == "t" and set(res["path"]) in ({'s', 0, 1, 2, 't'}, {'s', 0, 3, 2, 't'})
+    gold_len = sum(np.linalg.norm(x[:2] - x[2:]) for x, y in zip(d["v3_x_v_rounded"], d["v3_y_v_rounded"]) if y > 0.5)
+    assert abs(res["final_cost"] - gold_len) < 1e-4 * gold_len
+    assert list(res["y_v_sol"].keys()) == keys and list(res["y_e_sol"].keys()) == res["E"]
+
+
+def test_cli_writes_reference_pickle(tmp_path):
+    env = dict(os.environ)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "admm_solver_v3.py"), "--test_file=benchmark2", "--show_plot=False", "--seed=0"],
+                         capture_output=True, text=True, cwd=str(tmp_path), env=env, timeout=600)
+    assert out.returncode == 0, out.stderr
+    for landmark in ("Running ADMM Solver v3 on benchmark2", "V: ['s', 't', 0", "E: [", "it = 100/1000", "BREAKING FOR OPT",
+                     "Total solve time:", "Cost before rounding:", "POST-ROUNDING", "x_v_rounded=", "y_v_rounded="):
+        assert landmark in out.stdout, landmark
+    d = pickle.load(open(os.path.join(ROOT, "benchmark_data", "admm_solver_v3_benchmark2.pkl"), "rb"))
+    gold = load_golden("benchmark2")[3]
+    assert d["iterations"] == 100 and d["ADMM"] is True
+    assert abs(d["cost"] - float(gold["v3_cost"])) <= 1e-4 * float(gold["v3_cost"])
+    assert len(d["pri_res_seq"]) == 101 and isinstance(d["rho_seq"], np.ndarray)
+    bad = subprocess.run([sys.executable, os.path.join(ROOT, "admm_solver_v3.py"), "--test_file=nope"], capture_output=True, text=True, timeout=120)
+    assert bad.returncode == 1 and "Error: Test file 'nope' not found" in bad.stdout
+
+
+def test_small_grid_converges_to_a_sane_path():
+    """Run a 5x5 grid to max(pri, dual) < 1e-4: relaxation cost >= straight-line distance, rounded path cost >=
+    relaxation cost, path connects s to t through overlapping regions."""
+    from gcs_admm_b200.generator import grid_problem, packed_to_dicts
+    from gcs_admm_b200.solver import solve
+    off, A, b, s_pt, t_pt = grid_problem(5)
+    As, bs = packed_to_dicts(off, A, b)
+    res = solve(As, bs, 2, max_it=4000, abs_stop=1, abs_tol=1e-4, seed=0)
+    assert res["converged"] and max(res["pri_res_seq"][-1], res["dual_res_seq"][-1]) < 1e-4
+    straight = float(np.linalg.norm(t_pt - s_pt))
+    assert res["cost"] >= straight - 1e-3
+    assert res["final_cost"] >= res["cost"] - 1e-3 and res["final_cost"] < 1.5 * straight
+    p = res["path"]
+    assert p[0] == "s" and p[-1] == "t" and all((a, c) in set(res["E"]) for a, c in zip(p[:-1], p[1:]))
+
+
+def test_properties_at_full_size():
+    """100k-vertex grid (the BASELINE metric config), a few iterations: exact identities that do not need an
+    oracle — z is the average of the two copies, mu accumulates z - xc, reruns are bitwise reproducible."""
+    from gcs_admm_b200.generator import grid_packed_graph
+    from gcs_admm_b200.lib import Solver
+    g = grid_packed_graph(316)
+    assert g.nV == 99858 and g.nE == 398164
+    outs = []
+    for rep in range(2):
+        s = Solver(g)
+        s.step(6)
+        xc, mu, z, rho, it = s.state()
+        outs.append((xc, mu, z))
+        if rep == 0:
+            assert it == 6 and np.all(np.isfinite(xc)) and np.all(np.isfinite(mu))
+            assert np.array_equal(z, 0.5 * (xc[g.edge_he_tail] + xc[g.edge_he_head]))
+            mu_prev = mu.copy()
+            s.step(1)
+            xc2, mu2, z2, _, _ = s.state()
+            assert np.allclose(mu2, mu_prev + (z2[g.he_edge] - xc2), rtol=0, atol=1e-15)
+            st = s.status()
+            r = z2[g.he_edge] - xc2
+            assert abs(st["pri_res"] - np.sqrt(np.sum(r * r))) <= 1e-9 * max(1.0, st["pri_res"])
+        s.close()
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
