@@ -183,7 +183,8 @@ def main():
         "config": {"workload": f"grid{args.grid}x{args.grid} 2-D GCS: {g.nV} vertices, {g.nE} directed edges, m=8 rows/region "
                                "(BASELINE.json metric config: 100k-vertex 2-D GCS)", "mode": "parity (every vertex program solved to 1e-8 by the interior-point kernel)",
                    "l2": "flushed (256 MiB memset) before every timed iteration", "burn_in_iterations": burn, "inner_ipm_iters_per_vertex": (st["inner_iters"] - st0["inner_iters"]) / max(1, args.steps * g.nV),
-                   "inner_tol": 1e-8, "warm_start_theta": 1e-3},
+                   "inner_tol": 1e-8, "warm_start_theta": 1e-3, "zero_tol": 1e-12,
+                   "vertex_programs_skipped_as_zero_frac": (st["skipped"] - st0["skipped"]) / max(1, args.steps * g.nV)},
         "clocks": clocks,
         "e2e": {"value": n_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": gs_bytes / n_e2e, "d2h_bytes_per_step": out_bytes / n_e2e,
                 "note": "gcsadmm_solve_host from a cold start: graph upload + (burn_in + K) iterations + solution/history download, wall clock; value = (burn_in + K) / time"},

@@ -14,7 +14,7 @@ extern "C" int gcsemu_vertex_update_all(int nV, int nE, const int *poly_off, con
                                         const double *z, double *x_v, double *z_v, double *y_v, double rho, double mu_scale,
                                         double tol, int max_iter, int dcap, int mcap, long *total_iters, double *ws, double theta) {
     GcsGraphView G = {nV, nE, poly_off, polyA, polyb, he_off, he_edge, he_flags, vtype, cent};
-    GcsStateView St = {xc, mu, z, x_v, z_v, y_v, ws, theta};
+    GcsStateView St = {xc, mu, z, x_v, z_v, y_v, ws, theta, 0.0};
     GcsScratchLayout L = gcs_scratch_layout(dcap, mcap);
     double *S = (double *)malloc(sizeof(double) * L.total);
     int fails = 0;
@@ -23,7 +23,7 @@ extern "C" int gcsemu_vertex_update_all(int nV, int nE, const int *poly_off, con
         int status = 0;
         memset(S, 0, sizeof(double) * L.total);
         iters += gcs_vertex_update(G, St, v, rho, mu_scale, tol, max_iter, L, S, 0, &status);
-        if (status != 0 && status != 5) { fails++; if (getenv("GCSEMU_VERBOSE")) fprintf(stderr, "emu: vertex %d status %d\n", v, status); }
+        if (status > 0 && status != 5) { fails++; if (getenv("GCSEMU_VERBOSE")) fprintf(stderr, "emu: vertex %d status %d\n", v, status); }
     }
     free(S);
     *total_iters = iters;

@@ -37,7 +37,7 @@ struct Ctrl {
     double rho, mu_scale;
     double pri, dual, eps_pri, eps_dual;
     double sums[NSUMS];
-    unsigned long long inner_iters;
+    unsigned long long inner_iters, skipped;
     int it, stop, opt, diverged, inner_fail, ignore_stop;
 };
 
@@ -78,7 +78,8 @@ vertex_kernel(GcsGraphView G, GcsStateView St, Ctrl *ctrl, GcsScratchLayout L, d
     const int iters = gcs_vertex_update(G, St, v, ctrl->rho, ctrl->mu_scale, tol, max_iter, L, S, lane, &status);
     if (lane == 0) {
         if (iters) atomicAdd(&ctrl->inner_iters, (unsigned long long)iters);
-        if (status != 0 && status != 5) atomicAdd(&ctrl->inner_fail, 1);
+        if (status > 0 && status != 5) atomicAdd(&ctrl->inner_fail, 1);
+        if (status < 0) atomicAdd(&ctrl->skipped, 1ull);
     }
 }
 
@@ -193,7 +194,7 @@ extern "C" int gcsadmm_device_count(void) {
 extern "C" void gcsadmm_default_params(GcsParams *p) {
     p->rho0 = 1.0; p->tau_incr = 2.0; p->tau_decr = 2.0; p->nu = 10.0; p->frac = 0.1;
     p->eps_abs = 1e-4; p->eps_rel = 1e-3; p->max_it = 1000; p->inner_tol = 1e-8; p->inner_max_iter = 60;
-    p->check_every = 8; p->abs_stop = 0; p->abs_tol = 1e-4; p->warm_theta = 1e-3;
+    p->check_every = 8; p->abs_stop = 0; p->abs_tol = 1e-4; p->warm_theta = 1e-3; p->zero_tol = 1e-12;
 }
 extern "C" int gcsadmm_scratch_bytes(int max_live_degree, int max_rows) {
     return (int)(gcs_scratch_layout(max_live_degree, max_rows).total * sizeof(double));
@@ -325,7 +326,7 @@ static GcsGraphView graph_view(const GcsHandle *h) {
 }
 static GcsStateView state_view(const GcsHandle *h) {
     GcsStateView S; S.xc = h->xc; S.mu = h->mu; S.z = h->z; S.x_v = h->x_v; S.z_v = h->z_v; S.y_v = h->y_v;
-    S.ws = h->ws; S.theta = h->p.warm_theta;
+    S.ws = h->ws; S.theta = h->p.warm_theta; S.zero_tol = h->p.zero_tol;
     return S;
 }
 static int launch_k1(GcsHandle *h) {
@@ -354,7 +355,7 @@ static int fetch_ctrl(GcsHandle *h) {
 static void fill_status(const GcsHandle *h, GcsStatus *st) {
     const Ctrl *c = h->ctrl_host;
     st->iterations = c->it; st->converged = c->opt; st->diverged = c->diverged; st->inner_fail = c->inner_fail;
-    st->inner_iters = (int64_t)c->inner_iters; st->rho = c->rho; st->pri_res = c->pri; st->dual_res = c->dual;
+    st->inner_iters = (int64_t)c->inner_iters; st->skipped = (int64_t)c->skipped; st->rho = c->rho; st->pri_res = c->pri; st->dual_res = c->dual;
     st->eps_pri = c->eps_pri; st->eps_dual = c->eps_dual;
 }
 

@@ -24,6 +24,7 @@ struct GcsStateView {
     double *x_v, *z_v, *y_v;   // [nV][4], [nV][4], [nV]
     double *ws;                // [nV][gcs_ws_stride] warm-start records, or null
     double theta;
+    double zero_tol;           // targets with max-norm <= zero_tol are treated as exactly zero
 };
 
 // returns the interior-point iteration count (lane-uniform); *status receives the solve status
@@ -71,12 +72,13 @@ GCS_DEV int gcs_vertex_update(const GcsGraphView &G, const GcsStateView &St, int
     }
     GCS_SYNC();
     if (type == GCS_VT_GENERIC) {
-        // all consensus targets exactly zero (untouched region of a cold start): the program's optimum is the
-        // origin (cost t + eps y + rho/2 |.|^2 >= 0, attained at a = 0, y = 0, t = 0), no solve needed
+        // all consensus targets (numerically) zero — untouched or long-decayed region: for zero targets the
+        // program's optimum is the origin (cost t + eps y + rho/2 |.|^2 >= 0, attained at a = 0, y = 0, t = 0),
+        // and the prox map is non-expansive, so |solution| <= |targets| <= zero_tol (1e-12 by default): no solve needed
         double nz = 0.0;
         GCS_LANE_LOOP(q, 5 * d) nz = fmax(nz, fabs(S[L.tgt + q]));
         nz = gcs_warp_max(nz);
-        if (nz == 0.0) {
+        if (nz <= St.zero_tol) {
             GCS_LANE_LOOP(q, 5 * d) { const int j = q / 5; St.xc[5 * (size_t)hid[j] + (q - 5 * j)] = 0.0; }
             if (lane == 0) {
                 for (int k = 0; k < 4; ++k) { St.z_v[4 * (size_t)v + k] = 0.0; St.x_v[4 * (size_t)v + k] = G.cent[2 * (size_t)v + (k & 1)]; }
@@ -84,6 +86,7 @@ GCS_DEV int gcs_vertex_update(const GcsGraphView &G, const GcsStateView &St, int
                 if (St.ws) St.ws[(size_t)v * gcs_ws_stride(L)] = 0.0;
             }
             GCS_SYNC();
+            *status = -1;     // skipped
             return 0;
         }
     }

@@ -37,12 +37,12 @@ class GcsParams(C.Structure):
     _fields_ = [("rho0", C.c_double), ("tau_incr", C.c_double), ("tau_decr", C.c_double), ("nu", C.c_double),
                 ("frac", C.c_double), ("eps_abs", C.c_double), ("eps_rel", C.c_double), ("max_it", C.c_int32),
                 ("inner_tol", C.c_double), ("inner_max_iter", C.c_int32), ("check_every", C.c_int32),
-                ("abs_stop", C.c_int32), ("abs_tol", C.c_double), ("warm_theta", C.c_double)]
+                ("abs_stop", C.c_int32), ("abs_tol", C.c_double), ("warm_theta", C.c_double), ("zero_tol", C.c_double)]
 
 
 class GcsStatus(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("diverged", C.c_int32),
-                ("inner_fail", C.c_int32), ("inner_iters", C.c_int64), ("rho", C.c_double), ("pri_res", C.c_double),
+                ("inner_fail", C.c_int32), ("inner_iters", C.c_int64), ("skipped", C.c_int64), ("rho", C.c_double), ("pri_res", C.c_double),
                 ("dual_res", C.c_double), ("eps_pri", C.c_double), ("eps_dual", C.c_double)]
 
     def as_dict(self):

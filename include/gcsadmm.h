@@ -84,6 +84,8 @@ typedef struct GcsParams {       /* literals of admm_solver_v3.py:621-651 */
     double abs_tol;              /* 1e-4 (metric "time to residual 1e-4") */
     double warm_theta;           /* interior-point warm start: previous optimum pulled this fraction towards the
                                     analytic centre (1e-3); 0 = cold start every iteration */
+    double zero_tol;             /* a vertex whose consensus targets are all <= zero_tol in magnitude gets the zero
+                                    solution without a solve (prox maps are non-expansive); 1e-12, 0 = exact zeros only */
 } GcsParams;
 
 typedef struct GcsStatus {
@@ -92,6 +94,7 @@ typedef struct GcsStatus {
     int32_t diverged;
     int32_t inner_fail;          /* vertex programs that ended above the noise-floor acceptance */
     int64_t inner_iters;         /* interior-point iterations summed over all vertex programs */
+    int64_t skipped;             /* vertex programs answered by the zero-target shortcut */
     double rho, pri_res, dual_res, eps_pri, eps_dual;
 } GcsStatus;
 
