@@ -46,6 +46,7 @@ struct GcsHandle {
     cudaStream_t stream, own_stream;
     GcsParams p;
     int nV, nE, nHown, nHghost;
+    int nP;             // independent problems packed block-diagonally (1 = a single graph)
     long long n_x, n_mu;
     int dcap, mcap;
     GcsScratchLayout L;
@@ -54,6 +55,8 @@ struct GcsHandle {
     int *poly_off, *he_off, *he_edge, *edge_he_tail, *edge_he_head;
     double *polyA, *polyb, *cent;
     unsigned char *he_flags, *vtype, *edge_counted;
+    int *vprob, *prob_eoff; long long *prob_nx, *prob_nmu;   // batched mode (nP > 1)
+    int *he_prob_host;  // host: problem of each half-edge (batched mode)
     double *xc, *mu, *z, *x_v, *z_v, *y_v;
     double *ws;         // [nV][gcs_ws_stride] interior-point warm-start records (null when warm_theta == 0)
     double *partials;   // [edge_blocks][NSUMS]
@@ -67,12 +70,13 @@ struct GcsHandle {
 
 // ------------------------------------------------------------------------------------------ K1
 __global__ void __launch_bounds__(K1_MAX_WARPS * 32)
-vertex_kernel(GcsGraphView G, GcsStateView St, Ctrl *ctrl, GcsScratchLayout L, double tol, int max_iter) {
+vertex_kernel(GcsGraphView G, GcsStateView St, Ctrl *ctrl_all, const int *__restrict__ vprob, GcsScratchLayout L, double tol, int max_iter) {
     extern __shared__ double smem[];
-    if (ctrl->stop && !ctrl->ignore_stop) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int v = blockIdx.x * (blockDim.x >> 5) + warp;
     if (v >= G.nV) return;
+    Ctrl *ctrl = ctrl_all + (vprob ? vprob[v] : 0);
+    if (ctrl->stop && !ctrl->ignore_stop) return;
     double *S = smem + (size_t)warp * L.total;
     int status = 0;
     const int iters = gcs_vertex_update(G, St, v, ctrl->rho, ctrl->mu_scale, tol, max_iter, L, S, lane, &status);
@@ -161,9 +165,7 @@ __global__ void reduce_kernel(const double *__restrict__ partials, int nblocks, 
 
 // ------------------------------------------------------------------------------------------ K5
 // reference admm_solver_v3.py:697-713 and :733, on the reduced sums
-__global__ void control_kernel(Ctrl *ctrl, GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (ctrl->stop && !ctrl->ignore_stop) return;
+__device__ void control_apply(Ctrl *ctrl, const GcsParams &p, long long n_x, long long n_mu, double *hist, int hist_cap) {
     const int it = ctrl->it + 1;
     const double *s = ctrl->sums;
     const double rho = ctrl->rho;
@@ -181,6 +183,74 @@ __global__ void control_kernel(Ctrl *ctrl, GcsParams p, long long n_x, long long
     if (s[5] != 0.0 || !isfinite(pri) || !isfinite(dual)) { ctrl->diverged = 1; ctrl->stop = 1; return; }  // :662-664
     const bool opt = p.abs_stop ? (fmax(pri, dual) < p.abs_tol) : (pri < eps_pri && dual < eps_dual);        // :712
     if (opt) { ctrl->opt = 1; ctrl->stop = 1; }
+}
+
+__global__ void control_kernel(Ctrl *ctrl, GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (ctrl->stop && !ctrl->ignore_stop) return;
+    control_apply(ctrl, p, n_x, n_mu, hist, hist_cap);
+}
+
+// ------------------------------------------------------------------------------------------ batched K2-K5
+// Independent problems packed block-diagonally (BASELINE config "batch of 4096 queries"): one block per problem
+// does that problem's edges, its own residual sums and its own rho / stop decision — no communication, and a
+// problem that has converged stops costing anything.
+#define BATCH_THREADS 128
+__global__ void __launch_bounds__(BATCH_THREADS)
+batched_edge_kernel(int nP, const int *__restrict__ prob_eoff, int nHown, const int *__restrict__ edge_he_tail,
+                    const int *__restrict__ edge_he_head, const double *__restrict__ xc, double *__restrict__ mu,
+                    double *__restrict__ z, Ctrl *ctrl_all, GcsParams p, const long long *__restrict__ prob_nx,
+                    const long long *__restrict__ prob_nmu, double *hist, int hist_cap) {
+    __shared__ double sh[BATCH_THREADS / 32][6];
+    for (int q = blockIdx.x; q < nP; q += gridDim.x) {
+        Ctrl *ctrl = ctrl_all + q;
+        if (ctrl->stop && !ctrl->ignore_stop) continue;
+        const double ms = ctrl->mu_scale;
+        double r2 = 0, dz2 = 0, x2 = 0, z2 = 0, m2 = 0, bad = 0;
+        for (int e = prob_eoff[q] + threadIdx.x; e < prob_eoff[q + 1]; e += blockDim.x) {
+            const int ht = edge_he_tail[e], hh = edge_he_head[e];
+            double xt[5], xh[5], zn[5];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) { xt[c] = xc[5 * (size_t)ht + c]; xh[c] = xc[5 * (size_t)hh + c]; }
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                const double zo = z[5 * (size_t)e + c];
+                zn[c] = 0.5 * (xt[c] + xh[c]);
+                const double dd = zn[c] - zo;
+                dz2 += dd * dd; z2 += zn[c] * zn[c];
+                z[5 * (size_t)e + c] = zn[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                const double rt = zn[c] - xt[c], mt = ms * mu[5 * (size_t)ht + c] + rt;
+                mu[5 * (size_t)ht + c] = mt; r2 += rt * rt; x2 += xt[c] * xt[c]; m2 += mt * mt;
+                const double rh = zn[c] - xh[c], mh = ms * mu[5 * (size_t)hh + c] + rh;
+                mu[5 * (size_t)hh + c] = mh; r2 += rh * rh; x2 += xh[c] * xh[c]; m2 += mh * mh;
+            }
+        }
+        if (!isfinite(r2) || !isfinite(dz2) || !isfinite(x2) || !isfinite(z2)) bad = 1.0;
+        double vals[6] = {r2, dz2, x2, z2, m2, bad};
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+#pragma unroll
+            for (int o = 16; o; o >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], o);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0)
+            for (int k = 0; k < 6; ++k) sh[warp][k] = vals[k];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < 6; ++k) {
+                double sum = 0.0;
+                for (int w2 = 0; w2 < BATCH_THREADS / 32; ++w2) sum += sh[w2][k];
+                ctrl->sums[k] = sum;
+            }
+            control_apply(ctrl, p, prob_nx[q], prob_nmu[q], hist + (size_t)q * 3 * hist_cap, hist_cap);
+        }
+        __syncthreads();
+    }
+}
+__global__ void set_ignore_kernel(Ctrl *ctrl, int nP, int v) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nP; q += gridDim.x * blockDim.x) ctrl[q].ignore_stop = v;
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -213,9 +283,13 @@ static int upload(T **dst, const T *src, size_t n) {
 static int reset_ctrl(GcsHandle *h) {
     Ctrl c; memset(&c, 0, sizeof c);
     c.rho = h->p.rho0; c.mu_scale = 1.0;
-    CK(cudaMemcpyAsync(h->ctrl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
     double first[3] = {h->p.rho0, 0.0, 0.0};   // admm_solver_v3.py:637-639: seeds of the three sequences
-    for (int q = 0; q < 3; ++q) CK(cudaMemcpyAsync(h->hist + (size_t)q * h->hist_cap, &first[q], sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    for (int q = 0; q < h->nP; ++q) {
+        h->ctrl_host[q] = c;
+        for (int k = 0; k < 3; ++k)
+            CK(cudaMemcpyAsync(h->hist + ((size_t)q * 3 + k) * h->hist_cap, &first[k], sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaMemcpyAsync(h->ctrl, h->ctrl_host, sizeof(Ctrl) * h->nP, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -224,9 +298,11 @@ extern "C" int gcsadmm_destroy(GcsHandle *h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     void *ptrs[] = {h->poly_off, h->he_off, h->he_edge, h->edge_he_tail, h->edge_he_head, h->polyA, h->polyb, h->cent,
-                    h->he_flags, h->vtype, h->edge_counted, h->xc, h->mu, h->z, h->x_v, h->z_v, h->y_v, h->ws, h->partials, h->hist, h->ctrl};
+                    h->he_flags, h->vtype, h->edge_counted, h->xc, h->mu, h->z, h->x_v, h->z_v, h->y_v, h->ws, h->partials, h->hist, h->ctrl,
+                    h->vprob, h->prob_eoff, h->prob_nx, h->prob_nmu};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
+    free(h->he_prob_host);
     if (h->flush_buf) cudaFree(h->flush_buf);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -250,6 +326,8 @@ extern "C" int gcsadmm_create(const GcsGraph *g, const GcsParams *p, int device,
     if (p) h->p = *p; else gcsadmm_default_params(&h->p);
     if (h->p.check_every < 1) h->p.check_every = 1;
     h->nV = g->nV; h->nE = g->nE; h->nHown = g->nH_own; h->nHghost = g->nH_ghost;
+    h->nP = g->nP > 1 ? g->nP : 1;
+    if (h->nP > 1 && (g->nH_ghost > 0 || !g->prob_voff || !g->prob_eoff)) { delete h; return set_err(GCS_E_INVALID, "batched problems need prob_voff / prob_eoff and cannot be vertex-partitioned%s", ""); }
     h->n_x = g->n_x_global ? g->n_x_global : 9LL * g->nV + 18LL * g->nE;
     h->n_mu = g->n_mu_global ? g->n_mu_global : 10LL * g->nE;
     // capacity of a vertex program: live degree and polytope rows
@@ -299,11 +377,30 @@ extern "C" int gcsadmm_create(const GcsGraph *g, const GcsParams *p, int device,
     if (h->p.warm_theta > 0.0) UP(ws, (const double *)nullptr, (size_t)g->nV * gcs_ws_stride(h->L));
     UP(partials, (const double *)nullptr, (size_t)h->edge_blocks * NSUMS);
     h->hist_cap = h->p.max_it + 2;
-    UP(hist, (const double *)nullptr, 3 * (size_t)h->hist_cap);
+    UP(hist, (const double *)nullptr, 3 * (size_t)h->hist_cap * h->nP);
 #undef UP
     if (rc) { gcsadmm_destroy(h); return rc; }
-    CK(cudaMalloc((void **)&h->ctrl, sizeof(Ctrl)));
-    CK(cudaMallocHost((void **)&h->ctrl_host, sizeof(Ctrl)));
+    CK(cudaMalloc((void **)&h->ctrl, sizeof(Ctrl) * h->nP));
+    CK(cudaMallocHost((void **)&h->ctrl_host, sizeof(Ctrl) * h->nP));
+    if (h->nP > 1) {   // per-problem maps: vertex -> problem, edge ranges, len(x_global) / len(mu_global) of each problem
+        int *vp = (int *)malloc(sizeof(int) * g->nV);
+        long long *nx = (long long *)malloc(sizeof(long long) * h->nP), *nm = (long long *)malloc(sizeof(long long) * h->nP);
+        h->he_prob_host = (int *)malloc(sizeof(int) * (size_t)(g->nH_own > 0 ? g->nH_own : 1));
+        for (int q = 0; q < h->nP; ++q) {
+            for (int v = g->prob_voff[q]; v < g->prob_voff[q + 1]; ++v) {
+                vp[v] = q;
+                for (int hh = g->he_off[v]; hh < g->he_off[v + 1]; ++hh) h->he_prob_host[hh] = q;
+            }
+            const long long nv = g->prob_voff[q + 1] - g->prob_voff[q], ne = g->prob_eoff[q + 1] - g->prob_eoff[q];
+            nx[q] = 9 * nv + 18 * ne; nm[q] = 10 * ne;
+        }
+        rc = upload(&h->vprob, vp, (size_t)g->nV);
+        if (!rc) rc = upload(&h->prob_eoff, g->prob_eoff, (size_t)h->nP + 1);
+        if (!rc) rc = upload(&h->prob_nx, nx, (size_t)h->nP);
+        if (!rc) rc = upload(&h->prob_nmu, nm, (size_t)h->nP);
+        free(vp); free(nx); free(nm);
+        if (rc) { gcsadmm_destroy(h); return rc; }
+    }
     for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&h->ev[i]));
     rc = reset_ctrl(h);
     if (rc) { gcsadmm_destroy(h); return rc; }
@@ -330,33 +427,60 @@ static GcsStateView state_view(const GcsHandle *h) {
     return S;
 }
 static int launch_k1(GcsHandle *h) {
-    vertex_kernel<<<h->k1_blocks, h->k1_warps * 32, h->k1_smem, h->stream>>>(graph_view(h), state_view(h), h->ctrl, h->L, h->p.inner_tol, h->p.inner_max_iter);
+    vertex_kernel<<<h->k1_blocks, h->k1_warps * 32, h->k1_smem, h->stream>>>(graph_view(h), state_view(h), h->ctrl, h->vprob, h->L, h->p.inner_tol, h->p.inner_max_iter);
     return 0;
 }
 static int launch_edge(GcsHandle *h) {
+    if (h->nP > 1) {   // edges, sums and control of every problem in one launch
+        const int blocks = h->nP < 148 * 16 ? h->nP : 148 * 16;
+        batched_edge_kernel<<<blocks, BATCH_THREADS, 0, h->stream>>>(h->nP, h->prob_eoff, h->nHown, h->edge_he_tail, h->edge_he_head, h->xc, h->mu, h->z,
+                                                                     h->ctrl, h->p, h->prob_nx, h->prob_nmu, h->hist, h->hist_cap);
+        return 0;
+    }
     edge_kernel<<<h->edge_blocks, EDGE_THREADS, 0, h->stream>>>(h->nE, h->nHown, h->edge_he_tail, h->edge_he_head, h->edge_counted, h->xc, h->mu, h->z, h->ctrl, h->partials);
     reduce_kernel<<<1, 256, 0, h->stream>>>(h->partials, h->edge_blocks, h->ctrl);
     return 0;
 }
 static int launch_ctrl(GcsHandle *h) {
+    if (h->nP > 1) return 0;   // fused into batched_edge_kernel
     control_kernel<<<1, 32, 0, h->stream>>>(h->ctrl, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap);
     return 0;
 }
 static int set_ignore_stop(GcsHandle *h, int v) {
+    if (h->nP > 1) { set_ignore_kernel<<<(h->nP + 255) / 256, 256, 0, h->stream>>>(h->ctrl, h->nP, v); return 0; }
     CK(cudaMemcpyAsync((char *)h->ctrl + offsetof(Ctrl, ignore_stop), &v, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     return 0;
 }
 static int fetch_ctrl(GcsHandle *h) {
-    CK(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(Ctrl) * h->nP, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
     return 0;
 }
-static void fill_status(const GcsHandle *h, GcsStatus *st) {
-    const Ctrl *c = h->ctrl_host;
+static void fill_status_one(const Ctrl *c, GcsStatus *st) {
     st->iterations = c->it; st->converged = c->opt; st->diverged = c->diverged; st->inner_fail = c->inner_fail;
     st->inner_iters = (int64_t)c->inner_iters; st->skipped = (int64_t)c->skipped; st->rho = c->rho; st->pri_res = c->pri; st->dual_res = c->dual;
     st->eps_pri = c->eps_pri; st->eps_dual = c->eps_dual;
+}
+// batched handles: iterations = max, converged = all, residuals = worst problem, counters summed
+static void fill_status(const GcsHandle *h, GcsStatus *st) {
+    fill_status_one(h->ctrl_host, st);
+    for (int q = 1; q < h->nP; ++q) {
+        GcsStatus t; fill_status_one(h->ctrl_host + q, &t);
+        if (t.iterations > st->iterations) st->iterations = t.iterations;
+        st->converged = st->converged && t.converged; st->diverged = st->diverged || t.diverged;
+        st->inner_fail += t.inner_fail; st->inner_iters += t.inner_iters; st->skipped += t.skipped;
+        if (t.pri_res > st->pri_res) { st->pri_res = t.pri_res; st->eps_pri = t.eps_pri; }
+        if (t.dual_res > st->dual_res) { st->dual_res = t.dual_res; st->eps_dual = t.eps_dual; }
+    }
+}
+static bool all_stopped(const GcsHandle *h) {
+    for (int q = 0; q < h->nP; ++q) if (!h->ctrl_host[q].stop) return false;
+    return true;
+}
+static bool any_diverged(const GcsHandle *h) {
+    for (int q = 0; q < h->nP; ++q) if (h->ctrl_host[q].diverged) return true;
+    return false;
 }
 
 extern "C" int gcsadmm_vertex_update(GcsHandle *h) { if (!h) return set_err(GCS_E_INVALID, "null handle%s", ""); CK(cudaSetDevice(h->device)); launch_k1(h); CK(cudaGetLastError()); return 0; }
@@ -380,7 +504,7 @@ extern "C" int gcsadmm_run(GcsHandle *h, int max_iters, GcsStatus *st) {
     CK(cudaSetDevice(h->device));
     int rc = fetch_ctrl(h); if (rc) return rc;
     int done = 0;
-    while (done < max_iters && !h->ctrl_host->stop) {
+    while (done < max_iters && !all_stopped(h)) {
         int chunk = h->p.check_every;
         if (chunk > max_iters - done) chunk = max_iters - done;
         for (int i = 0; i < chunk; ++i) { launch_k1(h); launch_edge(h); launch_ctrl(h); }
@@ -389,7 +513,7 @@ extern "C" int gcsadmm_run(GcsHandle *h, int max_iters, GcsStatus *st) {
         done += chunk;
     }
     if (st) fill_status(h, st);
-    if (h->ctrl_host->diverged) return set_err(GCS_E_DIVERGED, "non-finite residuals (divergence)%s", "");
+    if (any_diverged(h)) return set_err(GCS_E_DIVERGED, "non-finite residuals (divergence)%s", "");
     return 0;
 }
 
@@ -401,6 +525,24 @@ extern "C" int gcsadmm_get_status(GcsHandle *h, GcsStatus *st) {
     return 0;
 }
 
+extern "C" int gcsadmm_get_problem_status(GcsHandle *h, int problem, GcsStatus *st) {
+    if (!h || !st || problem < 0 || problem >= h->nP) return set_err(GCS_E_INVALID, "bad argument%s", "");
+    CK(cudaSetDevice(h->device));
+    int rc = fetch_ctrl(h); if (rc) return rc;
+    fill_status_one(h->ctrl_host + problem, st);
+    return 0;
+}
+extern "C" int gcsadmm_get_problem_history(GcsHandle *h, int problem, double *rho, double *pri, double *dual, int cap) {
+    if (!h || problem < 0 || problem >= h->nP) return set_err(GCS_E_INVALID, "bad argument%s", "");
+    CK(cudaSetDevice(h->device));
+    int rc = fetch_ctrl(h); if (rc) return rc;
+    int n = h->ctrl_host[problem].it + 1;
+    if (n > h->hist_cap) n = h->hist_cap;
+    if (n > cap) n = cap;
+    double *dst[3] = {rho, pri, dual};
+    for (int k = 0; k < 3; ++k) if (dst[k]) CK(cudaMemcpy(dst[k], h->hist + ((size_t)problem * 3 + k) * h->hist_cap, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return n;
+}
 extern "C" int gcsadmm_get_history(GcsHandle *h, double *rho, double *pri, double *dual, int cap) {
     if (!h) return set_err(GCS_E_INVALID, "null handle%s", "");
     CK(cudaSetDevice(h->device));
@@ -431,8 +573,8 @@ extern "C" int gcsadmm_get_state(GcsHandle *h, double *xc, double *mu, double *z
     if (xc) CK(cudaMemcpy(xc, h->xc, sizeof(double) * 5 * ((size_t)h->nHown + h->nHghost), cudaMemcpyDeviceToHost));
     if (mu) {   // stored duals carry a pending rho-adaptation rescale: return the effective values
         CK(cudaMemcpy(mu, h->mu, sizeof(double) * 5 * (size_t)h->nHown, cudaMemcpyDeviceToHost));
-        const double s = h->ctrl_host->mu_scale;
-        if (s != 1.0) for (size_t i = 0; i < 5 * (size_t)h->nHown; ++i) mu[i] *= s;
+        if (h->nP > 1) { for (size_t hh = 0; hh < (size_t)h->nHown; ++hh) { const double s = h->ctrl_host[h->he_prob_host[hh]].mu_scale; if (s != 1.0) for (int c = 0; c < 5; ++c) mu[5 * hh + c] *= s; } }
+        else { const double s = h->ctrl_host->mu_scale; if (s != 1.0) for (size_t i = 0; i < 5 * (size_t)h->nHown; ++i) mu[i] *= s; }
     }
     if (z) CK(cudaMemcpy(z, h->z, sizeof(double) * 5 * (size_t)h->nE, cudaMemcpyDeviceToHost));
     if (rho) *rho = h->ctrl_host->rho;
@@ -447,9 +589,8 @@ extern "C" int gcsadmm_set_state(GcsHandle *h, const double *xc, const double *m
     if (xc) CK(cudaMemcpy(h->xc, xc, sizeof(double) * 5 * ((size_t)h->nHown + h->nHghost), cudaMemcpyHostToDevice));
     if (mu) CK(cudaMemcpy(h->mu, mu, sizeof(double) * 5 * (size_t)h->nHown, cudaMemcpyHostToDevice));
     if (z) CK(cudaMemcpy(h->z, z, sizeof(double) * 5 * (size_t)h->nE, cudaMemcpyHostToDevice));
-    Ctrl c = *h->ctrl_host;
-    c.rho = rho; c.it = it; c.mu_scale = 1.0; c.stop = 0; c.opt = 0; c.diverged = 0;
-    CK(cudaMemcpy(h->ctrl, &c, sizeof c, cudaMemcpyHostToDevice));
+    for (int q = 0; q < h->nP; ++q) { Ctrl &c = h->ctrl_host[q]; c.rho = rho; c.it = it; c.mu_scale = 1.0; c.stop = 0; c.opt = 0; c.diverged = 0; }
+    CK(cudaMemcpy(h->ctrl, h->ctrl_host, sizeof(Ctrl) * h->nP, cudaMemcpyHostToDevice));
     return 0;
 }
 

@@ -25,7 +25,7 @@ import numpy as np
 
 __all__ = [
     "convert_pt_to_polytope", "delta", "polygon_vertices", "build_graph",
-    "pack_polytopes", "build_graph_packed", "PackedGraph", "pack_graph",
+    "pack_polytopes", "build_graph_packed", "PackedGraph", "pack_graph", "pack_batch",
 ]
 
 OVERLAP_TOL = 1e-9
@@ -311,7 +311,10 @@ class PackedGraph:
         self.polyb = np.ascontiguousarray(b, dtype=np.float64)
         self.edge_tail = tail.astype(np.int32)
         self.edge_head = head.astype(np.int32)
-        self.src, self.dst = int(src), int(dst)
+        # one (src, dst) pair for a single graph, arrays for block-diagonally packed independent problems
+        self.srcs = np.atleast_1d(np.asarray(src, dtype=np.int64))
+        self.dsts = np.atleast_1d(np.asarray(dst, dtype=np.int64))
+        self.src, self.dst = int(self.srcs[0]), int(self.dsts[0])
         # per vertex: incoming edges (in edge order) then outgoing edges
         eid = np.arange(nE, dtype=np.int64)
         owner = np.concatenate([head, tail])
@@ -345,24 +348,22 @@ class PackedGraph:
         nV, H = self.nV, 2 * self.nE
         owner, out = self.he_owner.astype(np.int64), self.he_out.astype(bool)
         zero = np.zeros(H, dtype=bool)
-        if self.src >= 0:
-            zero |= (owner == self.src) & ~out
-        if self.dst >= 0:
-            zero |= (owner == self.dst) & out
+        is_src = np.zeros(nV, dtype=bool); is_src[self.srcs[self.srcs >= 0]] = True
+        is_dst = np.zeros(nV, dtype=bool); is_dst[self.dsts[self.dsts >= 0]] = True
+        zero |= is_src[owner] & ~out
+        zero |= is_dst[owner] & out
         live_in = np.bincount(owner[~out & ~zero], minlength=nV)
         live_out = np.bincount(owner[out & ~zero], minlength=nV)
-        vid = np.arange(nV)
-        dead = ((vid != self.src) & (live_in == 0)) | ((vid != self.dst) & (live_out == 0))
+        dead = (~is_src & (live_in == 0)) | (~is_dst & (live_out == 0))
         zero |= dead[owner]
         vtype = np.zeros(nV, dtype=np.uint8)
-        if self.src >= 0:
-            vtype[self.src] = 1
-        if self.dst >= 0:
-            vtype[self.dst] = 2
+        vtype[is_src] = 1
+        vtype[is_dst] = 2
         vtype[dead] = 3
-        for t, name in ((self.src, "source has no outgoing edge"), (self.dst, "target has no incoming edge")):
-            if t >= 0 and dead[t]:
-                raise ValueError(f"infeasible problem: {name}")
+        if np.any(dead & is_src):
+            raise ValueError("infeasible problem: source has no outgoing edge")
+        if np.any(dead & is_dst):
+            raise ValueError("infeasible problem: target has no incoming edge")
         self.he_flags = (out.astype(np.uint8) | (zero.astype(np.uint8) << 1)).astype(np.uint8)
         self.vtype = vtype
         live_deg = np.bincount(owner[~zero], minlength=nV)
@@ -393,3 +394,25 @@ def pack_graph(As, bs, V=None, E=None):
     tail = np.array([index[e[0]] for e in E], dtype=np.int64)
     head = np.array([index[e[1]] for e in E], dtype=np.int64)
     return PackedGraph(off, A, b, tail, head, index.get('s', -1), index.get('t', -1), keys=V)
+
+
+def pack_batch(graphs):
+    """Block-diagonal packing of independent problems (BASELINE config "batch of 4096 start/goal queries").
+
+    ``graphs``: list of PackedGraph (one per query).  Vertices, edges and half-edges of problem p stay
+    contiguous (``prob_voff``, ``prob_eoff``); the library then keeps residuals, rho and the stop decision per
+    problem and needs no communication between them."""
+    voff = np.concatenate([[0], np.cumsum([g.nV for g in graphs])]).astype(np.int64)
+    eoff = np.concatenate([[0], np.cumsum([g.nE for g in graphs])]).astype(np.int64)
+    roff = np.concatenate([[0], np.cumsum([int(g.poly_off[-1]) for g in graphs])]).astype(np.int64)
+    off = np.concatenate([[0]] + [g.poly_off[1:].astype(np.int64) + roff[i] for i, g in enumerate(graphs)])
+    A = np.concatenate([g.polyA for g in graphs])
+    b = np.concatenate([g.polyb for g in graphs])
+    tail = np.concatenate([g.edge_tail.astype(np.int64) + voff[i] for i, g in enumerate(graphs)])
+    head = np.concatenate([g.edge_head.astype(np.int64) + voff[i] for i, g in enumerate(graphs)])
+    srcs = np.array([g.src + voff[i] if g.src >= 0 else -1 for i, g in enumerate(graphs)], dtype=np.int64)
+    dsts = np.array([g.dst + voff[i] if g.dst >= 0 else -1 for i, g in enumerate(graphs)], dtype=np.int64)
+    big = PackedGraph(off, A, b, tail, head, srcs, dsts)
+    big.prob_voff = voff.astype(np.int32)
+    big.prob_eoff = eoff.astype(np.int32)
+    return big

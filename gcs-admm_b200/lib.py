@@ -20,7 +20,7 @@ EXPORTS = [
     "gcsadmm_get_status", "gcsadmm_vertex_update", "gcsadmm_edge_update", "gcsadmm_control",
     "gcsadmm_sums_device_ptr", "gcsadmm_xc_device_ptr", "gcsadmm_get_history", "gcsadmm_get_solution",
     "gcsadmm_get_state", "gcsadmm_set_state", "gcsadmm_time_steps", "gcsadmm_solve_host",
-    "gcsadmm_scratch_bytes", "gcsadmm_flush_l2",
+    "gcsadmm_scratch_bytes", "gcsadmm_flush_l2", "gcsadmm_get_problem_status", "gcsadmm_get_problem_history",
 ]
 
 
@@ -30,7 +30,8 @@ class GcsGraph(C.Structure):
                 ("he_off", C.c_void_p), ("he_edge", C.c_void_p), ("he_flags", C.c_void_p),
                 ("edge_he_tail", C.c_void_p), ("edge_he_head", C.c_void_p), ("edge_counted", C.c_void_p),
                 ("vtype", C.c_void_p), ("cent", C.c_void_p),
-                ("n_x_global", C.c_int64), ("n_mu_global", C.c_int64)]
+                ("n_x_global", C.c_int64), ("n_mu_global", C.c_int64),
+                ("nP", C.c_int32), ("prob_voff", C.c_void_p), ("prob_eoff", C.c_void_p)]
 
 
 class GcsParams(C.Structure):
@@ -75,6 +76,8 @@ def load():
     L.gcsadmm_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(GcsStatus)]
     L.gcsadmm_step.argtypes = [C.c_void_p, C.c_int]
     L.gcsadmm_get_status.argtypes = [C.c_void_p, C.POINTER(GcsStatus)]
+    L.gcsadmm_get_problem_status.argtypes = [C.c_void_p, C.c_int, C.POINTER(GcsStatus)]
+    L.gcsadmm_get_problem_history.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     for f in ("gcsadmm_vertex_update", "gcsadmm_edge_update", "gcsadmm_control"):
         getattr(L, f).argtypes = [C.c_void_p]
     L.gcsadmm_sums_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
@@ -139,6 +142,14 @@ def graph_struct(g):
     for k in ("poly_off", "polyA", "polyb", "he_off", "he_edge", "he_flags", "edge_he_tail", "edge_he_head", "vtype", "cent"):
         setattr(s, k, _ptr(keep[k]))
     s.edge_counted = _ptr(keep.get("edge_counted"))
+    pv = getattr(g, "prob_voff", None)
+    if pv is not None and len(pv) > 2:
+        keep["prob_voff"] = np.ascontiguousarray(pv, np.int32)
+        keep["prob_eoff"] = np.ascontiguousarray(g.prob_eoff, np.int32)
+        s.nP = len(pv) - 1
+        s.prob_voff, s.prob_eoff = _ptr(keep["prob_voff"]), _ptr(keep["prob_eoff"])
+    else:
+        s.nP = 1
     s.n_x_global = int(getattr(g, "n_x_global", 0))
     s.n_mu_global = int(getattr(g, "n_mu_global", 0))
     return s, keep
@@ -179,6 +190,17 @@ class Solver:
         st = GcsStatus()
         _check(load().gcsadmm_get_status(self._h, C.byref(st)))
         return st.as_dict()
+
+    def problem_status(self, p):
+        st = GcsStatus()
+        _check(load().gcsadmm_get_problem_status(self._h, int(p), C.byref(st)))
+        return st.as_dict()
+
+    def problem_history(self, p):
+        cap = self.params.max_it + 2
+        rho, pri, dual = np.zeros(cap), np.zeros(cap), np.zeros(cap)
+        n = _check(load().gcsadmm_get_problem_history(self._h, int(p), _ptr(rho), _ptr(pri), _ptr(dual), cap))
+        return rho[:n].copy(), pri[:n].copy(), dual[:n].copy()
 
     def vertex_update(self):
         _check(load().gcsadmm_vertex_update(self._h))

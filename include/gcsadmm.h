@@ -68,6 +68,12 @@ typedef struct GcsGraph {
     const double *cent;          /* [nV][2] a strictly interior point of each polytope */
     int64_t n_x_global;          /* len(x_global) = 9|V| + 18|E| of the WHOLE graph (0: derive from nV, nE) */
     int64_t n_mu_global;         /* len(mu_global) = 10|E| of the whole graph (0: derive) */
+    /* independent problems packed block-diagonally (batched queries): vertices / edges of problem p are the
+     * contiguous ranges prob_voff[p]..prob_voff[p+1], prob_eoff[p]..prob_eoff[p+1]; each problem keeps its own
+     * residuals, rho and stop decision.  nP <= 1: a single graph (pointers may be NULL). */
+    int32_t nP;
+    const int32_t *prob_voff;    /* [nP+1] */
+    const int32_t *prob_eoff;    /* [nP+1] */
 } GcsGraph;
 
 typedef struct GcsParams {       /* literals of admm_solver_v3.py:621-651 */
@@ -112,7 +118,8 @@ int gcsadmm_set_stream(GcsHandle *h, void *cuda_stream, int external);
 /* whole iterations */
 int gcsadmm_run(GcsHandle *h, int max_iters, GcsStatus *st);   /* until the stop rule fires or max_iters passes */
 int gcsadmm_step(GcsHandle *h, int k);                         /* exactly k passes, stop rule evaluated but ignored */
-int gcsadmm_get_status(GcsHandle *h, GcsStatus *st);
+int gcsadmm_get_status(GcsHandle *h, GcsStatus *st);            /* batched handle: worst residuals, max iterations, all-converged */
+int gcsadmm_get_problem_status(GcsHandle *h, int problem, GcsStatus *st);
 
 /* the individual kernels (per-kernel parity tests, multi-GPU driver) */
 int gcsadmm_vertex_update(GcsHandle *h);                       /* K1 */
@@ -123,6 +130,7 @@ int gcsadmm_xc_device_ptr(GcsHandle *h, void **dev_ptr);       /* [(nH_own + nH_
 
 /* results */
 int gcsadmm_get_history(GcsHandle *h, double *rho_seq, double *pri_seq, double *dual_seq, int cap); /* returns count or <0 */
+int gcsadmm_get_problem_history(GcsHandle *h, int problem, double *rho_seq, double *pri_seq, double *dual_seq, int cap);
 int gcsadmm_get_solution(GcsHandle *h, double *x_v, double *z_v, double *y_v, double *z_e);         /* any may be NULL */
 int gcsadmm_get_state(GcsHandle *h, double *xc, double *mu, double *z, double *rho, int *it);
 int gcsadmm_set_state(GcsHandle *h, const double *xc, const double *mu, const double *z, double rho, int it);

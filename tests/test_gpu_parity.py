@@ -109,3 +109,30 @@ def test_rejects_bad_input():
     h = C.c_void_p()
     rc = lib.load().gcsadmm_create(C.byref(gs), None, 0, C.byref(h))
     assert rc == -1 and b"n = 2" in lib.load().gcsadmm_last_error()
+
+
+def test_batched_queries_equal_individual_solves():
+    """Block-diagonal batch (BASELINE config 4 in miniature): every problem keeps its own residuals / stop
+    iteration and reproduces its stand-alone run bit for bit."""
+    from gcs_admm_b200.graph import pack_batch
+    names = ["benchmark1", "benchmark2", "test3", "benchmark1", "test_autogen1"]
+    graphs = [pack_graph(*load_golden(n)[:2]) for n in names]
+    big = pack_batch(graphs)
+    sb = _solver(big)
+    stb = sb.run()
+    x_v, z_v, y_v, z_e = sb.solution()
+    assert stb["converged"]
+    for p, (n, g) in enumerate(zip(names, graphs)):
+        s = _solver(g)
+        st = s.run()
+        ps = sb.problem_status(p)
+        assert ps["iterations"] == st["iterations"] and ps["converged"] == st["converged"]
+        r1, p1, d1 = s.history()
+        r2, p2, d2 = sb.problem_history(p)
+        assert np.array_equal(p1, p2) and np.array_equal(d1, d2) and np.array_equal(r1, r2)
+        xs, zs, ys, es = s.solution()
+        v0, v1, e0, e1 = big.prob_voff[p], big.prob_voff[p + 1], big.prob_eoff[p], big.prob_eoff[p + 1]
+        assert np.array_equal(zs, z_v[v0:v1]) and np.array_equal(ys, y_v[v0:v1]) and np.array_equal(es, z_e[e0:e1])
+        s.close()
+    assert stb["iterations"] == max(GOLD["benchmark1"], GOLD["benchmark2"], sb.problem_status(2)["iterations"], sb.problem_status(4)["iterations"])
+    sb.close()
