@@ -26,6 +26,7 @@
 
 #ifdef GCS_EMULATE
 #define GCS_DEV static inline
+#define GCS_DEV_NI static inline
 #define GCS_LANE_LOOP(i, n) for (int i = 0; i < (n); ++i)
 #define GCS_SYNC() ((void)0)
 static inline double gcs_warp_sum(double x) { return x; }
@@ -33,6 +34,7 @@ static inline double gcs_warp_max(double x) { return x; }
 static inline double gcs_warp_min(double x) { return x; }
 #else
 #define GCS_DEV __device__ __forceinline__
+#define GCS_DEV_NI __device__ __noinline__   // called several times per iteration: one copy keeps the kernel in the I-cache
 #define GCS_LANE_LOOP(i, n) for (int i = lane; i < (n); i += 32)
 #define GCS_SYNC() __syncwarp()
 __device__ __forceinline__ double gcs_warp_sum(double x) {
@@ -153,7 +155,7 @@ GCS_DEV int gcs_uw(int j) { return GCS_NCORE + 5 * j; }   // u-space offset of l
 
 // ---- the null-space map ---------------------------------------------------------------------
 // forward:  u = N v (+ up when `affine`)
-GCS_DEV void gcs_forward(const double *v, double *u, int d, int jstar, const int *prim, bool term, bool affine, int lane) {
+GCS_DEV_NI void gcs_forward(const double *v, double *u, int d, int jstar, const int *prim, bool term, bool affine, int lane) {
     GCS_LANE_LOOP(c, 5) {
         if (c < 4) u[GCS_UX + c] = v[c]; else u[GCS_UT] = v[4];
     }
@@ -174,7 +176,7 @@ GCS_DEV void gcs_forward(const double *v, double *u, int d, int jstar, const int
     GCS_SYNC();
 }
 // adjoint:  out = N' g
-GCS_DEV void gcs_adjoint(const double *g, double *out, int d, int jstar, const int *prim, bool term, int lane) {
+GCS_DEV_NI void gcs_adjoint(const double *g, double *out, int d, int jstar, const int *prim, bool term, int lane) {
     GCS_LANE_LOOP(c, 5) {
         if (c < 4) out[c] = g[GCS_UX + c] + (term ? g[GCS_UZ + c] + g[gcs_uw(jstar) + c] : 0.0); else out[4] = g[GCS_UT];
     }
@@ -317,7 +319,7 @@ GCS_DEV void gcs_rows(const GcsScratchLayout &L, double *S, int m, int d, bool t
 
 // gradient-like vector from the records:  gout = sign * G'w (+ the singles' signed terms)
 //   a_i / z_i slots:  wA(C3|C1) - wA(C4|C2);   y / y_v slots:  -wb(C3|C1) + wb(C4|C2);   x_i: sum over blocks of wA(C4|C2)
-GCS_DEV void gcs_fold(const GcsScratchLayout &L, double *S, int d, bool term, double *gout, double sign, int lane) {
+GCS_DEV_NI void gcs_fold(const GcsScratchLayout &L, double *S, int d, bool term, double *gout, double sign, int lane) {
     const double *ep = S + L.ep, *sy = S + L.sy;
     GCS_LANE_LOOP(q, 4 * (d + 1)) {
         const int blk = q >> 2, i = (q >> 1) & 1, c = q & 1;
@@ -437,7 +439,7 @@ GCS_DEV void gcs_cholesky(double *H, int nb, const double *diag0, double *Linv, 
     }
 }
 // x <- (L L')^-1 x   (y: scratch of n doubles)
-GCS_DEV void gcs_chol_solve(const double *__restrict__ H, int nb, const double *__restrict__ Linv, double *__restrict__ x, double *__restrict__ y, int lane) {
+GCS_DEV_NI void gcs_chol_solve(const double *__restrict__ H, int nb, const double *__restrict__ Linv, double *__restrict__ x, double *__restrict__ y, int lane) {
     const int n = 5 * nb;
     for (int b = 0; b < nb; ++b) {          // forward: L y = x
         const int o = 5 * b;

@@ -1,0 +1,78 @@
+"""BASELINE config 4: a batch of independent start/goal queries on the benchmark4 region set.
+
+    python tools/batch_queries.py --queries 4096 [--gpus N via torchrun: each rank takes queries rank::world]
+
+Every query is the 40 benchmark4 regions plus its own (s, t) drawn by rejection sampling inside two distinct
+random regions (np.random.default_rng(1)); queries are packed block-diagonally (gcs_admm_b200.graph.pack_batch)
+and solved in one handle per GPU with per-problem residuals / rho / stop — no communication.
+Prints one JSON line: problems/s, aggregate ADMM iterations/s, iteration statistics.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import utils  # noqa: E402,F401
+from gcs_admm_b200.graph import convert_pt_to_polytope, pack_batch, pack_graph  # noqa: E402
+from gcs_admm_b200.problem_io import load_test_file  # noqa: E402
+
+
+def make_queries(n, seed=1):
+    As, bs, _ = load_test_file("benchmark4")
+    regions = [k for k in As if not isinstance(k, str)]
+    lo = np.min([np.min(bs[k]) for k in regions]) * 0 - 25.0
+    hi = 25.0
+    rng = np.random.default_rng(seed)
+
+    def sample(k):
+        A, b = As[k], bs[k]
+        while True:
+            p = rng.uniform(lo, hi, size=2)
+            if np.all(A @ p <= b - 1e-3):
+                return p
+    out = []
+    for _ in range(n):
+        a, c = rng.choice(len(regions), size=2, replace=False)
+        s, t = sample(regions[a]), sample(regions[c])
+        Aq, bq = dict(As), dict(bs)
+        Aq["s"], bq["s"] = convert_pt_to_polytope(s)
+        Aq["t"], bq["t"] = convert_pt_to_polytope(t)
+        out.append((Aq, bq))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--queries", type=int, default=4096)
+    ap.add_argument("--max-it", type=int, default=1000)
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from gcs_admm_b200 import lib
+    t0 = time.perf_counter()
+    qs = make_queries(args.queries)[rank::world]
+    graphs = [pack_graph(A, b) for A, b in qs]
+    big = pack_batch(graphs)
+    t_build = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    s = lib.Solver(big, device=local, max_it=args.max_it, check_every=16)
+    st = s.run(args.max_it)
+    x_v, z_v, y_v, z_e = s.solution()
+    dt = time.perf_counter() - t0
+    its = np.array([s.problem_status(p)["iterations"] for p in range(len(graphs))])
+    conv = np.array([s.problem_status(p)["converged"] for p in range(len(graphs))])
+    line = {"rank": rank, "world": world, "queries": len(graphs), "vertices": int(big.nV), "edges": int(big.nE),
+            "host_build_s": t_build, "solve_s": dt, "problems_per_s": len(graphs) / dt,
+            "aggregate_problem_iterations_per_s": float(its.sum()) / dt, "converged": int(conv.sum()),
+            "iterations_min_median_max": [int(its.min()), int(np.median(its)), int(its.max())],
+            "inner_fail": st["inner_fail"], "inner_iters": st["inner_iters"]}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()
