@@ -175,6 +175,13 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     k1_ms = k1 / args.steps
+    traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch, from the committed ncu capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
+        if tj.get("workload") == f"grid{args.grid}x{args.grid}":
+            traffic = tj["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": W,
@@ -190,7 +197,8 @@ def main():
                 "note": "gcsadmm_solve_host from a cold start: graph upload + (burn_in + K) iterations + solution/history download, wall clock; value = (burn_in + K) / time"},
         "gpu_launches": 4 * args.steps,
         "roofline": {"bound": "hbm", "kernel": "vertex_kernel (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                     "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                     "traffic_note": "ncu --set full capture (profiles/r01_k1_grid316_ncu_summary.txt); includes the 2.7 KB/vertex warm-start records K1 reads and rewrites",
                      "algorithmic_bytes_per_launch": k1_bytes, "kernel_ms": k1_ms,
                      "whole_iteration": {"bytes": k1_bytes + k2_bytes, "achieved": (k1_bytes + k2_bytes) / (ms * 1e-3) / 1e9,
                                          "frac": (k1_bytes + k2_bytes) / (ms * 1e-3) / 1e9 / peak},
@@ -199,7 +207,7 @@ def main():
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(min(args.grid, 48), g.nV)
     if args.residual_run:
-        s2 = lib.Solver(g, device=0, max_it=args.residual_run, abs_stop=1, abs_tol=1e-4, check_every=16)
+        s2 = lib.Solver(g, device=0, max_it=args.residual_run, abs_stop=1, abs_tol=1e-4, check_every=64)
         t0 = time.perf_counter()
         st2 = s2.run(args.residual_run)
         line["time_to_residual_1e-4"] = {"seconds": time.perf_counter() - t0, "iterations": st2["iterations"], "reached": bool(st2["converged"]),

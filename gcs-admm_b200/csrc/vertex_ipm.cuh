@@ -230,23 +230,25 @@ GCS_DEV void gcs_rows(const GcsScratchLayout &L, double *S, int m, int d, bool t
         double ph = 0, pp0 = 0, pp1 = 0, dh = 0, dp0 = 0, dp1 = 0;
         if (need_p) { ph = fam ? -dua[yo] : dua[yo]; pp0 = fam ? dua[xo] - dua[po] : dua[po]; pp1 = fam ? dua[xo + 1] - dua[po + 1] : dua[po + 1]; }
         if (need_d) { dh = fam ? -du[yo] : du[yo]; dp0 = fam ? du[xo] - du[po] : du[po]; dp1 = fam ? du[xo + 1] - du[po + 1] : du[po + 1]; }
-        double *__restrict__ zr = S + L.zr + slot * m, *__restrict__ wr = S + L.wr + slot * m;
+        // row-major over k, slot-minor: lanes (= slots) touch consecutive doubles, no shared-memory bank conflicts
+        const int NS = 4 * (L.dcap + 1);
+        double *__restrict__ zr = S + L.zr + slot, *__restrict__ wr = S + L.wr + slot;
         double s_aa0 = 0, s_aa1 = 0, s_aa2 = 0, s_ba0 = 0, s_ba1 = 0, s_bb = 0, w_a0 = 0, w_a1 = 0, w_b = 0;
         for (int k = 0; k < m; ++k) {
             const double A0 = A[2 * k], A1 = A[2 * k + 1], bk = b[k];
             const double sl = h0 * bk - (A0 * p0 + A1 * p1);
-            if (mode == 6) { zr[k] = sl; acc_sum += sl; acc_cnt += 1.0; continue; }
-            const double z = zr[k];
+            if (mode == 6) { zr[k * NS] = sl; acc_sum += sl; acc_cnt += 1.0; continue; }
+            const double z = zr[k * NS];
             if (mode == 0) {
                 const double rs = gcs_rcp(sl), D = z * rs;
-                wr[k] = rs;                                   // cached 1/s for the other passes of this iteration
+                wr[k * NS] = rs;                                   // cached 1/s for the other passes of this iteration
                 s_aa0 += D * AA[3 * k]; s_aa1 += D * AA[3 * k + 1]; s_aa2 += D * AA[3 * k + 2];
                 s_ba0 += D * bk * A0; s_ba1 += D * bk * A1; s_bb += D * bk * bk;
                 w_a0 += A0 * z; w_a1 += A1 * z; w_b += bk * z;
                 const double pr = sl * z;
                 acc_sum += pr; acc_min = fmin(acc_min, pr);
             } else if (need_p) {
-                const double rs = wr[k];
+                const double rs = wr[k * NS];
                 const double ps = ph * bk - (A0 * pp0 + A1 * pp1);      // predictor ds
                 const double t = ps * rs;                                // ds / s
                 if (mode == 1) {
@@ -260,16 +262,16 @@ GCS_DEV void gcs_rows(const GcsScratchLayout &L, double *S, int m, int d, bool t
                     } else {
                         const double ds = dh * bk - (A0 * dp0 + A1 * dp1);
                         const double dz = (rc - z * ds) * rs;
-                        wr[k] = dz;                           // 1/s is not needed after this pass
+                        wr[k * NS] = dz;                           // 1/s is not needed after this pass
                         acc_max = fmax(acc_max, fmax(-ds * rs, -dz * gcs_rcp(z)));
                     }
                 }
             } else if (mode == 4) {
                 const double ds = dh * bk - (A0 * dp0 + A1 * dp1);
-                const double pr = (sl + ar.alpha * ds) * (z + ar.alpha * wr[k]);
+                const double pr = (sl + ar.alpha * ds) * (z + ar.alpha * wr[k * NS]);
                 acc_sum += pr; acc_min = fmin(acc_min, pr);
             } else {
-                zr[k] = z + ar.alpha * wr[k];
+                zr[k * NS] = z + ar.alpha * wr[k * NS];
             }
         }
         if (mode == 0 || mode == 2) {
@@ -549,13 +551,13 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
         if (getenv("GCSEMU_MU0")) mu0 *= atof(getenv("GCSEMU_MU0"));
 #endif
         if (warm) mu0 *= in.theta;
-        const int nfam = term ? 1 : 2;
-        GCS_LANE_LOOP(q, 4 * (d + 1) * m) {
-            double *zr = S + L.zr;
-            // slot-major layout with stride m; the record uses the same (slot * m + k) indexing
-            zr[q] = mu0 / zr[q] + (warm ? wz[q] : 0.0);
+        {
+            const int NS = 4 * (L.dcap + 1), ns = 4 * (d + 1);
+            GCS_LANE_LOOP(q, ns * m) {         // (k, slot) -> k * NS + slot, in scratch and in the record alike
+                const int k = q / ns, idx = k * NS + (q - k * ns);
+                S[L.zr + idx] = mu0 / S[L.zr + idx] + (warm ? wz[idx] : 0.0);
+            }
         }
-        (void)nfam;
         GCS_LANE_LOOP(j, d + 1) { double *zy = S + L.zy; if (!(j == d && term)) zy[j] = mu0 / zy[j] + (warm ? wy[j] : 0.0); }
         sq[0] = u[GCS_UT]; sq[1] = u[GCS_UZ] - u[GCS_UZ + 2]; sq[2] = u[GCS_UZ + 1] - u[GCS_UZ + 3];
         const double det = gcs_jnorm2(sq[0], sq[1], sq[2]);
@@ -799,7 +801,8 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
         double *wv = in.ws + 1, *wz = in.ws + 1 + L.ncap, *wy = wz + nrw, *wq = wy + L.dcap + 1;
         if (res.status == 0) {
             GCS_LANE_LOOP(q, n) wv[q] = v[q];
-            GCS_LANE_LOOP(q, 4 * (d + 1) * m) wz[q] = S[L.zr + q];
+            { const int NS = 4 * (L.dcap + 1), ns = 4 * (d + 1);
+              GCS_LANE_LOOP(q, ns * m) { const int k = q / ns, idx = k * NS + (q - k * ns); wz[idx] = S[L.zr + idx]; } }
             GCS_LANE_LOOP(j, d + 1) wy[j] = S[L.zy + j];
             if (lane == 0) { wq[0] = zq[0]; wq[1] = zq[1]; wq[2] = zq[2]; in.ws[0] = 1.0; }
         } else if (lane == 0) in.ws[0] = 0.0;

@@ -62,9 +62,7 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = library_path()
-    if not os.path.exists(path):
-        _build.build()
+    path = _build.build()          # no-op when libgcsadmm.so is newer than its sources; raises if nvcc is missing
     L = C.CDLL(path)
     L.gcsadmm_version.restype = C.c_char_p
     L.gcsadmm_last_error.restype = C.c_char_p
