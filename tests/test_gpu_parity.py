@@ -137,3 +137,22 @@ def test_batched_queries_equal_individual_solves():
         s.close()
     assert stb["iterations"] == max(GOLD["benchmark1"], GOLD["benchmark2"], sb.problem_status(2)["iterations"], sb.problem_status(4)["iterations"])
     sb.close()
+
+
+def test_random_generated_problem_matches_oracle():
+    """A generate_test_2D-style instance (irregular polygons, mixed degrees) outside the stored benchmarks."""
+    from c_oracle import COracle
+    from gcs_admm_b200.generator import generate_test_2D
+    As, bs, s_pt, t_pt = generate_test_2D(None, -20, 20, 1, 0.9, 60, seed=5)
+    g = pack_graph(As, bs)
+    assert g.max_live_degree >= 8
+    s, o = _solver(g), COracle(g)
+    for it in range(15):
+        s.step(1)
+        o.step(1)
+        xc, mu, z, rho, k = s.state()
+        xo, muo, zo = o.state()
+        assert np.max(np.abs(xc - xo)) < 1e-4 and np.max(np.abs(z - zo)) < 1e-4
+        s.set_state(xo, muo, zo, rho=o.info()["rho"], it=k)
+    assert s.status()["inner_fail"] <= 2
+    s.close()
