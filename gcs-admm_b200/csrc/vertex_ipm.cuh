@@ -69,7 +69,7 @@ __device__ __forceinline__ double gcs_warp_min(double x) {
 struct GcsScratchLayout {
     int dcap, mcap, ncap, nucap;
     int H, C, u, gu, Pu, qu, dua, du, ru, dv, rv, ytmp, Q, v, vbest, zr, wr, zy, dsy, dzy, sy;
-    int ep, A, b, AA, tgt, ints, diag0, Linv, total;
+    int ep, A, b, AA, tgt, ints, diag0, Linv, MS, CZ, total;
 };
 
 #if defined(__CUDACC__)
@@ -99,6 +99,7 @@ static inline GcsScratchLayout gcs_scratch_layout(int dcap, int mcap) {
     L.tgt = o; o += 5 * dcap;
     L.ints = o; o += (3 * dcap + 1) / 2 + 1;   // int arrays out / prim / hid packed behind the doubles
     L.diag0 = o; o += L.ncap; L.Linv = o; o += 15 * dcap;
+    L.MS = o; o += 25; L.CZ = o; o += 25;       // dense copies of M_* and C_zz for the Hessian assembly
     L.total = o;
     return L;
 }
@@ -122,7 +123,7 @@ static inline int gcs_ws_stride(const GcsScratchLayout &L) { return 1 + L.ncap +
 
 struct GcsVertexOut { int iters; int status; double gap, dres; };
 
-struct GcsNT { double w0, w1, w2, beta, l0, l1, l2; };
+struct GcsNT { double w0, w1, w2, beta, l0, l1, l2, lb0, lb1, lb2, inrm; };   // lb = lam / |lam|_J, inrm = 1 / |lam|_J
 
 GCS_DEV double gcs_jnorm2(double s0, double s1, double s2) { double n1 = hypot(s1, s2); return (s0 - n1) * (s0 + n1); }
 GCS_DEV void gcs_nt_apply(const GcsNT &S, double x0, double x1, double x2, bool inverse, double &y0, double &y1, double &y2) {
@@ -138,12 +139,12 @@ GCS_DEV void gcs_nt_build(GcsNT &S, const double *s, const double *z) {
     S.w0 = (sb0 + zb0) / (2 * gamma); S.w1 = (sb1 - zb1) / (2 * gamma); S.w2 = (sb2 - zb2) / (2 * gamma);
     S.beta = sqrt(sn / zn);
     gcs_nt_apply(S, z[0], z[1], z[2], false, S.l0, S.l1, S.l2);
+    S.inrm = 1.0 / sqrt(fmax(gcs_jnorm2(S.l0, S.l1, S.l2), 1e-300));
+    S.lb0 = S.l0 * S.inrm; S.lb1 = S.l1 * S.inrm; S.lb2 = S.l2 * S.inrm;
 }
 GCS_DEV double gcs_soc_max_step(const GcsNT &S, const double *d) {
-    double nrm = sqrt(fmax(gcs_jnorm2(S.l0, S.l1, S.l2), 1e-300));
-    double l0 = S.l0 / nrm, l1 = S.l1 / nrm, l2 = S.l2 / nrm;
-    double c0 = l0 * d[0] - l1 * d[1] - l2 * d[2], f = (c0 + d[0]) / (l0 + 1.0);
-    return (hypot(d[1] - f * l1, d[2] - f * l2) - c0) / nrm;
+    const double c0 = S.lb0 * d[0] - S.lb1 * d[1] - S.lb2 * d[2], f = (c0 + d[0]) / (S.lb0 + 1.0);
+    return (hypot(d[1] - f * S.lb1, d[2] - f * S.lb2) - c0) * S.inrm;
 }
 GCS_DEV void gcs_soc_div(const GcsNT &S, const double *v, double *x) {  // lam o x = v
     double det = gcs_jnorm2(S.l0, S.l1, S.l2);
@@ -659,11 +660,12 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
         GCS_SYNC();
         if (lane == 0) {
             // second-order cone block  B' W^-2 B  on (t, z1 - z2); a few ulps of its trace keep it PSD
+            // W^-2 = (2 wh wh' - J) / beta^2  with  wh = J w   (the inverse of a hyperbolic rotation is the rotation of J w)
             double Wi2[3][3];
-            for (int c = 0; c < 3; ++c) {
-                double e0 = c == 0, e1 = c == 1, e2 = c == 2, y0, y1, y2, w0, w1, w2;
-                gcs_nt_apply(nt, e0, e1, e2, true, y0, y1, y2); gcs_nt_apply(nt, y0, y1, y2, true, w0, w1, w2);
-                Wi2[0][c] = w0; Wi2[1][c] = w1; Wi2[2][c] = w2;
+            {
+                const double wh[3] = {nt.w0, -nt.w1, -nt.w2}, ib2 = 1.0 / (nt.beta * nt.beta);
+                for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c)
+                    Wi2[a][c] = (2.0 * wh[a] * wh[c] - (a == c ? (a == 0 ? 1.0 : -1.0) : 0.0)) * ib2;
             }
             const double lift = 16.0 * 2.2e-16 * (Wi2[0][0] + Wi2[1][1] + Wi2[2][2]);
             Wi2[0][0] += lift; Wi2[1][1] += lift; Wi2[2][2] += lift;
@@ -682,6 +684,9 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
         //   t col         :  cz_j C_tz
         {
             const double *Qs = Q + GCS_QN * jstar;
+            double *MS = S + L.MS, *CZ = S + L.CZ;
+            GCS_LANE_LOOP(e, 25) { const int a = e / 5, c = e - 5 * a; MS[e] = gcs_qM(Qs, a, c); CZ[e] = C[(GCS_UZ + a) * 10 + GCS_UZ + c]; }
+            GCS_SYNC();
             for (int jj = 0; jj < d - 1; ++jj) {
                 const int j = jj < jstar ? jj : jj + 1;
                 const double csj = prim[j] ? -1.0 : 1.0, czj = prim[j] ? 0.0 : 1.0;
@@ -691,7 +696,7 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
                     if (kk == jj && c > a) continue;                       // packed storage: lower triangle only
                     const int k = kk < jstar ? kk : kk + 1;
                     const double csk = prim[k] ? -1.0 : 1.0, czk = prim[k] ? 0.0 : 1.0;
-                    double sv = csj * csk * gcs_qM(Qs, a, c) + czj * czk * C[(GCS_UZ + a) * 10 + GCS_UZ + c];
+                    double sv = csj * csk * MS[ab] + czj * czk * CZ[ab];
                     if (kk == jj) sv += gcs_qM(Qj, a, c) + (a == c ? 1e-14 : 0.0);
                     H[gcs_tri(5 + 5 * jj + a) + 5 + 5 * kk + c] = sv;
                 }
@@ -700,7 +705,7 @@ GCS_DEV GcsVertexOut gcs_vertex_solve(const GcsScratchLayout &L, double *S, cons
                 const int r = e / 5, c = e - 5 * r, jj = r / 5, a = r - 5 * jj, j = jj < jstar ? jj : jj + 1;
                 const double csj = prim[j] ? -1.0 : 1.0, czj = prim[j] ? 0.0 : 1.0;
                 double sv;
-                if (c < 4) sv = gcs_qB(Q + GCS_QN * j, c, a) + csj * gcs_qB(Qs, c, a) + czj * C[c * 10 + GCS_UZ + a] + (term ? csj * gcs_qM(Qs, a, c) : 0.0);
+                if (c < 4) sv = gcs_qB(Q + GCS_QN * j, c, a) + csj * gcs_qB(Qs, c, a) + czj * C[c * 10 + GCS_UZ + a] + (term ? csj * MS[5 * a + c] : 0.0);
                 else sv = czj * C[GCS_UT * 10 + GCS_UZ + a];
                 H[gcs_tri(5 + r) + c] = sv;
             }
