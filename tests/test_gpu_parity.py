@@ -156,3 +156,17 @@ def test_random_generated_problem_matches_oracle():
         s.set_state(xo, muo, zo, rho=o.info()["rho"], it=k)
     assert s.status()["inner_fail"] <= 2
     s.close()
+
+
+@pytest.mark.parametrize("name,iters,tol", [("benchmark1", 3000, 1e-6), ("benchmark2", 5000, 5e-5)])
+def test_fixed_point_is_classic_optimum(name, iters, tol):
+    """Run far past the reference's loose stop: the iterates converge to the optimum of the monolithic convex
+    relaxation, which the reference's classic_solver pickles hold (3.000398 / 7.414245)."""
+    As, bs, n, d, keys = load_golden(name)
+    g = pack_graph(As, bs)
+    s = _solver(g, max_it=iters + 10, eps_abs=0.0, eps_rel=0.0)
+    s.step(iters)
+    x_v, z_v, y_v, z_e = s.solution()
+    cost = float(np.sum(np.linalg.norm(z_v[:, :2] - z_v[:, 2:], axis=1)) + 1e-4 * np.sum(z_e[:, 4]))
+    assert abs(cost - float(d["classic_cost"])) <= tol * float(d["classic_cost"])
+    s.close()
