@@ -126,6 +126,9 @@ def main():
     ap.add_argument("--impl", type=str, default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--burn-in", type=int, default=-1, help="untimed iterations before the timed window (default: grid side + 10, so that the\n                    cold-start wave has reached every vertex and no vertex program is the trivial all-zero one)")
+    ap.add_argument("--mode", type=str, default="parity", choices=["parity", "perf"],
+                    help="parity: exact interior-point x-update (reference trajectory); perf: K closed-form splitting iterations per x-update")
+    ap.add_argument("--inner", type=int, default=3, help="K of the perf mode")
     ap.add_argument("--residual-run", type=int, default=0, help="also run up to this many iterations with the abs 1e-4 stop and report the time")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -144,6 +147,11 @@ def main():
     g = grid_packed_graph(args.grid)
     k1_bytes, k2_bytes = algorithmic_bytes(g)
     s = lib.Solver(g, device=0, max_it=max(1000, args.steps + burn + 8), eps_abs=0.0, eps_rel=0.0)
+    tables = None
+    if args.mode == "perf":
+        from gcs_admm_b200 import perf as perf_mod
+        tables = perf_mod.perf_tables(g)
+        s.enable_perf(inner_iters=args.inner, tables=tables)
     s.step(burn)
     st0 = s.status()
     sampler = ClockSampler(0)
@@ -164,8 +172,15 @@ def main():
     out_bytes = 8 * (9 * g.nV + 5 * g.nE) + 3 * 8 * (burn + args.steps + 1)
     t0 = time.perf_counter()
     n_e2e = burn + args.steps
-    out = lib.solve_host(g, device=0, max_iters=n_e2e, max_it=max(1000, n_e2e + 8), check_every=64,
-                         eps_abs=0.0, eps_rel=0.0)
+    if args.mode == "perf":          # same sequence as gcsadmm_solve_host, plus the table upload
+        s3 = lib.Solver(g, device=0, max_it=max(1000, n_e2e + 8), check_every=64, eps_abs=0.0, eps_rel=0.0).enable_perf(inner_iters=args.inner, tables=tables)
+        s3.run(n_e2e)
+        s3.solution(); s3.history()
+        out = {"status": s3.status()}
+        s3.close()
+    else:
+        out = lib.solve_host(g, device=0, max_iters=n_e2e, max_it=max(1000, n_e2e + 8), check_every=64,
+                             eps_abs=0.0, eps_rel=0.0)
     e2e_s = time.perf_counter() - t0
     assert out["status"]["iterations"] == n_e2e
     peaks = {}
@@ -178,7 +193,7 @@ def main():
     traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch, from the committed ncu capture
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
-        if tj.get("workload") == f"grid{args.grid}x{args.grid}":
+        if tj.get("workload") == f"grid{args.grid}x{args.grid}" and args.mode == "parity":
             traffic = tj["traffic_bytes_per_launch"]
     except Exception:
         pass
@@ -196,7 +211,7 @@ def main():
         "e2e": {"value": n_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": gs_bytes / n_e2e, "d2h_bytes_per_step": out_bytes / n_e2e,
                 "note": "gcsadmm_solve_host from a cold start: graph upload + (burn_in + K) iterations + solution/history download, wall clock; value = (burn_in + K) / time"},
         "gpu_launches": 4 * args.steps,
-        "roofline": {"bound": "hbm", "kernel": "vertex_kernel (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "roofline": {"bound": "hbm", "kernel": "vertex_kernel (K1)" if args.mode == "parity" else "vertex_perf_kernel (K1, perf mode)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                      "traffic_note": "ncu --set full capture (profiles/r01_k1_grid316_ncu_summary.txt); includes the 2.7 KB/vertex warm-start records K1 reads and rewrites",
                      "algorithmic_bytes_per_launch": k1_bytes, "kernel_ms": k1_ms,

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "vertex_update.cuh"
+#include "vertex_perf.cuh"
 
 extern "C" int gcsemu_vertex_update_all(int nV, int nE, const int *poly_off, const double *polyA, const double *polyb,
                                         const int *he_off, const int *he_edge, const unsigned char *he_flags,
@@ -31,3 +32,28 @@ extern "C" int gcsemu_vertex_update_all(int nV, int nE, const int *poly_off, con
 }
 extern "C" int gcsemu_scratch_doubles(int dcap, int mcap) { return gcs_scratch_layout(dcap, mcap).total; }
 extern "C" int gcsemu_ws_stride(int dcap, int mcap) { return gcs_ws_stride(gcs_scratch_layout(dcap, mcap)); }
+
+// perf-mode K1 (vertex_perf.cuh), emulated
+extern "C" int gcsemu_vertex_update_perf_all(int nV, int nE, const int *poly_off, const double *polyA, const double *polyb,
+                                             const int *he_off, const int *he_edge, const unsigned char *he_flags,
+                                             const unsigned char *vtype, const double *cent, double *xc, const double *mu,
+                                             const double *z, double *x_v, double *z_v, double *y_v, double rho, double mu_scale,
+                                             int dcap, const int *vclass, const int *class_koff, const double *kinv,
+                                             const int *cone_off, const double *cone, double *state, int inner_iters,
+                                             double alpha, double kappa) {
+    GcsGraphView G = {nV, nE, poly_off, polyA, polyb, he_off, he_edge, he_flags, vtype, cent};
+    GcsStateView St = {xc, mu, z, x_v, z_v, y_v, 0, 0.0, 0.0};
+    int kcap = 3;
+    for (int v = 0; v < nV; ++v) if (cone_off[v + 1] - cone_off[v] > kcap) kcap = cone_off[v + 1] - cone_off[v];
+    GcsPerfLayout L = gcs_perf_layout(dcap, kcap);
+    GcsPerfTables T = {vclass, class_koff, kinv, cone_off, cone, state, gcs_perf_state_stride(dcap), inner_iters, alpha, kappa};
+    double *S = (double *)malloc(sizeof(double) * L.total);
+    int n = 0;
+    for (int v = 0; v < nV; ++v) {
+        memset(S, 0, sizeof(double) * L.total);
+        n += gcs_vertex_update_perf(G, St, T, v, rho, mu_scale, L, S, 0);
+    }
+    free(S);
+    return n;
+}
+extern "C" int gcsemu_perf_state_stride(int dcap) { return gcs_perf_state_stride(dcap); }

@@ -16,6 +16,7 @@
 
 #include "../../include/gcsadmm.h"
 #include "vertex_update.cuh"
+#include "vertex_perf.cuh"
 
 #define GCS_VERSION "gcsadmm 0.1.0 (sm_100a)"
 #define K1_MAX_WARPS 12  // __launch_bounds__(320): <= 204 registers/thread, 10 warps fill the register file of one SM
@@ -66,6 +67,11 @@ struct GcsHandle {
     Ctrl *ctrl_host;    // pinned
     cudaEvent_t ev[4];
     void *flush_buf; size_t flush_bytes;
+    // perf mode (inexact x-update by K closed-form splitting iterations)
+    int perf_on, perf_smem, perf_warps, perf_blocks;
+    GcsPerfLayout PL;
+    GcsPerfTables PT;
+    int *p_vclass, *p_class_koff, *p_cone_off; double *p_kinv, *p_cone, *p_state;
 };
 
 // ------------------------------------------------------------------------------------------ K1
@@ -85,6 +91,20 @@ vertex_kernel(GcsGraphView G, GcsStateView St, Ctrl *ctrl_all, const int *__rest
         if (status > 0 && status != 5) atomicAdd(&ctrl->inner_fail, 1);
         if (status < 0) atomicAdd(&ctrl->skipped, 1ull);
     }
+}
+
+// ------------------------------------------------------------------------------------------ K1 (perf mode)
+__global__ void __launch_bounds__(512)
+vertex_perf_kernel(GcsGraphView G, GcsStateView St, GcsPerfTables T, Ctrl *ctrl_all, const int *__restrict__ vprob, GcsPerfLayout L) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (v >= G.nV) return;
+    Ctrl *ctrl = ctrl_all + (vprob ? vprob[v] : 0);
+    if (ctrl->stop && !ctrl->ignore_stop) return;
+    double *S = smem + (size_t)warp * L.total;
+    const int did = gcs_vertex_update_perf(G, St, T, v, ctrl->rho, ctrl->mu_scale, L, S, lane);
+    if (lane == 0 && did) atomicAdd(&ctrl->inner_iters, (unsigned long long)T.inner_iters);
 }
 
 // ------------------------------------------------------------------------------------------ K2-K4
@@ -304,6 +324,7 @@ extern "C" int gcsadmm_destroy(GcsHandle *h) {
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
     free(h->he_prob_host);
     if (h->flush_buf) cudaFree(h->flush_buf);
+    { void *pp[] = {h->p_vclass, h->p_class_koff, h->p_cone_off, h->p_kinv, h->p_cone, h->p_state}; for (void *q : pp) if (q) cudaFree(q); }
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -427,6 +448,10 @@ static GcsStateView state_view(const GcsHandle *h) {
     return S;
 }
 static int launch_k1(GcsHandle *h) {
+    if (h->perf_on) {
+        vertex_perf_kernel<<<h->perf_blocks, h->perf_warps * 32, h->perf_smem, h->stream>>>(graph_view(h), state_view(h), h->PT, h->ctrl, h->vprob, h->PL);
+        return 0;
+    }
     vertex_kernel<<<h->k1_blocks, h->k1_warps * 32, h->k1_smem, h->stream>>>(graph_view(h), state_view(h), h->ctrl, h->vprob, h->L, h->p.inner_tol, h->p.inner_max_iter);
     return 0;
 }
@@ -649,10 +674,49 @@ extern "C" int gcsadmm_flush_l2(GcsHandle *h, long long bytes) {
     if (bytes <= 0) bytes = 256ll << 20;
     if (!h->flush_buf || h->flush_bytes < (size_t)bytes) {
         if (h->flush_buf) cudaFree(h->flush_buf);
+    { void *pp[] = {h->p_vclass, h->p_class_koff, h->p_cone_off, h->p_kinv, h->p_cone, h->p_state}; for (void *q : pp) if (q) cudaFree(q); }
         h->flush_buf = nullptr;
         CK(cudaMalloc(&h->flush_buf, (size_t)bytes));
         h->flush_bytes = (size_t)bytes;
     }
     CK(cudaMemsetAsync(h->flush_buf, 0, (size_t)bytes, h->stream));
+    return 0;
+}
+
+// Switches the x-update to the inexact `perf` mode (vertex_perf.cuh).  Tables are built by the host
+// (gcs-admm_b200/perf.py): the inverse K1^-1 of every vertex class and the polygon cones.
+extern "C" int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *c) {
+    if (!h || !c) return set_err(GCS_E_INVALID, "null argument%s", "");
+    if (c->inner_iters < 1 || c->n_classes < 1 || !c->vclass || !c->class_koff || !c->kinv || !c->cone_off || !c->cone)
+        return set_err(GCS_E_INVALID, "incomplete perf-mode tables%s", "");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    int rc = 0;
+    const size_t ncone = (size_t)c->cone_off[h->nV];
+    int kcap = 3;
+    for (int v = 0; v < h->nV; ++v) { const int k = c->cone_off[v + 1] - c->cone_off[v]; if (k > kcap) kcap = k; }
+    if (!rc) rc = upload(&h->p_vclass, c->vclass, (size_t)h->nV);
+    if (!rc) rc = upload(&h->p_class_koff, c->class_koff, (size_t)c->n_classes);
+    if (!rc) rc = upload(&h->p_kinv, c->kinv, (size_t)c->kinv_len);
+    if (!rc) rc = upload(&h->p_cone_off, c->cone_off, (size_t)h->nV + 1);
+    if (!rc) rc = upload(&h->p_cone, c->cone, 6 * ncone);
+    const int stride = gcs_perf_state_stride(h->dcap);
+    if (!rc) rc = upload(&h->p_state, (const double *)nullptr, (size_t)h->nV * stride);
+    if (rc) return rc;
+    h->PL = gcs_perf_layout(h->dcap, kcap);
+    h->PT.vclass = h->p_vclass; h->PT.class_koff = h->p_class_koff; h->PT.kinv = h->p_kinv; h->PT.cone_off = h->p_cone_off;
+    h->PT.cone = h->p_cone; h->PT.state = h->p_state; h->PT.state_stride = stride; h->PT.inner_iters = c->inner_iters;
+    h->PT.alpha = c->alpha; h->PT.kappa = c->kappa;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    const size_t per_warp = (size_t)h->PL.total * sizeof(double);
+    int w = (int)(prop.sharedMemPerBlockOptin / per_warp);
+    if (w < 1) return set_err(GCS_E_INVALID, "perf-mode vertex state too large for shared memory%s", "");
+    if (w > 16) w = 16;
+    h->perf_warps = w; h->perf_smem = (int)(w * per_warp);
+    h->perf_blocks = (h->nV + w - 1) / w;
+    CK(cudaFuncSetAttribute(vertex_perf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->perf_smem));
+    CK(cudaFuncSetAttribute(vertex_perf_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    h->perf_on = 1;
     return 0;
 }

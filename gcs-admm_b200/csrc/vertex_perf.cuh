@@ -1,0 +1,275 @@
+// K1 in `perf` mode — the x-update of the full-vertex-split ADMM done INEXACTLY by K warm-started iterations
+// of an operator-splitting scheme whose steps are all closed-form (north_star: "fixed-iteration inner
+// projection / primal-dual scheme").  One warp per vertex, state in shared memory, same null-space
+// parametrisation u = N v + up as the exact kernel (vertex_ipm.cuh).
+//
+// Every inequality of the vertex program (reference admm_solver_v3.py:416-440) says that a (point, flow) pair
+// lies in the perspective cone of the vertex's polygon,  K_P = {(p, h) in R^3 : A p <= h b}:
+//     C3: (a_i, y_e)        C4: (x_i - a_i, 1 - y_e)        C1: (z_i, y_v)        C2: (x_i - z_i, 1 - y_v)
+// and the pairs are 0/+-1 linear images  c = M u + m0  of the variables.  Splitting  c in prod K_P  from u:
+//     v-step : minimise  rho/2 |S u - T|^2 + eps'y + sigma/2 |M u + m0 - c + lam|^2   over v   (u = N v + up)
+//              -> v <- v - (1/rho) K1^-1 G(v),  K1 = N'(S'S + kappa M'M)N  depends only on the vertex CLASS
+//              (type, #in, #out) — not on the polygon —, so its inverse is a table shared by all vertices;
+//     c-step : c <- Proj_{K_P}(alpha (M u + m0) + (1 - alpha) c + lam)   exact 3-D cone projection, O(#polygon vertices);
+//              the path-length term |z_1 - z_2| (:380-384) is a block soft-threshold with threshold 1/sigma;
+//     lam    : lam <- lam + alpha (M u + m0) + (1 - alpha) c_old - c_new.
+// sigma = kappa * rho, so the rho-adaptation rescale of the ADMM duals (:705/:708) applies to lam as well.
+// (c, lam) persist per vertex in HBM between ADMM iterations (warm start).
+//
+// The fixed point of the outer ADMM is unchanged (an exact minimiser of the vertex program is a fixed point of
+// the inner iteration); the trajectory is not the reference's, so this mode is validated at convergence against
+// the classic relaxation optimum (tests/test_gpu_perf.py, tools/prototypes/inner_first_order.py), not per iteration.
+#pragma once
+#include "vertex_update.cuh"
+
+struct GcsPerfTables {
+    const int *vclass;         // [nV] class id (-1: vertex not solved here: dead)
+    const int *class_koff;     // [ncls] offset of the class's K1^-1 (n x n, row-major) in kinv
+    const double *kinv;
+    const int *cone_off;       // [nV+1] polygon vertices of vertex v: cone_off[v]..cone_off[v+1]
+    const double *cone;        // per polygon vertex k: Vx, Vy, nx, ny, nh (unit outward normal of the face between
+                               // rays k and k+1), 1/|r_k|^2  with r_k = (Vx, Vy, 1)
+    double *state;             // [nV][state_stride]: c then lam, (3 * 4 (dcap + 1) + 2) doubles each
+    int state_stride;
+    int inner_iters;           // K
+    double alpha, kappa;
+};
+
+// scratch (doubles) of one warp in perf mode
+struct GcsPerfLayout { int dcap, kcap, ncap, nucap, npair, u, gu, v, gv, pv, c, lam, w, cone, tgt, ints, total; };
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline GcsPerfLayout gcs_perf_layout(int dcap, int kcap) {
+    GcsPerfLayout L;
+    if (dcap < 1) dcap = 1;
+    if (kcap < 3) kcap = 3;
+    L.dcap = dcap; L.kcap = kcap; L.ncap = 5 * dcap; L.nucap = GCS_NCORE + 5 * dcap; L.npair = 4 * (dcap + 1);
+    int o = 0;
+    L.u = o; o += L.nucap; L.gu = o; o += L.nucap;
+    L.v = o; o += L.ncap; L.gv = o; o += L.ncap;
+    const int np3 = 3 * L.npair + 2;
+    L.pv = o; o += np3; L.c = o; o += np3; L.lam = o; o += np3; L.w = o; o += np3;
+    L.cone = o; o += 6 * kcap;
+    L.tgt = o; o += 5 * dcap;
+    L.ints = o; o += (3 * dcap + 1) / 2 + 1;
+    L.total = o;
+    return L;
+}
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline int gcs_perf_state_stride(int dcap) { return 2 * (3 * 4 * (dcap + 1) + 2); }
+
+// exact projection of c onto the cone spanned by the rays r_k = (V_k, 1), k = 0..nv-1 (counter-clockwise)
+GCS_DEV void gcs_cone_project(const double *cone, int nv, double c0, double c1, double c2, double &q0, double &q1, double &q2) {
+    bool inside = true;
+    for (int k = 0; k < nv; ++k) {
+        const double *ck = cone + 6 * k;
+        if (ck[2] * c0 + ck[3] * c1 + ck[4] * c2 > 0.0) { inside = false; break; }
+    }
+    if (inside) { q0 = c0; q1 = c1; q2 = c2; return; }
+    double bd = c0 * c0 + c1 * c1 + c2 * c2;     // the apex
+    q0 = 0.0; q1 = 0.0; q2 = 0.0;
+    for (int k = 0; k < nv; ++k) {
+        const double *ck = cone + 6 * k, *cn = cone + 6 * (k + 1 == nv ? 0 : k + 1);
+        const double rx = ck[0], ry = ck[1], sx = cn[0], sy = cn[1];
+        // ray k
+        double tau = (c0 * rx + c1 * ry + c2) * ck[5];
+        if (tau > 0.0) {
+            const double e0 = c0 - tau * rx, e1 = c1 - tau * ry, e2 = c2 - tau;
+            const double dd = e0 * e0 + e1 * e1 + e2 * e2;
+            if (dd < bd) { bd = dd; q0 = tau * rx; q1 = tau * ry; q2 = tau; }
+        }
+        // face between rays k and k+1: orthogonal projection onto its plane, kept if it falls inside the sector
+        const double nx = ck[2], ny = ck[3], nh = ck[4];
+        const double dist = nx * c0 + ny * c1 + nh * c2;
+        if (dist > 0.0) {
+            const double p0 = c0 - dist * nx, p1 = c1 - dist * ny, p2 = c2 - dist * nh;
+            // p = a r + b s with a, b >= 0.  For a counter-clockwise polygon r x s points INTO the cone, i.e. along -n,
+            // so  r x p = b (r x s)  and  p x s = a (r x s)  give  a, b >= 0  <=>  (r x p).n <= 0 and (p x s).n <= 0
+            const double a0 = ry * p2 - p1, a1 = p0 - rx * p2, a2 = rx * p1 - ry * p0;          // r x p, r = (rx, ry, 1)
+            const double b0 = p1 - p2 * sy, b1 = p2 * sx - p0, b2 = p0 * sy - p1 * sx;          // p x s
+            if (a0 * nx + a1 * ny + a2 * nh <= 0.0 && b0 * nx + b1 * ny + b2 * nh <= 0.0) {
+                const double dd = dist * dist;
+                if (dd < bd) { bd = dd; q0 = p0; q1 = p1; q2 = p2; }
+            }
+        }
+    }
+}
+
+// pair values  pv = M u + m0  (3 per family slot, then the 2 entries of z_1 - z_2)
+GCS_DEV void gcs_pair_values(const double *u, double *pv, int d, bool term, int npair_cap, int lane) {
+    const int nitems = term ? 2 * (d + 1) : 4 * (d + 1);
+    GCS_LANE_LOOP(it, nitems) {
+        int fam, i, blk;
+        if (term) { fam = 0; i = it & 1; blk = it >> 1; } else { fam = it & 1; i = (it >> 1) & 1; blk = it >> 2; }
+        const int po = (blk < d ? gcs_uw(blk) : GCS_UZ) + 2 * i, yo = blk < d ? gcs_uw(blk) + 4 : GCS_UYV, xo = GCS_UX + 2 * i;
+        double *p = pv + 3 * gcs_slot(blk, i, fam);
+        p[0] = fam ? u[xo] - u[po] : u[po];
+        p[1] = fam ? u[xo + 1] - u[po + 1] : u[po + 1];
+        p[2] = fam ? 1.0 - u[yo] : u[yo];
+    }
+    if (lane == 0) {
+        pv[3 * npair_cap] = u[GCS_UZ] - u[GCS_UZ + 2];
+        pv[3 * npair_cap + 1] = u[GCS_UZ + 1] - u[GCS_UZ + 3];
+    }
+    GCS_SYNC();
+}
+
+// gu = M' w  (w: 3 per slot + 2)
+GCS_DEV void gcs_pair_adjoint(const double *w, double *gu, int d, bool term, int npair_cap, int lane) {
+    GCS_LANE_LOOP(q, 4 * (d + 1)) {          // point slots a_i / z_i
+        const int blk = q >> 2, i = (q >> 1) & 1, c = q & 1;
+        const double *w3 = w + 3 * gcs_slot(blk, i, 0);
+        gu[(blk < d ? gcs_uw(blk) : GCS_UZ) + 2 * i + c] = w3[c] - (term ? 0.0 : w3[3 + c]);
+    }
+    GCS_LANE_LOOP(blk, d + 1) {              // flow slots y / y_v
+        const double *w0 = w + 3 * gcs_slot(blk, 0, 0);
+        double s = w0[2] + w0[6 + 2];
+        if (!term) s -= w0[3 + 2] + w0[9 + 2];
+        gu[blk < d ? gcs_uw(blk) + 4 : GCS_UYV] = s;
+    }
+    GCS_LANE_LOOP(q, 4) {                    // x_i collects every C4 | C2 pair of point i
+        const int i = q >> 1, c = q & 1;
+        double s = 0.0;
+        if (!term) for (int blk = 0; blk <= d; ++blk) s += w[3 * gcs_slot(blk, i, 1) + c];
+        gu[GCS_UX + q] = s;
+    }
+    GCS_SYNC();
+    if (lane == 0) {
+        gu[GCS_UT] = 0.0;
+        const double n0 = w[3 * npair_cap], n1 = w[3 * npair_cap + 1];
+        gu[GCS_UZ] += n0; gu[GCS_UZ + 1] += n1; gu[GCS_UZ + 2] -= n0; gu[GCS_UZ + 3] -= n1;
+    }
+    GCS_SYNC();
+}
+
+// x-update of one vertex in perf mode.  Returns 1 (the vertex did K inner iterations) or 0 (no program).
+GCS_DEV int gcs_vertex_update_perf(const GcsGraphView &G, const GcsStateView &St, const GcsPerfTables &T, int v, double rho,
+                                   double mu_scale, const GcsPerfLayout &L, double *S, int lane) {
+    const int h0 = G.he_off[v], h1 = G.he_off[v + 1];
+    const int type = G.vtype[v];
+    GCS_LANE_LOOP(i, h1 - h0) {                // forced-zero half-edges, as in the exact kernel
+        const int h = h0 + i;
+        if (G.he_flags[h] & GCS_HE_ZERO) {
+            double *x = St.xc + 5 * (size_t)h;
+            double x0 = 0.0, x1 = 0.0;
+            if (!(G.he_flags[h] & GCS_HE_OUT)) {
+                const int e = G.he_edge[h];
+                x0 = St.z[5 * (size_t)e] + mu_scale * St.mu[5 * (size_t)h];
+                x1 = St.z[5 * (size_t)e + 1] + mu_scale * St.mu[5 * (size_t)h + 1];
+            }
+            x[0] = x0; x[1] = x1; x[2] = 0.0; x[3] = 0.0; x[4] = 0.0;
+        }
+    }
+    if (type == GCS_VT_DEAD) {
+        if (lane == 0) {
+            for (int k = 0; k < 4; ++k) { St.z_v[4 * (size_t)v + k] = 0.0; St.x_v[4 * (size_t)v + k] = G.cent[2 * (size_t)v + (k & 1)]; }
+            St.y_v[v] = 0.0;
+        }
+        return 0;
+    }
+    int *out = (int *)(S + L.ints), *prim = out + L.dcap, *hid = out + 2 * L.dcap;
+    int d = 0;
+    for (int h = h0; h < h1; ++h) {
+        const int f = G.he_flags[h];
+        if (f & GCS_HE_ZERO) continue;
+        if (lane == 0) { out[d] = f & GCS_HE_OUT; hid[d] = h; prim[d] = (type == GCS_VT_TARGET) ? 1 : (f & GCS_HE_OUT); }
+        d++;
+    }
+    const bool term = type != GCS_VT_GENERIC;
+    const int n = 5 * d, nu = GCS_NCORE + 5 * d, np3 = 3 * L.npair + 2;
+    const int c0 = T.cone_off[v], nv = T.cone_off[v + 1] - c0;
+    GCS_LANE_LOOP(q, 6 * nv) S[L.cone + q] = T.cone[6 * (size_t)c0 + q];
+    GCS_SYNC();
+    int jstar = -1;
+    for (int j = 0; j < d; ++j) if (prim[j]) jstar = j;
+    GCS_LANE_LOOP(q, 5 * d) {
+        const int j = q / 5, c = q - 5 * j, h = hid[j], e = G.he_edge[h];
+        S[L.tgt + q] = St.z[5 * (size_t)e + c] + mu_scale * St.mu[5 * (size_t)h + c];
+    }
+    double *st = T.state + (size_t)v * T.state_stride;
+    GCS_LANE_LOOP(q, np3) { S[L.c + q] = st[q]; S[L.lam + q] = mu_scale * st[np3 + q]; }    // sigma = kappa rho: lam rescales with mu
+    GCS_SYNC();
+    double *u = S + L.u, *gu = S + L.gu, *vv = S + L.v, *gv = S + L.gv, *pv = S + L.pv, *cc = S + L.c, *lam = S + L.lam, *w = S + L.w;
+    const double *tgt = S + L.tgt;
+    const double sigma = T.kappa * rho, alpha = T.alpha;
+    const double *Kinv = T.kinv + T.class_koff[T.vclass[v]];
+    // start: v with  N v + up  closest to the stored pair copies is not needed — the v-step is an exact solve of a
+    // quadratic, so any starting v gives the same result; start from 0
+    GCS_LANE_LOOP(q, n) vv[q] = 0.0;
+    GCS_SYNC();
+    gcs_forward(vv, u, d, jstar, prim, term, true, lane);
+    gcs_pair_values(u, pv, d, term, L.npair, lane);
+    for (int it = 0; it < T.inner_iters; ++it) {
+        // G_u = rho S'(S u - T) + eps e_y + sigma M'(pv - c + lam)
+        GCS_LANE_LOOP(q, np3) w[q] = pv[q] - cc[q] + lam[q];
+        GCS_SYNC();
+        gcs_pair_adjoint(w, gu, d, term, L.npair, lane);
+        GCS_LANE_LOOP(q, nu) {
+            double g = sigma * gu[q];
+            if (q >= GCS_NCORE) {
+                const int j = (q - GCS_NCORE) / 5, c = q - GCS_NCORE - 5 * j;
+                const double *t = tgt + 5 * j;
+                if (out[j]) { if (c < 4) g += rho * (u[q] - t[c]); }
+                else if (c < 2) g += rho * (u[q] - t[2 + c]);
+                if (c == 4) g += rho * (u[q] - t[4]) + GCS_EDGE_PENALTY;
+            }
+            gu[q] = g;
+        }
+        GCS_SYNC();
+        gcs_adjoint(gu, gv, d, jstar, prim, term, lane);
+        // v <- v - (1/rho) K1^-1 G_v      (dense n x n table of the vertex class)
+        const double irho = 1.0 / rho;
+        GCS_LANE_LOOP(r, n) {
+            const double *kr = Kinv + (size_t)r * n;
+            double s = 0.0;
+            for (int k = 0; k < n; ++k) s += kr[k] * gv[k];
+            w[r] = vv[r] - irho * s;            // w doubles as the new v until every lane has read gv / vv
+        }
+        GCS_SYNC();
+        GCS_LANE_LOOP(r, n) vv[r] = (r == 4) ? 0.0 : w[r];     // the epigraph variable t is unused in this mode
+        GCS_SYNC();
+        gcs_forward(vv, u, d, jstar, prim, term, true, lane);
+        gcs_pair_values(u, pv, d, term, L.npair, lane);
+        // c-step and dual step
+        const int nitems = term ? 2 * (d + 1) : 4 * (d + 1);
+        GCS_LANE_LOOP(idx, nitems + 1) {
+            if (idx < nitems) {
+                int fam, i, blk;
+                if (term) { fam = 0; i = idx & 1; blk = idx >> 1; } else { fam = idx & 1; i = (idx >> 1) & 1; blk = idx >> 2; }
+                const int o = 3 * gcs_slot(blk, i, fam);
+                const double r0 = alpha * pv[o] + (1.0 - alpha) * cc[o], r1 = alpha * pv[o + 1] + (1.0 - alpha) * cc[o + 1],
+                             r2 = alpha * pv[o + 2] + (1.0 - alpha) * cc[o + 2];
+                double q0, q1, q2;
+                gcs_cone_project(S + L.cone, nv, r0 + lam[o], r1 + lam[o + 1], r2 + lam[o + 2], q0, q1, q2);
+                lam[o] += r0 - q0; lam[o + 1] += r1 - q1; lam[o + 2] += r2 - q2;
+                cc[o] = q0; cc[o + 1] = q1; cc[o + 2] = q2;
+            } else {           // |z_1 - z_2|: block soft-threshold, threshold 1 / sigma
+                const int o = 3 * L.npair;
+                const double r0 = alpha * pv[o] + (1.0 - alpha) * cc[o], r1 = alpha * pv[o + 1] + (1.0 - alpha) * cc[o + 1];
+                const double a0 = r0 + lam[o], a1 = r1 + lam[o + 1], nrm = hypot(a0, a1);
+                const double sc = nrm > 0.0 ? fmax(0.0, 1.0 - 1.0 / (sigma * nrm)) : 0.0;
+                const double q0 = sc * a0, q1 = sc * a1;
+                lam[o] += r0 - q0; lam[o + 1] += r1 - q1;
+                cc[o] = q0; cc[o + 1] = q1;
+            }
+        }
+        GCS_SYNC();
+    }
+    GCS_LANE_LOOP(q, np3) { st[q] = cc[q]; st[np3 + q] = lam[q]; }
+    GCS_LANE_LOOP(j, d) {     // scatter, edge-canonical order (same as the exact kernel)
+        const double *wj = u + gcs_uw(j), *t = tgt + 5 * j;
+        double *x = St.xc + 5 * (size_t)hid[j];
+        if (out[j]) { x[0] = wj[0]; x[1] = wj[1]; x[2] = wj[2]; x[3] = wj[3]; }
+        else        { x[0] = t[0]; x[1] = t[1]; x[2] = wj[0]; x[3] = wj[1]; }
+        x[4] = wj[4];
+    }
+    if (lane == 0) {
+        for (int k = 0; k < 4; ++k) { St.x_v[4 * (size_t)v + k] = u[GCS_UX + k]; St.z_v[4 * (size_t)v + k] = u[GCS_UZ + k]; }
+        St.y_v[v] = u[GCS_UYV];
+    }
+    GCS_SYNC();
+    return 1;
+}

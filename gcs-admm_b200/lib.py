@@ -20,7 +20,7 @@ EXPORTS = [
     "gcsadmm_get_status", "gcsadmm_vertex_update", "gcsadmm_edge_update", "gcsadmm_control",
     "gcsadmm_sums_device_ptr", "gcsadmm_xc_device_ptr", "gcsadmm_get_history", "gcsadmm_get_solution",
     "gcsadmm_get_state", "gcsadmm_set_state", "gcsadmm_time_steps", "gcsadmm_solve_host",
-    "gcsadmm_scratch_bytes", "gcsadmm_flush_l2", "gcsadmm_get_problem_status", "gcsadmm_get_problem_history",
+    "gcsadmm_scratch_bytes", "gcsadmm_flush_l2", "gcsadmm_get_problem_status", "gcsadmm_get_problem_history", "gcsadmm_enable_perf",
 ]
 
 
@@ -39,6 +39,12 @@ class GcsParams(C.Structure):
                 ("frac", C.c_double), ("eps_abs", C.c_double), ("eps_rel", C.c_double), ("max_it", C.c_int32),
                 ("inner_tol", C.c_double), ("inner_max_iter", C.c_int32), ("check_every", C.c_int32),
                 ("abs_stop", C.c_int32), ("abs_tol", C.c_double), ("warm_theta", C.c_double), ("zero_tol", C.c_double)]
+
+
+class GcsPerfConfig(C.Structure):
+    _fields_ = [("inner_iters", C.c_int32), ("alpha", C.c_double), ("kappa", C.c_double), ("n_classes", C.c_int32),
+                ("vclass", C.c_void_p), ("class_koff", C.c_void_p), ("kinv", C.c_void_p), ("kinv_len", C.c_int64),
+                ("cone_off", C.c_void_p), ("cone", C.c_void_p)]
 
 
 class GcsStatus(C.Structure):
@@ -87,6 +93,7 @@ def load():
     L.gcsadmm_time_steps.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.gcsadmm_solve_host.argtypes = [C.POINTER(GcsGraph), C.POINTER(GcsParams), C.c_int, C.c_int, C.POINTER(GcsStatus),
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.gcsadmm_enable_perf.argtypes = [C.c_void_p, C.POINTER(GcsPerfConfig)]
     L.gcsadmm_scratch_bytes.argtypes = [C.c_int, C.c_int]
     L.gcsadmm_flush_l2.argtypes = [C.c_void_p, C.c_longlong]
     _LIB = L
@@ -165,6 +172,21 @@ class Solver:
         _check(L.gcsadmm_create(C.byref(self._gs), C.byref(self.params), int(device), C.byref(h)))
         self._h = h
         self.nHall = self._gs.nH_own + self._gs.nH_ghost
+
+    def enable_perf(self, inner_iters=3, alpha=1.6, kappa=1.0, tables=None):
+        """Switch the x-update to the inexact `perf` mode (K closed-form splitting iterations per ADMM iteration)."""
+        from . import perf
+        T = tables if tables is not None else perf.perf_tables(self.g, kappa)
+        keep = dict(vclass=np.ascontiguousarray(T["vclass"], np.int32), class_koff=np.ascontiguousarray(T["class_koff"], np.int32),
+                    kinv=np.ascontiguousarray(T["kinv"], np.float64), cone_off=np.ascontiguousarray(T["cone_off"], np.int32),
+                    cone=np.ascontiguousarray(T["cone"], np.float64))
+        c = GcsPerfConfig()
+        c.inner_iters, c.alpha, c.kappa, c.n_classes = int(inner_iters), float(alpha), float(T["kappa"]), int(keep["class_koff"].shape[0])
+        c.vclass, c.class_koff, c.kinv, c.kinv_len = _ptr(keep["vclass"]), _ptr(keep["class_koff"]), _ptr(keep["kinv"]), int(keep["kinv"].shape[0])
+        c.cone_off, c.cone = _ptr(keep["cone_off"]), _ptr(keep["cone"])
+        _check(load().gcsadmm_enable_perf(self._h, C.byref(c)))
+        self.perf = dict(inner_iters=int(inner_iters), alpha=float(alpha), kappa=float(T["kappa"]), classes=len(T["classes"]))
+        return self
 
     def close(self):
         if getattr(self, "_h", None):

@@ -146,6 +146,25 @@ int gcsadmm_solve_host(const GcsGraph *g, const GcsParams *p, int device, int ma
                        double *x_v, double *z_v, double *y_v, double *z_e,
                        double *rho_seq, double *pri_seq, double *dual_seq, int hist_cap);
 
+/* `perf` mode of the x-update (K1): K warm-started closed-form splitting iterations per ADMM iteration instead of
+ * an exact interior-point solve (gcs-admm_b200/csrc/vertex_perf.cuh).  Same fixed point, different trajectory:
+ * validated at convergence against the classic relaxation optimum, not iteration by iteration.  The tables are
+ * built by the host (gcs-admm_b200/perf.py). */
+typedef struct GcsPerfConfig {
+    int32_t inner_iters;         /* K */
+    double alpha;                /* over-relaxation of the inner splitting (1.6) */
+    double kappa;                /* sigma = kappa * rho */
+    int32_t n_classes;           /* vertex classes (type, #live in-edges, #live out-edges) */
+    const int32_t *vclass;       /* [nV] class of each vertex (ignored for vtype 3) */
+    const int32_t *class_koff;   /* [n_classes] offset of the class's n x n inverse in kinv (n = 5 * live degree) */
+    const double *kinv;
+    int64_t kinv_len;
+    const int32_t *cone_off;     /* [nV+1] polygon vertices of each region, counter-clockwise */
+    const double *cone;          /* 6 doubles per polygon vertex: Vx, Vy, unit outward normal (3) of the face to the
+                                    next vertex's ray, 1 / (Vx^2 + Vy^2 + 1) */
+} GcsPerfConfig;
+int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *cfg);
+
 /* bytes of shared memory one vertex program needs (diagnostics) */
 int gcsadmm_scratch_bytes(int max_live_degree, int max_rows);
 

@@ -1,0 +1,119 @@
+"""`perf` mode of K1 (K closed-form splitting iterations per x-update) on the CPU: the kernel source compiled with
+GCS_EMULATE against the numpy prototype of the same iteration written in the LITERAL variables of the reference
+program (tools/prototypes/inner_first_order.py), and the convergence of the resulting inexact ADMM to the
+classic relaxation optimum."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from gcs_admm_b200 import perf
+from gcs_admm_b200.graph import pack_graph
+
+sys.path.insert(0, os.path.join(ROOT, "tools", "prototypes"))
+CSRC = os.path.join(ROOT, "gcs-admm_b200", "csrc")
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_bp = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(CSRC, "libgcsemu.so")
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-o", so, os.path.join(CSRC, "emulate.cpp")])
+    lib = C.CDLL(so)
+    lib.gcsemu_vertex_update_perf_all.restype = C.c_int
+    lib.gcsemu_vertex_update_perf_all.argtypes = [C.c_int, C.c_int, _ip, _dp, _dp, _ip, _ip, _bp, _bp, _dp, _dp, _dp, _dp, _dp, _dp, _dp,
+                                                  C.c_double, C.c_double, C.c_int, _ip, _ip, _dp, _ip, _dp, _dp, C.c_int, C.c_double, C.c_double]
+    lib.gcsemu_perf_state_stride.restype = C.c_int
+    return lib
+
+
+class EmuPerfADMM:
+    """Outer ADMM (numpy edge / dual / residual arithmetic of the kernels) around the emulated perf K1."""
+
+    def __init__(self, lib, g, K, kappa=1.0, alpha=1.6):
+        self.lib, self.g, self.K, self.alpha = lib, g, K, alpha
+        self.T = perf.perf_tables(g, kappa)
+        self.dcap = max(1, g.max_live_degree)
+        self.state = np.zeros((g.nV, lib.gcsemu_perf_state_stride(self.dcap)))
+        self.xc, self.mu, self.z = np.zeros((g.H, 5)), np.zeros((g.H, 5)), np.zeros((g.nE, 5))
+        self.x_v, self.z_v, self.y_v = np.zeros((g.nV, 4)), np.zeros((g.nV, 4)), np.zeros(g.nV)
+        self.cent = np.ascontiguousarray(g.interior_points())
+        self.rho, self.pri, self.dual = 1.0, [0.0], [0.0]
+
+    def step(self):
+        g, T = self.g, self.T
+        self.lib.gcsemu_vertex_update_perf_all(g.nV, g.nE, g.poly_off, g.polyA.reshape(-1), g.polyb, g.he_off, g.he_edge, g.he_flags,
+                                               g.vtype, self.cent.reshape(-1), self.xc.reshape(-1), self.mu.reshape(-1), self.z.reshape(-1),
+                                               self.x_v.reshape(-1), self.z_v.reshape(-1), self.y_v, self.rho, 1.0, self.dcap,
+                                               T["vclass"], T["class_koff"], T["kinv"], T["cone_off"], T["cone"].reshape(-1),
+                                               self.state.reshape(-1), self.K, self.alpha, T["kappa"])
+        zn = 0.5 * (self.xc[g.edge_he_tail] + self.xc[g.edge_he_head])
+        dz = zn - self.z
+        self.z = zn
+        r = zn[g.he_edge] - self.xc
+        self.mu += r
+        self.pri.append(float(np.sqrt(np.sum(r * r)))); self.dual.append(self.rho * float(np.sqrt(2 * np.sum(dz * dz))))
+
+    def cost(self):
+        return float(np.sum(np.linalg.norm(self.z_v[:, :2] - self.z_v[:, 2:], axis=1)) + 1e-4 * np.sum(self.z[:, 4]))
+
+
+def test_cone_projection_table_is_consistent():
+    g = pack_graph(*load_golden("benchmark3")[:2])
+    off, cone = perf.cone_table(g)
+    cent = g.interior_points()
+    for v in range(g.nV):
+        ck = cone[off[v]:off[v + 1]]
+        A, b = g.polyA[g.poly_off[v]:g.poly_off[v + 1]], g.polyb[g.poly_off[v]:g.poly_off[v + 1]]
+        assert ck.shape[0] >= 3
+        assert np.all(ck[:, :2] @ A.T <= b[None, :] + 1e-7)                               # polygon vertices are feasible
+        assert np.all(ck[:, 2:5] @ np.r_[cent[v], 1.0] < 0)                                 # normals point outwards
+        R = np.hstack([ck[:, :2], np.ones((ck.shape[0], 1))])
+        assert np.allclose(np.sum(ck[:, 2:5] * R, axis=1), 0, atol=1e-7)                    # each face contains its two rays
+        assert np.allclose(np.sum(ck[:, 2:5] * np.roll(R, -1, axis=0), axis=1), 0, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["benchmark1", "test3"])
+def test_emulated_perf_kernel_equals_literal_prototype(emu, name):
+    """Null-space kernel vs the literal-variable numpy prototype: the same inner iteration, iterate by iterate."""
+    import inner_first_order as proto
+    K = 3
+    g = pack_graph(*load_golden(name)[:2])
+    a = EmuPerfADMM(emu, g, K)
+    o = proto.OracleADMM(g)
+    splits = {v: proto.SplitVertex(g, v, p, 1.0) for v, p in enumerate(o.progs) if not (p.d == 0 or p.dead)}
+
+    def inexact():
+        for v, p in enumerate(o.progs):
+            hs = p.hs
+            if v not in splits:
+                o.z_v[v] = 0.0; o.y_v[v] = 0.0
+                for h in hs:
+                    tgt = o.z[g.he_edge[h]] + o.mu[h]
+                    o.xc[h] = 0.0
+                    if not g.he_out[h]:
+                        o.xc[h, 0:2] = tgt[0:2]
+                continue
+            u = splits[v].iterate(o.rho, o.z[g.he_edge[hs]] + o.mu[hs], K)
+            o.x_v[v] = u[0:4]; o.z_v[v] = u[4:8]; o.y_v[v] = u[8]
+            o.xc[hs] = u[p.sel].reshape(-1, 5)
+    o.vertex_update = inexact
+    for it in range(25):
+        a.step(); o.step()
+        assert np.max(np.abs(a.xc - o.xc)) < 1e-8, it
+        assert np.max(np.abs(a.z_v - o.z_v)) < 1e-8 and np.max(np.abs(a.y_v - o.y_v)) < 1e-8
+
+
+def test_inexact_admm_converges_to_classic_optimum(emu):
+    As, bs, n, d, keys = load_golden("benchmark1")
+    a = EmuPerfADMM(emu, pack_graph(As, bs), K=3)
+    for _ in range(400):
+        a.step()
+    assert a.pri[-1] < 1e-6 and a.dual[-1] < 1e-6
+    assert abs(a.cost() - float(d["classic_cost"])) < 1e-5
