@@ -22,7 +22,7 @@ extern "C" int gcsemu_vertex_update_all(int nV, int nE, const int *poly_off, con
     long iters = 0;
     for (int v = 0; v < nV; ++v) {
         int status = 0;
-        memset(S, 0, sizeof(double) * L.total);
+        memset(S, getenv("GCSEMU_POISON") ? 0xFF : 0, sizeof(double) * L.total);
         iters += gcs_vertex_update(G, St, v, rho, mu_scale, tol, max_iter, L, S, 0, &status);
         if (status > 0 && status != 5) { fails++; if (getenv("GCSEMU_VERBOSE")) fprintf(stderr, "emu: vertex %d status %d\n", v, status); }
     }
@@ -50,7 +50,7 @@ extern "C" int gcsemu_vertex_update_perf_all(int nV, int nE, const int *poly_off
     double *S = (double *)malloc(sizeof(double) * L.total);
     int n = 0;
     for (int v = 0; v < nV; ++v) {
-        memset(S, 0, sizeof(double) * L.total);
+        memset(S, getenv("GCSEMU_POISON") ? 0xFF : 0, sizeof(double) * L.total);   // 0xFF: NaN doubles / -1 ints expose uninitialised reads
         n += gcs_vertex_update_perf(G, St, T, v, rho, mu_scale, L, S, 0);
     }
     free(S);
