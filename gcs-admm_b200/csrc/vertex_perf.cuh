@@ -223,10 +223,19 @@ GCS_DEV int gcs_vertex_update_perf(const GcsGraphView &G, const GcsStateView &St
         // v <- v - (1/rho) K1^-1 G_v      (dense n x n table of the vertex class)
         const double irho = 1.0 / rho;
         GCS_LANE_LOOP(r, n) {
-            const double *kr = Kinv + (size_t)r * n;
-            double s = 0.0;
-            for (int k = 0; k < n; ++k) s += kr[k] * gv[k];
-            w[r] = vv[r] - irho * s;            // w doubles as the new v until every lane has read gv / vv
+            // K1^-1 is symmetric: walk column r (= row r) so that the lanes of a warp read consecutive doubles of
+            // row k — coalesced, L1-resident table shared by every vertex of the class
+            const double *kc = Kinv + r;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int k = 0;
+            for (; k + 3 < n; k += 4) {
+                s0 += kc[(size_t)k * n] * gv[k];
+                s1 += kc[(size_t)(k + 1) * n] * gv[k + 1];
+                s2 += kc[(size_t)(k + 2) * n] * gv[k + 2];
+                s3 += kc[(size_t)(k + 3) * n] * gv[k + 3];
+            }
+            for (; k < n; ++k) s0 += kc[(size_t)k * n] * gv[k];
+            w[r] = vv[r] - irho * ((s0 + s1) + (s2 + s3));            // w doubles as the new v until every lane has read gv / vv
         }
         GCS_SYNC();
         GCS_LANE_LOOP(r, n) vv[r] = (r == 4) ? 0.0 : w[r];     // the epigraph variable t is unused in this mode
