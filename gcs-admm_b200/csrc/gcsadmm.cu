@@ -700,7 +700,7 @@ extern "C" int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *c) {
     if (!rc) rc = upload(&h->p_class_koff, c->class_koff, (size_t)c->n_classes);
     if (!rc) rc = upload(&h->p_kinv, c->kinv, (size_t)c->kinv_len);
     if (!rc) rc = upload(&h->p_cone_off, c->cone_off, (size_t)h->nV + 1);
-    if (!rc) rc = upload(&h->p_cone, c->cone, 6 * ncone);
+    if (!rc) rc = upload(&h->p_cone, c->cone, GCS_CONE_REC * ncone);
     const int stride = gcs_perf_state_stride(h->dcap);
     if (!rc) rc = upload(&h->p_state, (const double *)nullptr, (size_t)h->nV * stride);
     if (rc) return rc;

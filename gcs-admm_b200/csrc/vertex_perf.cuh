@@ -21,14 +21,14 @@
 // the classic relaxation optimum (tests/test_gpu_perf.py, tools/prototypes/inner_first_order.py), not per iteration.
 #pragma once
 #include "vertex_update.cuh"
+#define GCS_CONE_REC 12   // doubles per polygon vertex in the cone table
 
 struct GcsPerfTables {
     const int *vclass;         // [nV] class id (-1: vertex not solved here: dead)
     const int *class_koff;     // [ncls] offset of the class's K1^-1 (n x n, row-major) in kinv
     const double *kinv;
     const int *cone_off;       // [nV+1] polygon vertices of vertex v: cone_off[v]..cone_off[v+1]
-    const double *cone;        // per polygon vertex k: Vx, Vy, nx, ny, nh (unit outward normal of the face between
-                               // rays k and k+1), 1/|r_k|^2  with r_k = (Vx, Vy, 1)
+    const double *cone;        // GCS_CONE_REC doubles per polygon vertex (see gcs_cone_project)
     double *state;             // [nV][state_stride]: c then lam, (3 * 4 (dcap + 1) + 2) doubles each
     int state_stride;
     int inner_iters;           // K
@@ -50,7 +50,7 @@ static inline GcsPerfLayout gcs_perf_layout(int dcap, int kcap) {
     L.v = o; o += L.ncap; L.gv = o; o += L.ncap;
     const int np3 = 3 * L.npair + 2;
     L.pv = o; o += np3; L.c = o; o += np3; L.lam = o; o += np3; L.w = o; o += np3;
-    L.cone = o; o += 6 * kcap;
+    L.cone = o; o += GCS_CONE_REC * kcap;
     L.tgt = o; o += 5 * dcap;
     L.ints = o; o += (3 * dcap + 1) / 2 + 1;
     L.total = o;
@@ -61,41 +61,34 @@ __host__ __device__
 #endif
 static inline int gcs_perf_state_stride(int dcap) { return 2 * (3 * 4 * (dcap + 1) + 2); }
 
-// exact projection of c onto the cone spanned by the rays r_k = (V_k, 1), k = 0..nv-1 (counter-clockwise)
+// exact projection of c onto the cone spanned by the rays r_k = (V_k, 1), k = 0..nv-1 (counter-clockwise).
+// record k: V_k (2) | unit outward normal n_k of the face between rays k and k+1 (3) | 1/|r_k|^2 | sector normals ma, mb (3 + 3)
+// The projection is c itself, or lies on a face (inside its sector), on a ray, or is the apex: take the nearest candidate.
 GCS_DEV void gcs_cone_project(const double *cone, int nv, double c0, double c1, double c2, double &q0, double &q1, double &q2) {
-    bool inside = true;
-    for (int k = 0; k < nv; ++k) {
-        const double *ck = cone + 6 * k;
-        if (ck[2] * c0 + ck[3] * c1 + ck[4] * c2 > 0.0) { inside = false; break; }
-    }
-    if (inside) { q0 = c0; q1 = c1; q2 = c2; return; }
     double bd = c0 * c0 + c1 * c1 + c2 * c2;     // the apex
     q0 = 0.0; q1 = 0.0; q2 = 0.0;
+    bool inside = true;
     for (int k = 0; k < nv; ++k) {
-        const double *ck = cone + 6 * k, *cn = cone + 6 * (k + 1 == nv ? 0 : k + 1);
-        const double rx = ck[0], ry = ck[1], sx = cn[0], sy = cn[1];
-        // ray k
-        double tau = (c0 * rx + c1 * ry + c2) * ck[5];
+        const double *ck = cone + GCS_CONE_REC * k;
+        const double rx = ck[0], ry = ck[1];
+        const double tau = (c0 * rx + c1 * ry + c2) * ck[5];                  // ray k
         if (tau > 0.0) {
             const double e0 = c0 - tau * rx, e1 = c1 - tau * ry, e2 = c2 - tau;
             const double dd = e0 * e0 + e1 * e1 + e2 * e2;
             if (dd < bd) { bd = dd; q0 = tau * rx; q1 = tau * ry; q2 = tau; }
         }
-        // face between rays k and k+1: orthogonal projection onto its plane, kept if it falls inside the sector
         const double nx = ck[2], ny = ck[3], nh = ck[4];
         const double dist = nx * c0 + ny * c1 + nh * c2;
-        if (dist > 0.0) {
+        if (dist > 0.0) {                                                      // outside face k
+            inside = false;
             const double p0 = c0 - dist * nx, p1 = c1 - dist * ny, p2 = c2 - dist * nh;
-            // p = a r + b s with a, b >= 0.  For a counter-clockwise polygon r x s points INTO the cone, i.e. along -n,
-            // so  r x p = b (r x s)  and  p x s = a (r x s)  give  a, b >= 0  <=>  (r x p).n <= 0 and (p x s).n <= 0
-            const double a0 = ry * p2 - p1, a1 = p0 - rx * p2, a2 = rx * p1 - ry * p0;          // r x p, r = (rx, ry, 1)
-            const double b0 = p1 - p2 * sy, b1 = p2 * sx - p0, b2 = p0 * sy - p1 * sx;          // p x s
-            if (a0 * nx + a1 * ny + a2 * nh <= 0.0 && b0 * nx + b1 * ny + b2 * nh <= 0.0) {
+            if (p0 * ck[6] + p1 * ck[7] + p2 * ck[8] >= 0.0 && p0 * ck[9] + p1 * ck[10] + p2 * ck[11] >= 0.0) {
                 const double dd = dist * dist;
                 if (dd < bd) { bd = dd; q0 = p0; q1 = p1; q2 = p2; }
             }
         }
     }
+    if (inside) { q0 = c0; q1 = c1; q2 = c2; }
 }
 
 // pair values  pv = M u + m0  (3 per family slot, then the 2 entries of z_1 - z_2)
@@ -181,7 +174,7 @@ GCS_DEV int gcs_vertex_update_perf(const GcsGraphView &G, const GcsStateView &St
     const bool term = type != GCS_VT_GENERIC;
     const int n = 5 * d, nu = GCS_NCORE + 5 * d, np3 = 3 * L.npair + 2;
     const int c0 = T.cone_off[v], nv = T.cone_off[v + 1] - c0;
-    GCS_LANE_LOOP(q, 6 * nv) S[L.cone + q] = T.cone[6 * (size_t)c0 + q];
+    GCS_LANE_LOOP(q, GCS_CONE_REC * nv) S[L.cone + q] = T.cone[GCS_CONE_REC * (size_t)c0 + q];
     GCS_SYNC();
     int jstar = -1;
     for (int j = 0; j < d; ++j) if (prim[j]) jstar = j;

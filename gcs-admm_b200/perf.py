@@ -104,7 +104,8 @@ def class_inverse(vtype, din, dout, kappa):
 
 def cone_table(g):
     """Per region: polygon vertices (counter-clockwise) with the unit outward normal of the cone face spanned by the
-    rays through vertex k and k+1, and 1/|r_k|^2 (r_k = (V_k, 1)).  Vectorised over regions with the same vertex count."""
+    rays through vertex k and k+1, 1/|r_k|^2 (r_k = (V_k, 1)) and the two in-plane sector normals of that face
+    (12 doubles per polygon vertex).  Vectorised over regions with the same vertex count."""
     verts, cnt = _vertices_batch(g.poly_off.astype(np.int64), g.polyA, g.polyb)
     nV = g.nV
     # duplicates (redundant rows meeting in one vertex) are rare: handle those regions one by one
@@ -126,7 +127,12 @@ def cone_table(g):
         inner = np.concatenate([c, np.ones((c.shape[0], 1, 1))], axis=2)
         flip = np.sum(Nn * inner, axis=2) > 0
         Nn = np.where(flip[..., None], -Nn, Nn)
-        rec = np.concatenate([P, Nn, 1.0 / np.sum(R * R, axis=2, keepdims=True)], axis=2)      # (g, k, 6)
+        Rn = np.roll(R, -1, axis=1)
+        # in-plane sector tests of face k: p = a r + b s with a, b >= 0  <=>  p.ma >= 0 and p.mb >= 0, where
+        # ma = n x s (zero on s, positive on r) and mb = r x n (zero on r, positive on s), n = outward unit normal
+        ma = np.cross(Nn, Rn); mb = np.cross(R, Nn)
+        ma *= np.sign(np.sum(ma * R, axis=2, keepdims=True)); mb *= np.sign(np.sum(mb * Rn, axis=2, keepdims=True))
+        rec = np.concatenate([P, Nn, 1.0 / np.sum(R * R, axis=2, keepdims=True), ma, mb], axis=2)      # (g, k, 12)
         for gi, v in enumerate(idx):
             per[v] = rec[gi] if clean[gi] else None
     for v in range(nV):
@@ -150,7 +156,10 @@ def _cone_one(P):
     Nn /= np.linalg.norm(Nn, axis=1, keepdims=True)
     flip = (Nn @ np.array([c[0], c[1], 1.0])) > 0
     Nn[flip] *= -1.0
-    return np.hstack([P, Nn, 1.0 / np.sum(R * R, axis=1, keepdims=True)])
+    Rn = np.roll(R, -1, axis=0)
+    ma = np.cross(Nn, Rn); mb = np.cross(R, Nn)
+    ma *= np.sign(np.sum(ma * R, axis=1, keepdims=True)); mb *= np.sign(np.sum(mb * Rn, axis=1, keepdims=True))
+    return np.hstack([P, Nn, 1.0 / np.sum(R * R, axis=1, keepdims=True), ma, mb])
 
 
 def perf_tables(g, kappa=1.0):

@@ -160,8 +160,8 @@ typedef struct GcsPerfConfig {
     const double *kinv;
     int64_t kinv_len;
     const int32_t *cone_off;     /* [nV+1] polygon vertices of each region, counter-clockwise */
-    const double *cone;          /* 6 doubles per polygon vertex: Vx, Vy, unit outward normal (3) of the face to the
-                                    next vertex's ray, 1 / (Vx^2 + Vy^2 + 1) */
+    const double *cone;          /* 12 doubles per polygon vertex: Vx, Vy, unit outward normal (3) of the cone face to the
+                                    next vertex's ray, 1 / (Vx^2 + Vy^2 + 1), the face's two in-plane sector normals (3 + 3) */
 } GcsPerfConfig;
 int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *cfg);
 
