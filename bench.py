@@ -117,6 +117,10 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+MODE_TEXT = {"parity": "parity (every vertex program solved to 1e-8 by the interior-point kernel)",
+             "perf": "perf (inexact x-update: warm-started splitting iterations, gcsadmm_enable_perf)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -129,6 +133,9 @@ def main():
     ap.add_argument("--mode", type=str, default="parity", choices=["parity", "perf"],
                     help="parity: exact interior-point x-update (reference trajectory); perf: K closed-form splitting iterations per x-update")
     ap.add_argument("--inner", type=int, default=3, help="K of the perf mode")
+    ap.add_argument("--no-perf-report", dest="perf_report", action="store_false",
+                    help="parity runs also time the perf mode on the same graph and report it as a nested object; this switches that off")
+    ap.add_argument("--perf-trace-iters", type=int, default=20000, help="perf report: residuals and wall time after this many K=1 iterations from a cold start")
     ap.add_argument("--residual-run", type=int, default=0, help="also run up to this many iterations with the abs 1e-4 stop and report the time")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -146,50 +153,61 @@ def main():
     burn = max(W, args.grid + 10 if args.burn_in < 0 else args.burn_in)
     g = grid_packed_graph(args.grid)
     k1_bytes, k2_bytes = algorithmic_bytes(g)
-    s = lib.Solver(g, device=0, max_it=max(1000, args.steps + burn + 8), eps_abs=0.0, eps_rel=0.0)
     tables = None
-    if args.mode == "perf":
+    if args.mode == "perf" or args.perf_report:
         from gcs_admm_b200 import perf as perf_mod
         tables = perf_mod.perf_tables(g)
-        s.enable_perf(inner_iters=args.inner, tables=tables)
-    s.step(burn)
-    st0 = s.status()
-    sampler = ClockSampler(0)
-    sampler.start()
-    tot = k1 = ed = 0.0
-    for _ in range(args.steps):          # L2 flushed before every timed iteration, outside the event pair
-        s.flush_l2()
-        a, b, c = s.time_steps(1, split=True)
-        tot += a; k1 += b; ed += c
-    clocks = sampler.finish()
-    st = s.status()
-    ms = tot / args.steps
+
+    def timed(mode, inner):
+        """burn-in, then `steps` iterations timed one by one with CUDA events on the solver's stream, L2 flushed before each"""
+        s = lib.Solver(g, device=0, max_it=max(1000, args.steps + burn + 8), eps_abs=0.0, eps_rel=0.0)
+        if mode == "perf":
+            s.enable_perf(inner_iters=inner, tables=tables)
+        s.step(burn)
+        st0 = s.status()
+        sampler = ClockSampler(0)
+        sampler.start()
+        tot = k1 = ed = 0.0
+        for _ in range(args.steps):          # L2 flushed before every timed iteration, outside the event pair
+            s.flush_l2()
+            a, b, c = s.time_steps(1, split=True)
+            tot += a; k1 += b; ed += c
+        clocks = sampler.finish()
+        st = s.status()
+        s.close()
+        return dict(ms=tot / args.steps, k1_ms=k1 / args.steps, ed_ms=ed / args.steps, clocks=clocks, st0=st0, st=st)
+
+    def end_to_end(mode, inner, n_e2e):
+        """host buffers -> host buffers through the C-ABI, wall clock: graph (and table) upload + n iterations + download"""
+        t0 = time.perf_counter()
+        if mode == "perf":          # same sequence as gcsadmm_solve_host, plus the table upload
+            s3 = lib.Solver(g, device=0, max_it=max(1000, n_e2e + 8), check_every=64, eps_abs=0.0, eps_rel=0.0).enable_perf(inner_iters=inner, tables=tables)
+            s3.run(n_e2e)
+            s3.solution(); s3.history()
+            out = {"status": s3.status()}
+            s3.close()
+        else:
+            out = lib.solve_host(g, device=0, max_iters=n_e2e, max_it=max(1000, n_e2e + 8), check_every=64,
+                                 eps_abs=0.0, eps_rel=0.0)
+        dt = time.perf_counter() - t0
+        assert out["status"]["iterations"] == n_e2e
+        return dt
+
+    m = timed(args.mode, args.inner)
+    ms, k1, ed, clocks, st0, st = m["ms"], m["k1_ms"] * args.steps, m["ed_ms"] * args.steps, m["clocks"], m["st0"], m["st"]
     value = 1e3 / ms
-    s.close()
-    # end to end through the host-buffer C-ABI call (graph upload + K iterations + download)
     gs_bytes = sum(a.nbytes for a in (g.poly_off, g.polyA, g.polyb, g.he_off, g.he_edge, g.he_flags, g.edge_he_tail,
                                       g.edge_he_head, g.vtype)) + 16 * g.nV
     out_bytes = 8 * (9 * g.nV + 5 * g.nE) + 3 * 8 * (burn + args.steps + 1)
-    t0 = time.perf_counter()
     n_e2e = burn + args.steps
-    if args.mode == "perf":          # same sequence as gcsadmm_solve_host, plus the table upload
-        s3 = lib.Solver(g, device=0, max_it=max(1000, n_e2e + 8), check_every=64, eps_abs=0.0, eps_rel=0.0).enable_perf(inner_iters=args.inner, tables=tables)
-        s3.run(n_e2e)
-        s3.solution(); s3.history()
-        out = {"status": s3.status()}
-        s3.close()
-    else:
-        out = lib.solve_host(g, device=0, max_iters=n_e2e, max_it=max(1000, n_e2e + 8), check_every=64,
-                             eps_abs=0.0, eps_rel=0.0)
-    e2e_s = time.perf_counter() - t0
-    assert out["status"]["iterations"] == n_e2e
+    e2e_s = end_to_end(args.mode, args.inner, n_e2e)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    k1_ms = k1 / args.steps
+    k1_ms = m["k1_ms"]
     traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch, from the committed ncu capture
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
@@ -203,7 +221,7 @@ def main():
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"grid{args.grid}x{args.grid} 2-D GCS: {g.nV} vertices, {g.nE} directed edges, m=8 rows/region "
-                               "(BASELINE.json metric config: 100k-vertex 2-D GCS)", "mode": "parity (every vertex program solved to 1e-8 by the interior-point kernel)",
+                               "(BASELINE.json metric config: 100k-vertex 2-D GCS)", "mode": MODE_TEXT[args.mode] + (f", K={args.inner}" if args.mode == "perf" else ""),
                    "l2": "flushed (256 MiB memset) before every timed iteration", "burn_in_iterations": burn, "inner_ipm_iters_per_vertex": (st["inner_iters"] - st0["inner_iters"]) / max(1, args.steps * g.nV),
                    "inner_tol": 1e-8, "warm_start_theta": 1e-3, "zero_tol": 1e-12,
                    "vertex_programs_skipped_as_zero_frac": (st["skipped"] - st0["skipped"]) / max(1, args.steps * g.nV)},
@@ -213,7 +231,7 @@ def main():
         "gpu_launches": 4 * args.steps,
         "roofline": {"bound": "hbm", "kernel": "vertex_kernel (K1)" if args.mode == "parity" else "vertex_perf_kernel (K1, perf mode)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                     "traffic_note": "ncu --set full capture (profiles/r01_k1_grid316_ncu_summary.txt); includes the 2.7 KB/vertex warm-start records K1 reads and rewrites",
+                     "traffic_note": "ncu --set full capture (profiles/r01_k1_grid316_ncu_summary.txt); includes the 2.7 KB/vertex warm-start records K1 reads and rewrites" if args.mode == "parity" else None,
                      "algorithmic_bytes_per_launch": k1_bytes, "kernel_ms": k1_ms,
                      "whole_iteration": {"bytes": k1_bytes + k2_bytes, "achieved": (k1_bytes + k2_bytes) / (ms * 1e-3) / 1e9,
                                          "frac": (k1_bytes + k2_bytes) / (ms * 1e-3) / 1e9 / peak},
@@ -221,6 +239,24 @@ def main():
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(min(args.grid, 48), g.nV)
+    if args.mode == "parity" and args.perf_report:
+        rep = {"what": "same graph, same timing protocol, x-update = K warm-started splitting iterations per ADMM iteration (gcsadmm_enable_perf) instead of an exact "
+                       "interior-point solve; same fixed point (tests/test_gpu_perf.py), not the reference's trajectory, hence not the headline value"}
+        for K in (3, 1):
+            pm = timed("perf", K)
+            pe = end_to_end("perf", K, n_e2e)
+            rep[f"K={K}"] = {"value": 1e3 / pm["ms"], "unit": UNIT, "ms_per_step": pm["ms"], "kernel_ms": pm["k1_ms"], "edge_ms": pm["ed_ms"],
+                             "roofline_frac_k1": k1_bytes / (pm["k1_ms"] * 1e-3) / 1e9 / peak,
+                             "roofline_frac_iteration": (k1_bytes + k2_bytes) / (pm["ms"] * 1e-3) / 1e9 / peak,
+                             "e2e": n_e2e / pe, "clocks": pm["clocks"]}
+        if args.perf_trace_iters > 0:
+            s4 = lib.Solver(g, device=0, max_it=10 * args.perf_trace_iters, abs_stop=1, abs_tol=1e-4, check_every=64).enable_perf(inner_iters=1, tables=tables)
+            t0 = time.perf_counter()
+            st4 = s4.run(args.perf_trace_iters)
+            rep["residual_trace_K=1"] = {"iterations": st4["iterations"], "seconds": time.perf_counter() - t0, "pri_res": st4["pri_res"], "dual_res": st4["dual_res"],
+                                         "rho": st4["rho"], "reached_1e-4": bool(st4["converged"])}
+            s4.close()
+        line["perf_mode"] = rep
     if args.residual_run:
         s2 = lib.Solver(g, device=0, max_it=args.residual_run, abs_stop=1, abs_tol=1e-4, check_every=64)
         t0 = time.perf_counter()

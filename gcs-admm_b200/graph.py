@@ -376,11 +376,14 @@ class PackedGraph:
 
     def interior_points(self):
         """One strictly interior point per polytope (vertex centroid); the device
-        IPM starts from it and reports it as x_v of flow-less vertices."""
+        IPM starts from it and reports it as x_v of flow-less vertices.  Computed once per graph."""
+        if getattr(self, "_cent", None) is not None:
+            return self._cent
         verts, cnt = _vertices_batch(self.poly_off.astype(np.int64), self.polyA, self.polyb)
         mask = np.arange(verts.shape[1])[None, :] < cnt[:, None]
         c = (verts * mask[:, :, None]).sum(axis=1) / cnt[:, None]
-        return np.ascontiguousarray(c)
+        self._cent = np.ascontiguousarray(c)
+        return self._cent
 
 
 def pack_graph(As, bs, V=None, E=None):

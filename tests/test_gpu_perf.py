@@ -15,11 +15,12 @@ def _cost(s):
     return float(np.sum(np.linalg.norm(z_v[:, :2] - z_v[:, 2:], axis=1)) + 1e-4 * np.sum(z_e[:, 4]))
 
 
-@pytest.mark.parametrize("name,iters,tol", [("benchmark1", 500, 1e-5), ("benchmark2", 3000, 1e-4), ("benchmark4", 6000, 2e-2)])
-def test_perf_mode_converges_to_classic_optimum(name, iters, tol):
+@pytest.mark.parametrize("name,K,iters,tol", [("benchmark1", 3, 500, 1e-5), ("benchmark2", 3, 3000, 1e-4), ("benchmark4", 3, 6000, 2e-2),
+                                              ("benchmark1", 1, 1500, 1e-5), ("benchmark2", 1, 8000, 1e-4), ("benchmark4", 1, 15000, 2e-2)])
+def test_perf_mode_converges_to_classic_optimum(name, K, iters, tol):
     from gcs_admm_b200.lib import Solver
     As, bs, n, d, keys = load_golden(name)
-    s = Solver(pack_graph(As, bs), max_it=iters + 10, eps_abs=0.0, eps_rel=0.0).enable_perf(inner_iters=3)
+    s = Solver(pack_graph(As, bs), max_it=iters + 10, eps_abs=0.0, eps_rel=0.0).enable_perf(inner_iters=K)
     s.step(iters)
     st = s.status()
     assert not st["diverged"] and np.isfinite(st["pri_res"])
