@@ -152,9 +152,14 @@ class _Scaling:
         return WiG
 
 
-def solve_conic_qp(P, q, G, h, l, socs=(), E=None, f=None, *, tol=1e-10, max_iter=80, reg=1e-13, centrality=1e-2):
+def solve_conic_qp(P, q, G, h, l, socs=(), E=None, f=None, *, tol=1e-10, max_iter=80, reg=1e-13, centrality=1e-2,
+                   augmented=False, static_reg=1e-9):
     """Solve the conic QP above.  ``G`` rows: first ``l`` linear inequalities, then
-    the SOC blocks of sizes ``socs`` (each block (t; w) means t >= ||w||)."""
+    the SOC blocks of sizes ``socs`` (each block (t; w) means t >= ||w||).
+
+    ``augmented=True``: the Newton systems are solved on the sparse quasi-definite augmented matrix
+    ``[P + dI, E', G'; E, -dI, 0; G, 0, -W'W]`` (sparse LU, static regularisation ``d`` removed by iterative
+    refinement) instead of the dense normal equations — for large, sparse, degenerate programs (``classic.py``)."""
     n = q.shape[0]
     cone = _Cone(l, socs)
     P = np.zeros((n, n)) if P is None else np.asarray(P, float)
@@ -163,8 +168,45 @@ def solve_conic_qp(P, q, G, h, l, socs=(), E=None, f=None, *, tol=1e-10, max_ite
         f = np.zeros(0)
     p = E.shape[0]
     e = cone.identity()
+    if augmented:
+        import scipy.sparse as sp
+        from scipy.sparse.linalg import splu
+        Gs, Es, Ps = sp.csc_matrix(G), sp.csc_matrix(E), sp.csc_matrix(P)
+        G, E, P = Gs, Es, Ps            # matrix-vector products below work unchanged on sparse matrices
+        mz = cone.dim
+
+    def kkt_factor_aug(W):
+        if W is None:
+            W2 = sp.identity(mz, format="csc")
+        else:
+            dlin = W.d * W.d
+            blocks = [sp.diags(dlin)] if cone.l else []
+            for k, (a, b) in enumerate(cone.blocks):
+                q_ = b - a
+                B = np.empty((q_, q_))
+                for j in range(q_):
+                    ej = np.zeros(q_); ej[j] = 1.0
+                    B[:, j] = W._soc(k, W._soc(k, ej, False), False)
+                blocks.append(sp.csc_matrix(B))
+            W2 = sp.block_diag(blocks, format="csc")
+        K = sp.bmat([[Ps + static_reg * sp.identity(n), Es.T if p else None, Gs.T],
+                     [Es if p else None, -static_reg * sp.identity(p) if p else None, None],
+                     [Gs, None, -W2]], format="csc") if p else \
+            sp.bmat([[Ps + static_reg * sp.identity(n), Gs.T], [Gs, -W2]], format="csc")
+        if not np.all(np.isfinite(K.data)):
+            raise np.linalg.LinAlgError('non-finite KKT matrix')
+        try:
+            return splu(K)      # COLAMD + partial pivoting: measured more robust here than the symmetric-mode orderings
+        except RuntimeError as ex:
+            raise np.linalg.LinAlgError(str(ex))
+
+    def kkt_solve_once_aug(fac, W, bx, by, bz):
+        sol = fac.solve(np.concatenate([bx, by, bz]))
+        return sol[:n], sol[n:n + p], sol[n + p:]
 
     def kkt_factor(W):
+        if augmented:
+            return kkt_factor_aug(W)
         WiG = W.gram_inv(G) if W is not None else G
         H0 = P + WiG.T @ WiG
         # static regularisation relative to the matrix scale, raised until the
@@ -183,8 +225,15 @@ def solve_conic_qp(P, q, G, h, l, socs=(), E=None, f=None, *, tol=1e-10, max_ite
         if p:
             Li_Et = np.linalg.solve(L, E.T)
             S = Li_Et.T @ Li_Et
-            S = S + reg * np.eye(p)
-            LS = np.linalg.cholesky(S)
+            ds = max(reg, 1e-16 * float(np.max(np.diag(S))))
+            while True:             # same lifting as for H0; iterative refinement removes its effect
+                try:
+                    LS = np.linalg.cholesky(S + ds * np.eye(p))
+                    break
+                except np.linalg.LinAlgError:
+                    ds *= 100.0
+                    if ds > 1e-4 * max(1.0, float(np.max(np.diag(S)))):
+                        raise
         else:
             Li_Et = LS = None
         return L, Li_Et, LS, H0
@@ -201,6 +250,8 @@ def solve_conic_qp(P, q, G, h, l, socs=(), E=None, f=None, *, tol=1e-10, max_ite
         return np.linalg.solve(L.T, Lr), dy
 
     def kkt_solve_once(fac, W, bx, by, bz):
+        if augmented:
+            return kkt_solve_once_aug(fac, W, bx, by, bz)
         if W is not None:
             t = W.apply_inv(W.apply_inv(bz))
         else:
