@@ -28,12 +28,15 @@ class _DevArray:
 class CudaBackend:
     """libgcsadmm.so on the current CUDA device, kernels enqueued on torch's current stream."""
 
-    def __init__(self, lp, device, **params):
+    def __init__(self, lp, device, perf=None, **params):
+        """``perf``: None (exact x-update) or dict(inner_iters=K, tables=perf.local_tables(perf_tables(g), lp))."""
         from . import lib
         self.lp = lp
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         self.solver = lib.Solver(lp, device=device, **params)
+        if perf is not None:
+            self.solver.enable_perf(inner_iters=perf.get("inner_iters", 3), tables=perf["tables"])
         self.solver.set_stream(torch.cuda.current_stream().cuda_stream)
         nall = lp.he_off[-1] + lp.nH_ghost
         self.xc = torch.as_tensor(_DevArray(self.solver.xc_ptr(), (int(nall), 5)), device=self.device)

@@ -181,3 +181,18 @@ def perf_tables(g, kappa=1.0):
     cone_off, cone = cone_table(g)
     return dict(vclass=vclass, class_koff=np.array(koff, dtype=np.int32), kinv=np.concatenate(mats), cone_off=cone_off,
                 cone=cone, classes=keys, kappa=float(kappa))
+
+
+def local_tables(T, lp):
+    """Tables of one rank's share of the graph (``partition.LocalProblem``): the class inverses are global, the
+    per-vertex class ids and cone records are sliced in the rank's vertex order."""
+    lv = np.asarray(lp.global_vertices, dtype=np.int64)
+    off = T["cone_off"].astype(np.int64)
+    cnt = off[lv + 1] - off[lv]
+    loff = np.zeros(lv.shape[0] + 1, dtype=np.int64)
+    np.cumsum(cnt, out=loff[1:])
+    rec = T["cone"].reshape(-1, 12)
+    idx = np.repeat(off[lv] - loff[:-1], cnt) + np.arange(int(loff[-1]))
+    out = dict(T)
+    out.update(vclass=T["vclass"][lv].copy(), cone_off=loff.astype(np.int32), cone=np.ascontiguousarray(rec[idx]))
+    return out

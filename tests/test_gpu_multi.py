@@ -23,7 +23,11 @@ torch.cuda.set_device(rank)
 dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
 g = grid_packed_graph(12)
 lp = split_graph(g, partition_vertices(g, world), world)[rank]
-be = CudaBackend(lp, rank)
+pf = None
+if int(os.environ.get("GCS_PERF", "0")):
+    from gcs_admm_b200 import perf
+    pf = dict(inner_iters=int(os.environ["GCS_PERF"]), tables=perf.local_tables(perf.perf_tables(g), lp))
+be = CudaBackend(lp, rank, perf=pf)
 drv = DistributedADMM(lp, be)
 drv.iterate(20)
 x_v, z_v, y_v, z_e = be.solution()
@@ -34,7 +38,8 @@ dist.destroy_process_group()
 '''
 
 
-def test_two_gpus_match_one(tmp_path):
+@pytest.mark.parametrize("perf_k", [0, 2])
+def test_two_gpus_match_one(tmp_path, perf_k):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -42,11 +47,13 @@ def test_two_gpus_match_one(tmp_path):
     from gcs_admm_b200.lib import Solver
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, GCS_ROOT=ROOT, GCS_OUT=str(tmp_path))
+    env = dict(os.environ, GCS_ROOT=ROOT, GCS_OUT=str(tmp_path), GCS_PERF=str(perf_k))
     subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)], env=env, timeout=600)
+                           "--master-addr", "127.0.0.1", "--master-port", str(29533 + perf_k), str(script)], env=env, timeout=600)
     g = grid_packed_graph(12)
     s = Solver(g)
+    if perf_k:
+        s.enable_perf(inner_iters=perf_k)
     s.step(20)
     _, _, _, z = s.solution()
     rho, pri, dual = s.history()

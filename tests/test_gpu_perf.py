@@ -65,3 +65,18 @@ def test_perf_mode_rounds_to_the_reference_path():
     gold_on = {k for k, y in zip(keys, d["v3_y_v_rounded"]) if y > 0.5}
     assert set(path) == gold_on
     s.close()
+
+
+def test_grid_fixed_point_equals_our_classic_solver():
+    """north_star: configurations without a stored reference run are compared with classic_solver — here OUR Drake-free one."""
+    from gcs_admm_b200.classic import solve_classic
+    from gcs_admm_b200.generator import grid_problem, packed_to_dicts
+    from gcs_admm_b200.lib import Solver
+    off, A, b, s_pt, t_pt = grid_problem(6)
+    As, bs = packed_to_dicts(off, A, b)
+    ref = solve_classic(As, bs, 2, round_solution=False)
+    assert ref["status"] == "optimal"
+    s = Solver(pack_graph(As, bs), max_it=40010, eps_abs=0.0, eps_rel=0.0).enable_perf(inner_iters=1)
+    s.step(40000)
+    assert abs(_cost(s) - ref["cost"]) <= 1e-3 * ref["cost"]
+    s.close()
