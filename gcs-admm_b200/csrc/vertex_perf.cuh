@@ -64,18 +64,17 @@ static inline int gcs_perf_state_stride(int dcap) { return 2 * (3 * 4 * (dcap + 
 // exact projection of c onto the cone spanned by the rays r_k = (V_k, 1), k = 0..nv-1 (counter-clockwise).
 // record k: V_k (2) | unit outward normal n_k of the face between rays k and k+1 (3) | 1/|r_k|^2 | sector normals ma, mb (3 + 3)
 // The projection is c itself, or lies on a face (inside its sector), on a ray, or is the apex: take the nearest candidate.
-GCS_DEV void gcs_cone_project(const double *cone, int nv, double c0, double c1, double c2, double &q0, double &q1, double &q2) {
-    double bd = c0 * c0 + c1 * c1 + c2 * c2;     // the apex
-    q0 = 0.0; q1 = 0.0; q2 = 0.0;
-    bool inside = true;
-    for (int k = 0; k < nv; ++k) {
+// Candidates are coded  -1 apex | 2k ray k | 2k+1 face k  and scanned in that order with a strict "<", so the result does
+// not depend on how the scan is split over lanes (ties go to the smallest code).
+GCS_DEV void gcs_cone_scan(const double *cone, int nv, int first, int step, double c0, double c1, double c2, double &bd, int &code, bool &inside) {
+    for (int k = first; k < nv; k += step) {
         const double *ck = cone + GCS_CONE_REC * k;
         const double rx = ck[0], ry = ck[1];
         const double tau = (c0 * rx + c1 * ry + c2) * ck[5];                  // ray k
         if (tau > 0.0) {
             const double e0 = c0 - tau * rx, e1 = c1 - tau * ry, e2 = c2 - tau;
             const double dd = e0 * e0 + e1 * e1 + e2 * e2;
-            if (dd < bd) { bd = dd; q0 = tau * rx; q1 = tau * ry; q2 = tau; }
+            if (dd < bd) { bd = dd; code = 2 * k; }
         }
         const double nx = ck[2], ny = ck[3], nh = ck[4];
         const double dist = nx * c0 + ny * c1 + nh * c2;
@@ -84,11 +83,32 @@ GCS_DEV void gcs_cone_project(const double *cone, int nv, double c0, double c1, 
             const double p0 = c0 - dist * nx, p1 = c1 - dist * ny, p2 = c2 - dist * nh;
             if (p0 * ck[6] + p1 * ck[7] + p2 * ck[8] >= 0.0 && p0 * ck[9] + p1 * ck[10] + p2 * ck[11] >= 0.0) {
                 const double dd = dist * dist;
-                if (dd < bd) { bd = dd; q0 = p0; q1 = p1; q2 = p2; }
+                if (dd < bd) { bd = dd; code = 2 * k + 1; }
             }
         }
     }
-    if (inside) { q0 = c0; q1 = c1; q2 = c2; }
+}
+GCS_DEV void gcs_cone_point(const double *cone, int code, bool inside, double c0, double c1, double c2, double &q0, double &q1, double &q2) {
+    if (inside) { q0 = c0; q1 = c1; q2 = c2; return; }
+    q0 = 0.0; q1 = 0.0; q2 = 0.0;
+    if (code < 0) return;
+    const double *ck = cone + GCS_CONE_REC * (code >> 1);
+    if (code & 1) {
+        const double nx = ck[2], ny = ck[3], nh = ck[4];
+        const double dist = nx * c0 + ny * c1 + nh * c2;
+        q0 = c0 - dist * nx; q1 = c1 - dist * ny; q2 = c2 - dist * nh;
+    } else {
+        const double rx = ck[0], ry = ck[1];
+        const double tau = (c0 * rx + c1 * ry + c2) * ck[5];
+        q0 = tau * rx; q1 = tau * ry; q2 = tau;
+    }
+}
+GCS_DEV void gcs_cone_project(const double *cone, int nv, double c0, double c1, double c2, double &q0, double &q1, double &q2) {
+    double bd = c0 * c0 + c1 * c1 + c2 * c2;     // the apex
+    int code = -1;
+    bool inside = true;
+    gcs_cone_scan(cone, nv, 0, 1, c0, c1, c2, bd, code, inside);
+    gcs_cone_point(cone, code, inside, c0, c1, c2, q0, q1, q2);
 }
 
 // pair values  pv = M u + m0  (3 per family slot, then the 2 entries of z_1 - z_2)
@@ -215,7 +235,12 @@ GCS_DEV int gcs_vertex_update_perf(const GcsGraphView &G, const GcsStateView &St
         gcs_adjoint(gu, gv, d, jstar, prim, term, lane);
         // v <- v - (1/rho) K1^-1 G_v      (dense n x n table of the vertex class)
         const double irho = 1.0 / rho;
-        GCS_LANE_LOOP(r, n) {
+#ifdef GCS_EMULATE
+        const int mv_full = n;
+#else
+        const int mv_full = n & ~31;                  // whole rounds of 32 rows: one lane per row
+#endif
+        GCS_LANE_LOOP(r, mv_full) {
             // K1^-1 is symmetric: walk column r (= row r) so that the lanes of a warp read consecutive doubles of
             // row k — coalesced, L1-resident table shared by every vertex of the class
             const double *kc = Kinv + r;
@@ -230,34 +255,99 @@ GCS_DEV int gcs_vertex_update_perf(const GcsGraphView &G, const GcsStateView &St
             for (; k < n; ++k) s0 += kc[(size_t)k * n] * gv[k];
             w[r] = vv[r] - irho * ((s0 + s1) + (s2 + s3));            // w doubles as the new v until every lane has read gv / vv
         }
+#ifndef GCS_EMULATE
+        if (n > mv_full) {       // the last R < 32 rows: lp = 2^k lanes per row split the columns, partial sums reduced by shuffles
+            const int R = n - mv_full;
+            int lp = 1, lg = 0;
+            while (2 * lp * R <= 32) { lp *= 2; ++lg; }
+            const int grp = lane >> lg, sub = lane & (lp - 1), r = mv_full + (grp < R ? grp : 0);
+            const double *kc = Kinv + r;
+            double s0 = 0.0, s1 = 0.0;
+            int k = sub;
+            for (; k + lp < n; k += 2 * lp) {
+                s0 += kc[(size_t)k * n] * gv[k];
+                s1 += kc[(size_t)(k + lp) * n] * gv[k + lp];
+            }
+            if (k < n) s0 += kc[(size_t)k * n] * gv[k];
+            double sum = s0 + s1;
+            for (int m = 1; m < lp; m <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
+            if (grp < R && sub == 0) w[r] = vv[r] - irho * sum;
+        }
+#endif
         GCS_SYNC();
         GCS_LANE_LOOP(r, n) vv[r] = (r == 4) ? 0.0 : w[r];     // the epigraph variable t is unused in this mode
         GCS_SYNC();
         gcs_forward(vv, u, d, jstar, prim, term, true, lane);
         gcs_pair_values(u, pv, d, term, L.npair, lane);
-        // c-step and dual step
+        // c-step and dual step: item idx < nitems is a (point, flow) pair, item nitems is |z_1 - z_2|
         const int nitems = term ? 2 * (d + 1) : 4 * (d + 1);
-        GCS_LANE_LOOP(idx, nitems + 1) {
+        auto pair_slot = [&](int idx) {
+            int fam, i, blk;
+            if (term) { fam = 0; i = idx & 1; blk = idx >> 1; } else { fam = idx & 1; i = (idx >> 1) & 1; blk = idx >> 2; }
+            return 3 * gcs_slot(blk, i, fam);
+        };
+        auto norm_item = [&]() {           // block soft-threshold, threshold 1 / sigma
+            const int o = 3 * L.npair;
+            const double r0 = alpha * pv[o] + (1.0 - alpha) * cc[o], r1 = alpha * pv[o + 1] + (1.0 - alpha) * cc[o + 1];
+            const double a0 = r0 + lam[o], a1 = r1 + lam[o + 1], nrm = hypot(a0, a1);
+            const double sc = nrm > 0.0 ? fmax(0.0, 1.0 - 1.0 / (sigma * nrm)) : 0.0;
+            const double q0 = sc * a0, q1 = sc * a1;
+            lam[o] += r0 - q0; lam[o + 1] += r1 - q1;
+            cc[o] = q0; cc[o + 1] = q1;
+        };
+#ifdef GCS_EMULATE
+        const int full_end = nitems + 1;
+#else
+        const int full_end = (nitems + 1) & ~31;      // whole rounds of 32 items: one lane per item
+#endif
+        GCS_LANE_LOOP(idx, full_end) {
             if (idx < nitems) {
-                int fam, i, blk;
-                if (term) { fam = 0; i = idx & 1; blk = idx >> 1; } else { fam = idx & 1; i = (idx >> 1) & 1; blk = idx >> 2; }
-                const int o = 3 * gcs_slot(blk, i, fam);
+                const int o = pair_slot(idx);
                 const double r0 = alpha * pv[o] + (1.0 - alpha) * cc[o], r1 = alpha * pv[o + 1] + (1.0 - alpha) * cc[o + 1],
                              r2 = alpha * pv[o + 2] + (1.0 - alpha) * cc[o + 2];
                 double q0, q1, q2;
                 gcs_cone_project(S + L.cone, nv, r0 + lam[o], r1 + lam[o + 1], r2 + lam[o + 2], q0, q1, q2);
                 lam[o] += r0 - q0; lam[o + 1] += r1 - q1; lam[o + 2] += r2 - q2;
                 cc[o] = q0; cc[o + 1] = q1; cc[o + 2] = q2;
-            } else {           // |z_1 - z_2|: block soft-threshold, threshold 1 / sigma
-                const int o = 3 * L.npair;
-                const double r0 = alpha * pv[o] + (1.0 - alpha) * cc[o], r1 = alpha * pv[o + 1] + (1.0 - alpha) * cc[o + 1];
-                const double a0 = r0 + lam[o], a1 = r1 + lam[o + 1], nrm = hypot(a0, a1);
-                const double sc = nrm > 0.0 ? fmax(0.0, 1.0 - 1.0 / (sigma * nrm)) : 0.0;
-                const double q0 = sc * a0, q1 = sc * a1;
-                lam[o] += r0 - q0; lam[o + 1] += r1 - q1;
-                cc[o] = q0; cc[o + 1] = q1;
+            } else norm_item();
+        }
+#ifndef GCS_EMULATE
+        {   // the last R < 32 items: lp = 2^k lanes per item share the scan of its faces, then reduce (value, code) by shuffles
+            const int R = nitems + 1 - full_end;
+            if (R > 0) {
+                int lp = 1, lg = 0;
+                while (2 * lp * R <= 32) { lp *= 2; ++lg; }
+                const int grp = lane >> lg, sub = lane & (lp - 1), idx = full_end + grp;
+                const bool pair = grp < R && idx < nitems;
+                const int o = pair ? pair_slot(idx) : 0;
+                double r0 = 0.0, r1 = 0.0, r2 = 0.0, c0 = 0.0, c1 = 0.0, c2 = 0.0;
+                if (pair) {
+                    r0 = alpha * pv[o] + (1.0 - alpha) * cc[o]; r1 = alpha * pv[o + 1] + (1.0 - alpha) * cc[o + 1];
+                    r2 = alpha * pv[o + 2] + (1.0 - alpha) * cc[o + 2];
+                    c0 = r0 + lam[o]; c1 = r1 + lam[o + 1]; c2 = r2 + lam[o + 2];
+                }
+                double bd = c0 * c0 + c1 * c1 + c2 * c2;
+                int code = -1;
+                bool inside = true;
+                gcs_cone_scan(S + L.cone, pair ? nv : 0, sub, lp, c0, c1, c2, bd, code, inside);
+                int in_i = inside ? 1 : 0;
+                for (int m = 1; m < lp; m <<= 1) {
+                    const double obd = __shfl_xor_sync(0xffffffffu, bd, m);
+                    const int ocode = __shfl_xor_sync(0xffffffffu, code, m);
+                    in_i &= __shfl_xor_sync(0xffffffffu, in_i, m);
+                    if (obd < bd || (obd == bd && ocode < code)) { bd = obd; code = ocode; }
+                }
+                __syncwarp();
+                if (pair && sub == 0) {
+                    double q0, q1, q2;
+                    gcs_cone_point(S + L.cone, code, in_i != 0, c0, c1, c2, q0, q1, q2);
+                    lam[o] += r0 - q0; lam[o + 1] += r1 - q1; lam[o + 2] += r2 - q2;
+                    cc[o] = q0; cc[o + 1] = q1; cc[o + 2] = q2;
+                }
+                if (grp < R && idx == nitems && sub == 0) norm_item();
             }
         }
+#endif
         GCS_SYNC();
     }
     GCS_LANE_LOOP(q, np3) { st[q] = cc[q]; st[np3 + q] = lam[q]; }
