@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--no-perf-report", dest="perf_report", action="store_false",
                     help="parity runs also time the perf mode on the same graph and report it as a nested object; this switches that off")
     ap.add_argument("--perf-trace-iters", type=int, default=20000, help="perf report: residuals and wall time after this many K=1 iterations from a cold start")
+    ap.add_argument("--dist-graph", action="store_true", help="N > 1: replay one captured CUDA graph per ADMM iteration (kernels + NCCL collectives)")
     ap.add_argument("--residual-run", type=int, default=0, help="also run up to this many iterations with the abs 1e-4 stop and report the time")
     args = ap.parse_args()
     if args.impl == "reference":

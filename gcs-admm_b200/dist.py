@@ -42,6 +42,12 @@ class CudaBackend:
         self.xc = torch.as_tensor(_DevArray(self.solver.xc_ptr(), (int(nall), 5)), device=self.device)
         self.sums = torch.as_tensor(_DevArray(self.solver.sums_ptr(), (8,)), device=self.device)
 
+    supports_graph = True
+
+    def use_stream(self, stream):
+        """enqueue the library's kernels on this torch stream from now on (synchronises the previous one)"""
+        self.solver.set_stream(stream.cuda_stream)
+
     def vertex_update(self):
         self.solver.vertex_update()
 
@@ -65,8 +71,15 @@ class CudaBackend:
 
 
 class DistributedADMM:
-    def __init__(self, lp, backend, group=None):
+    def __init__(self, lp, backend, group=None, graph=False):
+        """``graph``: after two eager iterations (NCCL warmed up) one whole iteration — K1, halo pack, all_to_all, unpack,
+        K2-K4, all_reduce, K5 — is captured into a CUDA graph and replayed: one launch per ADMM iteration instead of ~10
+        launches + 2 collective calls from Python (0.2 ms -> tens of microseconds of per-iteration overhead).  Call
+        ``release_graph()`` before ``destroy_process_group()``: NCCL cannot tear a communicator down while a graph that
+        captured its collectives is alive."""
         self.lp, self.be, self.group = lp, backend, group
+        self._graph, self._eager_done = None, 0
+        self._want_graph = bool(graph) and getattr(backend, "supports_graph", False)
         dev = backend.xc.device
         self.send_idx = torch.as_tensor(lp.send_idx, dtype=torch.long, device=dev)
         self.in_splits = [int(x) * 5 for x in lp.send_counts]
@@ -84,7 +97,7 @@ class DistributedADMM:
         dist.all_to_all_single(self.recv, send, self.out_splits, self.in_splits, group=self.group)
         xc[self.nH_own:].copy_(self.recv.view(-1, 5))
 
-    def iterate(self, k=1):
+    def _iterate_eager(self, k):
         for _ in range(k):
             self.be.vertex_update()
             self.exchange()
@@ -92,6 +105,35 @@ class DistributedADMM:
             if self.world > 1:
                 dist.all_reduce(self.be.sums, group=self.group)
             self.be.control()
+
+    def _capture(self):
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        self.be.use_stream(side)                 # before the capture starts: set_stream synchronises
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            self._iterate_eager(1)
+        cur.wait_stream(side)
+        self.be.use_stream(cur)
+        self._graph = g
+
+    def release_graph(self):
+        self._graph = None
+        self._want_graph = False
+
+    def iterate(self, k=1):
+        if self._want_graph and self.world > 1:
+            while k > 0 and self._eager_done < 2:
+                self._iterate_eager(1)
+                self._eager_done += 1
+                k -= 1
+            if k > 0 and self._graph is None:
+                self._capture()
+            for _ in range(k):
+                self._graph.replay()
+            return
+        self._iterate_eager(k)
 
     def run(self, max_iters, check_every=8):
         done = 0

@@ -37,7 +37,7 @@ def main(args):
         """-> (ms per iteration [max over ranks], clocks, e2e seconds [max over ranks])"""
         pf = dict(inner_iters=inner, tables=tables) if mode == "perf" else None
         be = CudaBackend(lp, local_rank, perf=pf, max_it=max(1000, args.steps + burn + 8), eps_abs=0.0, eps_rel=0.0)
-        drv = DistributedADMM(lp, be)
+        drv = DistributedADMM(lp, be, graph=args.dist_graph)
         drv.iterate(burn)
         torch.cuda.synchronize()
         ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -61,18 +61,20 @@ def main(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_max = float(t.item())
         clocks = sampler.finish() if sampler else None
+        drv.release_graph()
         be.close()
         # end to end: local graph upload + K iterations + local solution download, wall clock, max over ranks
         dist.barrier()
         t0 = time.perf_counter()
         be2 = CudaBackend(lp, local_rank, perf=pf, max_it=max(1000, n_e2e + 8), eps_abs=0.0, eps_rel=0.0)
-        drv2 = DistributedADMM(lp, be2)
+        drv2 = DistributedADMM(lp, be2, graph=args.dist_graph)
         drv2.iterate(n_e2e)
         be2.solution()
         be2.history()
         e2e = time.perf_counter() - t0
         t = torch.tensor([e2e], dtype=torch.float64, device=be2.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        drv2.release_graph()
         be2.close()
         return ms_max / args.steps, clocks, float(t.item())
 
@@ -100,7 +102,8 @@ def main(args):
                 "ms_per_step": per, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"grid{args.grid}x{args.grid} 2-D GCS: {g.nV} vertices, {g.nE} directed edges, strips over {world} GPUs",
                            "mode": bench.MODE_TEXT[args.mode] + (f", K={args.inner}" if args.mode == "perf" else ""), "l2": "flushed (256 MiB) before every timed iteration", "burn_in_iterations": burn,
-                           "halo_half_edges_rank0": int(lp.nH_ghost), "collectives": "all_to_all_single(halo) + all_reduce(8 doubles) per iteration, NCCL"},
+                           "halo_half_edges_rank0": int(lp.nH_ghost), "collectives": "all_to_all_single(halo) + all_reduce(8 doubles) per iteration, NCCL",
+                           "cuda_graph": bool(args.dist_graph)},
                 "clocks": clocks,
                 "e2e": {"value": n_e2e / e2e, "unit": bench.UNIT, "h2d_bytes_per_step": gs_bytes / n_e2e,
                         "d2h_bytes_per_step": out_bytes / n_e2e, "note": "per rank, from a cold start: local graph upload + (burn_in + K) iterations + solution download; max over ranks"},
