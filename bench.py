@@ -66,7 +66,7 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons}
 
 
-def cpu_baseline(G_sample, V_full, iters=2):
+def cpu_baseline(G_sample, V_full, iters=10):
     """C oracle (port of the reference's algorithm, OpenMP over vertices) on a bounded sample:
     a G_sample x G_sample grid of the same family; cost per iteration is linear in |V|, so the
     figure is scaled to the full graph's vertex count."""
@@ -76,13 +76,13 @@ def cpu_baseline(G_sample, V_full, iters=2):
     from gcs_admm_b200.generator import grid_packed_graph
     g = grid_packed_graph(G_sample)
     o = COracle(g)
-    o.step(1)                       # warm-up (first iteration is the all-zero start)
+    o.step(G_sample + 10)           # same burn-in rule as the GPU arm: the cold-start wave has reached every vertex
     t0 = time.perf_counter()
     o.step(iters)
     dt = (time.perf_counter() - t0) / iters
     its_sample = 1.0 / dt
     return {"value": its_sample * g.nV / V_full, "unit": UNIT, "cores": olib().gcso_num_threads(), "kind": "port",
-            "sample": f"{iters} ADMM iterations of the C oracle on the {G_sample}x{G_sample} grid ({g.nV} vertices, "
+            "sample": f"{iters} ADMM iterations (after a burn-in of {G_sample + 10}) of the C oracle on the {G_sample}x{G_sample} grid ({g.nV} vertices, "
                       f"{its_sample:.3f} it/s), scaled by |V| to the {V_full}-vertex workload"}
 
 
@@ -100,13 +100,14 @@ def run_reference(args):
     Gs = min(args.grid, 48)
     g = grid_packed_graph(Gs)
     o = COracle(g)
+    o.step(Gs + 10)                 # same burn-in rule as the GPU arm (every vertex program live), untimed
     for _ in range(args.warmup):
         o.step(1)
     t0 = time.perf_counter()
     o.step(args.steps)
     dt = time.perf_counter() - t0
     val = args.steps / dt * g.nV / V_full
-    sample = (f"each step = one ADMM iteration of the C oracle on the {Gs}x{Gs} grid ({g.nV} vertices), "
+    sample = (f"each step = one ADMM iteration of the C oracle (after a burn-in of {Gs + 10}) on the {Gs}x{Gs} grid ({g.nV} vertices), "
               f"scaled by |V| to the {V_full}-vertex workload")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps * V_full / g.nV, "higher_is_better": True,
@@ -114,6 +115,17 @@ def run_reference(args):
             "config": {"workload": f"grid{args.grid}x{args.grid} 2-D GCS ({V_full} vertices)", "sample": sample},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": olib().gcso_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.no_classic:
+        # the reference's other CPU solver (classic_solver.py: one monolithic conic program), Drake-free restatement, on a bounded sample
+        from gcs_admm_b200.classic import solve_classic
+        from gcs_admm_b200.generator import grid_problem, packed_to_dicts
+        off, A, b, _, _ = grid_problem(8)
+        As, bs = packed_to_dicts(off, A, b)
+        t0 = time.perf_counter()
+        rc = solve_classic(As, bs, 2, round_solution=False)
+        line["classic_solver"] = {"workload": f"grid8x8 ({len(As)} vertices)", "seconds": time.perf_counter() - t0, "status": rc["status"],
+                                  "ip_iterations": rc["iterations"], "cost": rc["cost"], "kind": "port (gcs_admm_b200.classic, sparse interior point, 1 thread)",
+                                  "note": "whole solve to optimality, not an iteration rate; 258 vertices take ~90 s, so it is not run at the metric's size"}
     print(json.dumps(line))
 
 
@@ -129,6 +141,7 @@ def main():
     ap.add_argument("--grid", type=int, default=316, help="G: the workload is the G x G grid GCS (316 -> 99 858 vertices)")
     ap.add_argument("--impl", type=str, default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-classic", action="store_true", help="reference arm: skip the classic-solver sample")
     ap.add_argument("--burn-in", type=int, default=-1, help="untimed iterations before the timed window (default: grid side + 10, so that the\n                    cold-start wave has reached every vertex and no vertex program is the trivial all-zero one)")
     ap.add_argument("--mode", type=str, default="parity", choices=["parity", "perf"],
                     help="parity: exact interior-point x-update (reference trajectory); perf: K closed-form splitting iterations per x-update")

@@ -225,7 +225,7 @@ def solve_conic_qp(P, q, G, h, l, socs=(), E=None, f=None, *, tol=1e-10, max_ite
         if p:
             Li_Et = np.linalg.solve(L, E.T)
             S = Li_Et.T @ Li_Et
-            ds = max(reg, 1e-16 * float(np.max(np.diag(S))))
+            ds = reg
             while True:             # same lifting as for H0; iterative refinement removes its effect
                 try:
                     LS = np.linalg.cholesky(S + ds * np.eye(p))

@@ -299,9 +299,7 @@ extern "C" int gcsadmm_scratch_bytes(int max_live_degree, int max_rows) {
 template <typename T>
 static int upload(T **dst, const T *src, size_t n) {
     if (n == 0) n = 1, src = nullptr;
-    const size_t pad = getenv("GCS_PAD") ? (size_t)atol(getenv("GCS_PAD")) : 0;   // debugging aid: guard bytes behind every array
-    cudaError_t e = cudaMalloc((void **)dst, n * sizeof(T) + pad);
-    if (e == cudaSuccess && pad) cudaMemset(*dst, 0, n * sizeof(T) + pad);
+    cudaError_t e = cudaMalloc((void **)dst, n * sizeof(T));
     if (e != cudaSuccess) return set_err(GCS_E_NOMEM, "cudaMalloc(%s bytes): %s", "", cudaGetErrorString(e));
     if (src) { e = cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice); if (e != cudaSuccess) return set_err(GCS_E_CUDA, "cudaMemcpy H2D: %s", cudaGetErrorString(e)); }
     else cudaMemset(*dst, 0, n * sizeof(T));
@@ -720,7 +718,6 @@ extern "C" int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *c) {
     int w = (int)(prop.sharedMemPerBlockOptin / per_warp);
     if (w < 1) return set_err(GCS_E_INVALID, "perf-mode vertex state too large for shared memory%s", "");
     if (w > PERF_MAX_WARPS) w = PERF_MAX_WARPS;
-    if (getenv("GCS_PERF_WARPS")) { int e = atoi(getenv("GCS_PERF_WARPS")); if (e >= 1 && e < w) w = e; }
     h->perf_warps = w; h->perf_smem = (int)(w * per_warp);
     h->perf_blocks = (h->nV + w - 1) / w;
     CK(cudaFuncSetAttribute(vertex_perf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->perf_smem));

@@ -117,3 +117,21 @@ def test_inexact_admm_converges_to_classic_optimum(emu):
         a.step()
     assert a.pri[-1] < 1e-6 and a.dual[-1] < 1e-6
     assert abs(a.cost() - float(d["classic_cost"])) < 1e-5
+
+
+def test_local_tables_slice_the_global_ones():
+    """multi-GPU perf mode: a rank's tables are the global class inverses + its own vertices' class ids / cone records"""
+    from gcs_admm_b200 import perf
+    from gcs_admm_b200.generator import grid_packed_graph
+    from gcs_admm_b200.partition import partition_vertices, split_graph
+    g = grid_packed_graph(10)
+    T = perf.perf_tables(g)
+    seen = 0
+    for lp in split_graph(g, partition_vertices(g, 3), 3):
+        L = perf.local_tables(T, lp)
+        assert L["kinv"] is T["kinv"] and L["cone_off"][-1] == L["cone"].shape[0] and L["cone_off"].shape[0] == lp.nV + 1
+        for i, v in enumerate(lp.global_vertices):
+            assert L["vclass"][i] == T["vclass"][v]
+            assert np.array_equal(L["cone"][L["cone_off"][i]:L["cone_off"][i + 1]], T["cone"][T["cone_off"][v]:T["cone_off"][v + 1]])
+        seen += lp.nV
+    assert seen == g.nV
