@@ -184,7 +184,23 @@ GCS_DEV int gcs_vertex_update_perf(const GcsGraphView &G, const GcsStateView &St
         return 0;
     }
     int *out = (int *)(S + L.ints), *prim = out + L.dcap, *hid = out + 2 * L.dcap;
-    int d = 0;
+    int d = 0, jstar = -1;
+    bool have_jstar = false;
+#ifndef GCS_EMULATE
+    if (h1 - h0 <= 32) {       // one lane per half-edge: live list by ballot + prefix popcount instead of a serial scan
+        const int f = lane < h1 - h0 ? G.he_flags[h0 + lane] : GCS_HE_ZERO;
+        const bool live = !(f & GCS_HE_ZERO);
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const int k = __popc(m & ((1u << lane) - 1u));
+            out[k] = f & GCS_HE_OUT; hid[k] = h0 + lane; prim[k] = (type == GCS_VT_TARGET) ? 1 : (f & GCS_HE_OUT);
+        }
+        d = __popc(m);
+        const unsigned pm = __ballot_sync(0xffffffffu, live && ((type == GCS_VT_TARGET) || (f & GCS_HE_OUT)));
+        if (pm) jstar = __popc(m & ((1u << (31 - __clz(pm))) - 1u));      // the last primary block is the dependent one
+        have_jstar = true;
+    } else
+#endif
     for (int h = h0; h < h1; ++h) {
         const int f = G.he_flags[h];
         if (f & GCS_HE_ZERO) continue;
@@ -196,8 +212,7 @@ GCS_DEV int gcs_vertex_update_perf(const GcsGraphView &G, const GcsStateView &St
     const int c0 = T.cone_off[v], nv = T.cone_off[v + 1] - c0;
     GCS_LANE_LOOP(q, GCS_CONE_REC * nv) S[L.cone + q] = T.cone[GCS_CONE_REC * (size_t)c0 + q];
     GCS_SYNC();
-    int jstar = -1;
-    for (int j = 0; j < d; ++j) if (prim[j]) jstar = j;
+    if (!have_jstar) for (int j = 0; j < d; ++j) if (prim[j]) jstar = j;
     GCS_LANE_LOOP(q, 5 * d) {
         const int j = q / 5, c = q - 5 * j, h = hid[j], e = G.he_edge[h];
         S[L.tgt + q] = St.z[5 * (size_t)e + c] + mu_scale * St.mu[5 * (size_t)h + c];
@@ -246,11 +261,11 @@ GCS_DEV int gcs_vertex_update_perf(const GcsGraphView &G, const GcsStateView &St
             const double *kc = Kinv + r;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             int k = 0;
-            for (; k + 3 < n; k += 4) {
-                s0 += kc[(size_t)k * n] * gv[k];
-                s1 += kc[(size_t)(k + 1) * n] * gv[k + 1];
-                s2 += kc[(size_t)(k + 2) * n] * gv[k + 2];
-                s3 += kc[(size_t)(k + 3) * n] * gv[k + 3];
+            for (; k + 7 < n; k += 8) {                   // 8 independent table loads in flight per lane
+                const double a0 = kc[(size_t)k * n], a1 = kc[(size_t)(k + 1) * n], a2 = kc[(size_t)(k + 2) * n], a3 = kc[(size_t)(k + 3) * n];
+                const double a4 = kc[(size_t)(k + 4) * n], a5 = kc[(size_t)(k + 5) * n], a6 = kc[(size_t)(k + 6) * n], a7 = kc[(size_t)(k + 7) * n];
+                s0 += a0 * gv[k]; s1 += a1 * gv[k + 1]; s2 += a2 * gv[k + 2]; s3 += a3 * gv[k + 3];
+                s0 += a4 * gv[k + 4]; s1 += a5 * gv[k + 5]; s2 += a6 * gv[k + 6]; s3 += a7 * gv[k + 7];
             }
             for (; k < n; ++k) s0 += kc[(size_t)k * n] * gv[k];
             w[r] = vv[r] - irho * ((s0 + s1) + (s2 + s3));            // w doubles as the new v until every lane has read gv / vv
