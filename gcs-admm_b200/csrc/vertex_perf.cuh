@@ -163,17 +163,46 @@ GCS_DEV int gcs_vertex_update_perf(const GcsGraphView &G, const GcsStateView &St
                                    double mu_scale, const GcsPerfLayout &L, double *S, int lane) {
     const int h0 = G.he_off[v], h1 = G.he_off[v + 1];
     const int type = G.vtype[v];
-    GCS_LANE_LOOP(i, h1 - h0) {                // forced-zero half-edges, as in the exact kernel
-        const int h = h0 + i;
-        if (G.he_flags[h] & GCS_HE_ZERO) {
+    // Loads are issued in two dependent stages only: (flags, edge ids, cone records, stored state) -> (edge variables, duals).
+#ifndef GCS_EMULATE
+    const bool fast = h1 - h0 <= 32;           // one lane per half-edge keeps its flags / edge id in registers
+    int f = GCS_HE_ZERO, e_l = 0;
+    if (fast && lane < h1 - h0) { f = G.he_flags[h0 + lane]; e_l = G.he_edge[h0 + lane]; }
+#else
+    const bool fast = false;
+    const int f = 0, e_l = 0;
+#endif
+    const int np3 = 3 * L.npair + 2;
+    const int c0 = T.cone_off[v], nv = T.cone_off[v + 1] - c0;
+    double *st = T.state + (size_t)v * T.state_stride;
+    if (type != GCS_VT_DEAD) {
+        GCS_LANE_LOOP(q, GCS_CONE_REC * nv) S[L.cone + q] = T.cone[GCS_CONE_REC * (size_t)c0 + q];
+        GCS_LANE_LOOP(q, np3) { S[L.c + q] = st[q]; S[L.lam + q] = mu_scale * st[np3 + q]; }    // sigma = kappa rho: lam rescales with mu
+    }
+    if (fast) {                                 // forced-zero half-edges, as in the exact kernel
+        if (lane < h1 - h0 && (f & GCS_HE_ZERO)) {
+            const int h = h0 + lane;
             double *x = St.xc + 5 * (size_t)h;
             double x0 = 0.0, x1 = 0.0;
-            if (!(G.he_flags[h] & GCS_HE_OUT)) {
-                const int e = G.he_edge[h];
-                x0 = St.z[5 * (size_t)e] + mu_scale * St.mu[5 * (size_t)h];
-                x1 = St.z[5 * (size_t)e + 1] + mu_scale * St.mu[5 * (size_t)h + 1];
+            if (!(f & GCS_HE_OUT)) {
+                x0 = St.z[5 * (size_t)e_l] + mu_scale * St.mu[5 * (size_t)h];
+                x1 = St.z[5 * (size_t)e_l + 1] + mu_scale * St.mu[5 * (size_t)h + 1];
             }
             x[0] = x0; x[1] = x1; x[2] = 0.0; x[3] = 0.0; x[4] = 0.0;
+        }
+    } else {
+        GCS_LANE_LOOP(i, h1 - h0) {
+            const int h = h0 + i;
+            if (G.he_flags[h] & GCS_HE_ZERO) {
+                double *x = St.xc + 5 * (size_t)h;
+                double x0 = 0.0, x1 = 0.0;
+                if (!(G.he_flags[h] & GCS_HE_OUT)) {
+                    const int e = G.he_edge[h];
+                    x0 = St.z[5 * (size_t)e] + mu_scale * St.mu[5 * (size_t)h];
+                    x1 = St.z[5 * (size_t)e + 1] + mu_scale * St.mu[5 * (size_t)h + 1];
+                }
+                x[0] = x0; x[1] = x1; x[2] = 0.0; x[3] = 0.0; x[4] = 0.0;
+            }
         }
     }
     if (type == GCS_VT_DEAD) {
@@ -185,40 +214,38 @@ GCS_DEV int gcs_vertex_update_perf(const GcsGraphView &G, const GcsStateView &St
     }
     int *out = (int *)(S + L.ints), *prim = out + L.dcap, *hid = out + 2 * L.dcap;
     int d = 0, jstar = -1;
-    bool have_jstar = false;
 #ifndef GCS_EMULATE
-    if (h1 - h0 <= 32) {       // one lane per half-edge: live list by ballot + prefix popcount instead of a serial scan
-        const int f = lane < h1 - h0 ? G.he_flags[h0 + lane] : GCS_HE_ZERO;
+    if (fast) {                // live list by ballot + prefix popcount instead of a serial scan; each live lane gathers its own targets
         const bool live = !(f & GCS_HE_ZERO);
         const unsigned m = __ballot_sync(0xffffffffu, live);
         if (live) {
-            const int k = __popc(m & ((1u << lane) - 1u));
-            out[k] = f & GCS_HE_OUT; hid[k] = h0 + lane; prim[k] = (type == GCS_VT_TARGET) ? 1 : (f & GCS_HE_OUT);
+            const int k = __popc(m & ((1u << lane) - 1u)), h = h0 + lane;
+            out[k] = f & GCS_HE_OUT; hid[k] = h; prim[k] = (type == GCS_VT_TARGET) ? 1 : (f & GCS_HE_OUT);
+            const double *zz = St.z + 5 * (size_t)e_l, *mm = St.mu + 5 * (size_t)h;
+            double *t = S + L.tgt + 5 * k;
+            for (int c = 0; c < 5; ++c) t[c] = zz[c] + mu_scale * mm[c];
         }
         d = __popc(m);
         const unsigned pm = __ballot_sync(0xffffffffu, live && ((type == GCS_VT_TARGET) || (f & GCS_HE_OUT)));
         if (pm) jstar = __popc(m & ((1u << (31 - __clz(pm))) - 1u));      // the last primary block is the dependent one
-        have_jstar = true;
     } else
 #endif
-    for (int h = h0; h < h1; ++h) {
-        const int f = G.he_flags[h];
-        if (f & GCS_HE_ZERO) continue;
-        if (lane == 0) { out[d] = f & GCS_HE_OUT; hid[d] = h; prim[d] = (type == GCS_VT_TARGET) ? 1 : (f & GCS_HE_OUT); }
-        d++;
+    {
+        for (int h = h0; h < h1; ++h) {
+            const int fl = G.he_flags[h];
+            if (fl & GCS_HE_ZERO) continue;
+            if (lane == 0) { out[d] = fl & GCS_HE_OUT; hid[d] = h; prim[d] = (type == GCS_VT_TARGET) ? 1 : (fl & GCS_HE_OUT); }
+            d++;
+        }
+        GCS_SYNC();
+        for (int j = 0; j < d; ++j) if (prim[j]) jstar = j;
+        GCS_LANE_LOOP(q, 5 * d) {
+            const int j = q / 5, c = q - 5 * j, h = hid[j], e = G.he_edge[h];
+            S[L.tgt + q] = St.z[5 * (size_t)e + c] + mu_scale * St.mu[5 * (size_t)h + c];
+        }
     }
     const bool term = type != GCS_VT_GENERIC;
-    const int n = 5 * d, nu = GCS_NCORE + 5 * d, np3 = 3 * L.npair + 2;
-    const int c0 = T.cone_off[v], nv = T.cone_off[v + 1] - c0;
-    GCS_LANE_LOOP(q, GCS_CONE_REC * nv) S[L.cone + q] = T.cone[GCS_CONE_REC * (size_t)c0 + q];
-    GCS_SYNC();
-    if (!have_jstar) for (int j = 0; j < d; ++j) if (prim[j]) jstar = j;
-    GCS_LANE_LOOP(q, 5 * d) {
-        const int j = q / 5, c = q - 5 * j, h = hid[j], e = G.he_edge[h];
-        S[L.tgt + q] = St.z[5 * (size_t)e + c] + mu_scale * St.mu[5 * (size_t)h + c];
-    }
-    double *st = T.state + (size_t)v * T.state_stride;
-    GCS_LANE_LOOP(q, np3) { S[L.c + q] = st[q]; S[L.lam + q] = mu_scale * st[np3 + q]; }    // sigma = kappa rho: lam rescales with mu
+    const int n = 5 * d, nu = GCS_NCORE + 5 * d;
     GCS_SYNC();
     double *u = S + L.u, *gu = S + L.gu, *vv = S + L.v, *gv = S + L.gv, *pv = S + L.pv, *cc = S + L.c, *lam = S + L.lam, *w = S + L.w;
     const double *tgt = S + L.tgt;
