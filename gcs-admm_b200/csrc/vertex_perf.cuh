@@ -22,6 +22,14 @@
 #pragma once
 #include "vertex_update.cuh"
 #define GCS_CONE_REC 12   // doubles per polygon vertex in the cone table
+// the per-vertex (c, lam) records are streamed once per iteration: evict-first loads / stores keep L2 for xc, z, mu and the tables
+#if defined(__CUDA_ARCH__)
+#define GCS_LD_STREAM(p) __ldcs(p)
+#define GCS_ST_STREAM(p, x) __stcs((p), (x))
+#else
+#define GCS_LD_STREAM(p) (*(p))
+#define GCS_ST_STREAM(p, x) (*(p) = (x))
+#endif
 
 struct GcsPerfTables {
     const int *vclass;         // [nV] class id (-1: vertex not solved here: dead)
@@ -177,7 +185,7 @@ GCS_DEV int gcs_vertex_update_perf(const GcsGraphView &G, const GcsStateView &St
     double *st = T.state + (size_t)v * T.state_stride;
     if (type != GCS_VT_DEAD) {
         GCS_LANE_LOOP(q, GCS_CONE_REC * nv) S[L.cone + q] = T.cone[GCS_CONE_REC * (size_t)c0 + q];
-        GCS_LANE_LOOP(q, np3) { S[L.c + q] = st[q]; S[L.lam + q] = mu_scale * st[np3 + q]; }    // sigma = kappa rho: lam rescales with mu
+        GCS_LANE_LOOP(q, np3) { S[L.c + q] = GCS_LD_STREAM(st + q); S[L.lam + q] = mu_scale * GCS_LD_STREAM(st + np3 + q); }    // sigma = kappa rho: lam rescales with mu
     }
     if (fast) {                                 // forced-zero half-edges, as in the exact kernel
         if (lane < h1 - h0 && (f & GCS_HE_ZERO)) {
@@ -392,7 +400,7 @@ GCS_DEV int gcs_vertex_update_perf(const GcsGraphView &G, const GcsStateView &St
 #endif
         GCS_SYNC();
     }
-    GCS_LANE_LOOP(q, np3) { st[q] = cc[q]; st[np3 + q] = lam[q]; }
+    GCS_LANE_LOOP(q, np3) { GCS_ST_STREAM(st + q, cc[q]); GCS_ST_STREAM(st + np3 + q, lam[q]); }
     GCS_LANE_LOOP(j, d) {     // scatter, edge-canonical order (same as the exact kernel)
         const double *wj = u + gcs_uw(j), *t = tgt + 5 * j;
         double *x = St.xc + 5 * (size_t)hid[j];
