@@ -224,8 +224,8 @@ def main():
     k1_ms = m["k1_ms"]
     traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch, from the committed ncu capture
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
-        if tj.get("workload") == f"grid{args.grid}x{args.grid}" and args.mode == "parity":
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json" if args.mode == "parity" else "r01_k1perf_traffic.json")))
+        if tj.get("workload") == f"grid{args.grid}x{args.grid}" and (args.mode == "parity" or tj.get("inner_iters") == args.inner):
             traffic = tj["traffic_bytes_per_launch"]
     except Exception:
         pass
