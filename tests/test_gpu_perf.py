@@ -80,3 +80,26 @@ def test_grid_fixed_point_equals_our_classic_solver():
     s.step(40000)
     assert abs(_cost(s) - ref["cost"]) <= 1e-3 * ref["cost"]
     s.close()
+
+
+def test_batched_perf_queries_equal_individual_solves():
+    """perf mode on a block-diagonal batch: every problem keeps its own residuals / rho / stop and equals its stand-alone run
+    (the class tables of the batch are a superset of each problem's, so the arithmetic per vertex is identical)."""
+    from gcs_admm_b200.graph import pack_batch
+    from gcs_admm_b200.lib import Solver
+    names = ["benchmark1", "benchmark2", "test3", "benchmark4"]
+    graphs = [pack_graph(*load_golden(n)[:2]) for n in names]
+    big = pack_batch(graphs)
+    sb = Solver(big, max_it=3000).enable_perf(inner_iters=2)
+    stb = sb.run(3000)
+    x_v, z_v, y_v, z_e = sb.solution()
+    for p, g in enumerate(graphs):
+        s = Solver(g, max_it=3000).enable_perf(inner_iters=2)
+        st = s.run(3000)
+        ps = sb.problem_status(p)
+        assert ps["iterations"] == st["iterations"] and ps["converged"] == st["converged"], (names[p], ps, st)
+        xs, zs, ys, es = s.solution()
+        v0, v1, e0, e1 = big.prob_voff[p], big.prob_voff[p + 1], big.prob_eoff[p], big.prob_eoff[p + 1]
+        assert np.allclose(zs, z_v[v0:v1], rtol=0, atol=1e-12) and np.allclose(es, z_e[e0:e1], rtol=0, atol=1e-12)
+        s.close()
+    sb.close()

@@ -50,6 +50,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--queries", type=int, default=4096)
     ap.add_argument("--max-it", type=int, default=1000)
+    ap.add_argument("--mode", default="parity", choices=["parity", "perf"])
+    ap.add_argument("--inner", type=int, default=1, help="K of the perf mode")
+    ap.add_argument("--eps-rel", type=float, default=1e-3, help="reference stop rule (1e-3); perf mode wants a tighter one")
+    ap.add_argument("--eps-abs", type=float, default=1e-4)
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -60,13 +64,16 @@ def main():
     big = pack_batch(graphs)
     t_build = time.perf_counter() - t0
     t0 = time.perf_counter()
-    s = lib.Solver(big, device=local, max_it=args.max_it, check_every=16)
+    s = lib.Solver(big, device=local, max_it=args.max_it, check_every=16, eps_rel=args.eps_rel, eps_abs=args.eps_abs)
+    if args.mode == "perf":
+        s.enable_perf(inner_iters=args.inner)
     st = s.run(args.max_it)
     x_v, z_v, y_v, z_e = s.solution()
     dt = time.perf_counter() - t0
     its = np.array([s.problem_status(p)["iterations"] for p in range(len(graphs))])
     conv = np.array([s.problem_status(p)["converged"] for p in range(len(graphs))])
-    line = {"rank": rank, "world": world, "queries": len(graphs), "vertices": int(big.nV), "edges": int(big.nE),
+    line = {"mode": args.mode + (f" K={args.inner}" if args.mode == "perf" else ""), "eps_rel": args.eps_rel, "eps_abs": args.eps_abs, "max_it": args.max_it,
+            "rank": rank, "world": world, "queries": len(graphs), "vertices": int(big.nV), "edges": int(big.nE),
             "host_build_s": t_build, "solve_s": dt, "problems_per_s": len(graphs) / dt,
             "aggregate_problem_iterations_per_s": float(its.sum()) / dt, "converged": int(conv.sum()),
             "iterations_min_median_max": [int(its.min()), int(np.median(its)), int(its.max())],
