@@ -135,3 +135,20 @@ def test_local_tables_slice_the_global_ones():
             assert np.array_equal(L["cone"][L["cone_off"][i]:L["cone_off"][i + 1]], T["cone"][T["cone_off"][v]:T["cone_off"][v + 1]])
         seen += lp.nV
     assert seen == g.nV
+
+
+def test_emulated_perf_mode_reaches_our_classic_optimum_on_a_generated_problem(emu):
+    """Irregular polygons (up to 10 rows), live degrees up to 14, no stored reference run: the perf-mode fixed point is
+    compared with the Drake-free classic solver (north_star: "compare against classic_solver" where v3 has no run)."""
+    from gcs_admm_b200.classic import solve_classic
+    from gcs_admm_b200.generator import generate_test_2D
+    As, bs, s_pt, t_pt = generate_test_2D(None, -20, 20, 1, 0.9, 40, seed=7)
+    g = pack_graph(As, bs)
+    assert g.max_live_degree > 8 and g.max_rows > 8
+    ref = solve_classic(As, bs, 2, round_solution=False)
+    assert ref["status"] == "optimal"
+    a = EmuPerfADMM(emu, g, K=1)
+    for _ in range(8000):
+        a.step()
+    assert a.pri[-1] < 1e-3 and a.dual[-1] < 1e-3
+    assert abs(a.cost() - ref["cost"]) <= 5e-4 * ref["cost"]
