@@ -112,7 +112,8 @@ def _vertices_batch(off, A, b, tol=1e-9):
     """
     nV = off.shape[0] - 1
     ms = np.diff(off)
-    verts = [None] * nV
+    groups = []
+    cnt = np.zeros(nV, dtype=np.int64)
     for m in np.unique(ms):
         idx = np.nonzero(ms == m)[0]
         rows = off[idx][:, None] + np.arange(m)[None, :]
@@ -128,17 +129,17 @@ def _vertices_batch(off, A, b, tol=1e-9):
         scale = np.maximum(1.0, np.max(np.abs(bg), axis=1))[:, None, None]
         viol = np.einsum('gpk,gmk->gpm', P, Ag) - bg[:, None, :]
         feas = good & np.all(viol <= tol * scale, axis=2)
-        for g, v in enumerate(idx):
-            verts[v] = P[g][feas[g]]
-    kmax = max(1, max(p.shape[0] for p in verts))
+        order = np.argsort(~feas, axis=1, kind="stable")          # feasible intersections first, original order kept
+        groups.append((idx, np.take_along_axis(P, order[..., None], axis=1)))
+        cnt[idx] = feas.sum(axis=1)
+    kmax = max(1, int(cnt.max()) if nV else 1)
     out = np.zeros((nV, kmax, 2))
-    cnt = np.zeros(nV, dtype=np.int64)
-    for v, p in enumerate(verts):
-        k = p.shape[0]
-        cnt[v] = k
-        if k:
-            out[v, :k] = p
-            out[v, k:] = p[0]
+    for idx, Ps in groups:
+        k = min(kmax, Ps.shape[1])
+        out[idx, :k] = Ps[:, :k]
+    pad = np.arange(kmax)[None, :] >= cnt[:, None]
+    out = np.where(pad[..., None], out[:, :1], out)
+    out[cnt == 0] = 0.0
     return out, cnt
 
 
@@ -374,12 +375,18 @@ class PackedGraph:
     def H(self):
         return 2 * self.nE
 
+    def polygon_vertices_batch(self):
+        """(verts[nV, kmax, 2], count[nV]) of every region's polygon, computed once per graph (interior points, cone tables)."""
+        if getattr(self, "_verts", None) is None:
+            self._verts = _vertices_batch(self.poly_off.astype(np.int64), self.polyA, self.polyb)
+        return self._verts
+
     def interior_points(self):
         """One strictly interior point per polytope (vertex centroid); the device
         IPM starts from it and reports it as x_v of flow-less vertices.  Computed once per graph."""
         if getattr(self, "_cent", None) is not None:
             return self._cent
-        verts, cnt = _vertices_batch(self.poly_off.astype(np.int64), self.polyA, self.polyb)
+        verts, cnt = self.polygon_vertices_batch()
         mask = np.arange(verts.shape[1])[None, :] < cnt[:, None]
         c = (verts * mask[:, :, None]).sum(axis=1) / cnt[:, None]
         self._cent = np.ascontiguousarray(c)

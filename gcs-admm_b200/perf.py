@@ -106,7 +106,7 @@ def cone_table(g):
     """Per region: polygon vertices (counter-clockwise) with the unit outward normal of the cone face spanned by the
     rays through vertex k and k+1, 1/|r_k|^2 (r_k = (V_k, 1)) and the two in-plane sector normals of that face
     (12 doubles per polygon vertex).  Vectorised over regions with the same vertex count."""
-    verts, cnt = _vertices_batch(g.poly_off.astype(np.int64), g.polyA, g.polyb)
+    verts, cnt = g.polygon_vertices_batch() if hasattr(g, "polygon_vertices_batch") else _vertices_batch(g.poly_off.astype(np.int64), g.polyA, g.polyb)
     nV = g.nV
     # duplicates (redundant rows meeting in one vertex) are rare: handle those regions one by one
     per = [None] * nV
