@@ -34,8 +34,8 @@ def solve(As, bs, n, *, device=0, max_it=MAX_IT, round_solution=True, seed=None,
     ~30x cheaper iterations, not the reference's trajectory — compare at convergence).
 
     Returns a dict: cost (pre-rounding, what the reference pickles), final_cost, x_v_sol, y_v_sol,
-    z_v_sol, y_e_sol, x_v_rounded, y_v_rounded, path, iterations, converged, rho_seq, pri_res_seq,
-    dual_res_seq, solve_time, V, E.
+    z_v_sol, y_e_sol (also under the short names x_v, y_v, z_v, y_e), x_v_rounded, y_v_rounded, path, iterations,
+    converged, diverged, rho_seq, pri_res_seq, dual_res_seq, solve_time, status, mode, V, E.
     """
     if int(n) != 2:
         raise ValueError("gcs-admm_b200 implements the 2-D case (n = 2), like all reference data")
@@ -70,7 +70,9 @@ def solve(As, bs, n, *, device=0, max_it=MAX_IT, round_solution=True, seed=None,
     res = dict(cost=cost, x_v_sol=x_v_sol, y_v_sol=y_v_sol, z_v_sol=z_v_sol, y_e_sol=y_e_sol,
                iterations=int(st["iterations"]), converged=bool(st["converged"]), diverged=bool(st["diverged"]),
                rho_seq=out["rho_seq"], pri_res_seq=out["pri_res_seq"], dual_res_seq=out["dual_res_seq"],
-               solve_time=solve_time, status=st, V=V, E=E, final_cost=None, x_v_rounded=None, y_v_rounded=None, path=None)
+               solve_time=solve_time, status=st, V=V, E=E, final_cost=None, x_v_rounded=None, y_v_rounded=None, path=None,
+               mode=mode)
+    res.update(x_v=x_v_sol, y_v=y_v_sol, z_v=z_v_sol, y_e=y_e_sol)      # short names of SURVEY.md section 8b (same objects)
     if round_solution:
         fc, xr, yr, path = rounding(y_e_sol, V, E, I_v_out, As, bs, n, rng=seed, return_path=True)   # :759
         res.update(final_cost=fc, x_v_rounded=xr, y_v_rounded=yr, path=path)
