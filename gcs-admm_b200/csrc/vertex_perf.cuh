@@ -262,9 +262,18 @@ GCS_DEV int gcs_vertex_update_perf(const GcsGraphView &G, const GcsStateView &St
     // start: v with  N v + up  closest to the stored pair copies is not needed — the v-step is an exact solve of a
     // quadratic, so any starting v gives the same result; start from 0
     GCS_LANE_LOOP(q, n) vv[q] = 0.0;
-    GCS_SYNC();
-    gcs_forward(vv, u, d, jstar, prim, term, true, lane);
-    gcs_pair_values(u, pv, d, term, L.npair, lane);
+    if (!term) {
+        // generic vertex: u(0) = up = 0, so the pair values are the constants  (a_i, y) = 0,  (x_i - a_i, 1 - y) = (0, 0, 1)
+        GCS_LANE_LOOP(q, nu) u[q] = 0.0;
+        GCS_LANE_LOOP(q, np3) pv[q] = 0.0;
+        GCS_SYNC();
+        GCS_LANE_LOOP(q, 2 * (d + 1)) pv[3 * gcs_slot(q >> 1, q & 1, 1) + 2] = 1.0;
+        GCS_SYNC();
+    } else {
+        GCS_SYNC();
+        gcs_forward(vv, u, d, jstar, prim, term, true, lane);
+        gcs_pair_values(u, pv, d, term, L.npair, lane);
+    }
     for (int it = 0; it < T.inner_iters; ++it) {
         // G_u = rho S'(S u - T) + eps e_y + sigma M'(pv - c + lam)
         GCS_LANE_LOOP(q, np3) w[q] = pv[q] - cc[q] + lam[q];
