@@ -53,11 +53,18 @@ def main(argv=None):
     g = pack_graph(As, bs, V, E)
     res = solve(As, bs, n, device=args.device, seed=args.seed, graph=(V, E, I_v_in, I_v_out, g))
     it = res["iterations"]
+    # progress lines of the reference loop (:716-718): every 100 iterations, at MAX_IT and at the stop iteration — replayed
+    # from the residual history the device kept; a diverged pass breaks before its line is printed (:662-664)
+    last_printed = it - 1 if res["diverged"] else it
+    for k in range(1, last_printed + 1):
+        if k % 100 == 0 or k == MAX_IT or (k == it and res["converged"]):
+            print(f"it = {k}/{MAX_IT}, pri_res_seq[-1]={res['pri_res_seq'][k]}, dual_res_seq[-1]={res['dual_res_seq'][k]}")
     if res["diverged"]:
         print("BREAKING FOR Divergence")
-    print(f"it = {it}/{MAX_IT}, pri_res_seq[-1]={res['pri_res_seq'][-1]}, dual_res_seq[-1]={res['dual_res_seq'][-1]}")
     if res["converged"]:
         print("BREAKING FOR OPT")
+    elif not res["diverged"]:
+        it += 1          # the reference leaves `while it <= MAX_IT` with it = MAX_IT + 1 and pickles that (:733, :775)
     print(f"x_v: {res['x_v_sol']}")
     print(f"y_v: {res['y_v_sol']}")
     print(f"Total solve time: {res['solve_time']} s.")

@@ -8,8 +8,15 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "gcsadmm.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "vertex_ipm.cuh"), os.path.join(HERE, "csrc", "vertex_update.cuh"),
-        os.path.join(os.path.dirname(HERE), "include", "gcsadmm.h")]
+
+
+def deps():
+    """Every source the library is built from: a change to any of them triggers a rebuild in ``lib.load()``."""
+    import glob
+    return sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")) + glob.glob(os.path.join(HERE, "csrc", "*.cuh"))
+                  + glob.glob(os.path.join(os.path.dirname(HERE), "include", "*.h")))
+
+
 OUT = os.path.join(HERE, "libgcsadmm.so")
 
 
@@ -21,7 +28,7 @@ def nvcc_path():
 
 
 def build(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps()):
         return OUT
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-Xptxas", "-v", "-shared", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-o", OUT, SRC]

@@ -33,27 +33,35 @@ extern "C" int gcsemu_vertex_update_all(int nV, int nE, const int *poly_off, con
 extern "C" int gcsemu_scratch_doubles(int dcap, int mcap) { return gcs_scratch_layout(dcap, mcap).total; }
 extern "C" int gcsemu_ws_stride(int dcap, int mcap) { return gcs_ws_stride(gcs_scratch_layout(dcap, mcap)); }
 
-// perf-mode K1 (vertex_perf.cuh), emulated
+// perf-mode K1 (vertex_perf.cuh), emulated: one host thread plays each thread block (tile) in turn
 extern "C" int gcsemu_vertex_update_perf_all(int nV, int nE, const int *poly_off, const double *polyA, const double *polyb,
                                              const int *he_off, const int *he_edge, const unsigned char *he_flags,
                                              const unsigned char *vtype, const double *cent, double *xc, const double *mu,
                                              const double *z, double *x_v, double *z_v, double *y_v, double rho, double mu_scale,
-                                             int dcap, const int *vclass, const int *class_koff, const double *kinv,
-                                             const int *cone_off, const double *cone, double *state, int inner_iters,
-                                             double alpha, double kappa) {
+                                             const int *vclass, const double *cls_tab, const int *cone_off, const double *cone,
+                                             const int *blk_off, const int *blk_he, const int *blk_info, const int *tile_voff, int ntiles,
+                                             int cap_blocks, int cap_verts, int cap_cone, double *tstate, double *tn,
+                                             int inner_iters, double alpha, double kappa) {
     GcsGraphView G = {nV, nE, poly_off, polyA, polyb, he_off, he_edge, he_flags, vtype, cent};
     GcsStateView St = {xc, mu, z, x_v, z_v, y_v, 0, 0.0, 0.0};
-    int kcap = 3;
-    for (int v = 0; v < nV; ++v) if (cone_off[v + 1] - cone_off[v] > kcap) kcap = cone_off[v + 1] - cone_off[v];
-    GcsPerfLayout L = gcs_perf_layout(dcap, kcap);
-    GcsPerfTables T = {vclass, class_koff, kinv, cone_off, cone, state, gcs_perf_state_stride(dcap), inner_iters, alpha, kappa};
-    double *S = (double *)malloc(sizeof(double) * L.total);
-    int n = 0;
-    for (int v = 0; v < nV; ++v) {
-        memset(S, getenv("GCSEMU_POISON") ? 0xFF : 0, sizeof(double) * L.total);   // 0xFF: NaN doubles / -1 ints expose uninitialised reads
-        n += gcs_vertex_update_perf(G, St, T, v, rho, mu_scale, L, S, 0);
+    GcsPerfLayout L = gcs_perf_layout(cap_blocks, cap_verts, cap_cone);
+    GcsPerfTables T = {vclass, cls_tab, cone_off, cone, blk_off, blk_he, blk_info, tile_voff, ntiles, tstate, tn, inner_iters, alpha, kappa};
+    Ctrl ctrl;
+    memset(&ctrl, 0, sizeof ctrl);
+    ctrl.rho = rho; ctrl.mu_scale = mu_scale;
+    const int poison = getenv("GCSEMU_POISON") ? 0xFF : 0;     // 0xFF: NaN doubles / -1 ints expose uninitialised reads
+#pragma omp parallel
+    {
+        double *S = (double *)malloc(sizeof(double) * L.total);
+#pragma omp for schedule(dynamic, 16)
+        for (int t = 0; t < ntiles; ++t) {
+            memset(S, poison, sizeof(double) * L.total);
+            Ctrl local = ctrl;
+            gcs_perf_tile(G, St, T, L, S, t, &local, 0, 0);
+        }
+        free(S);
     }
-    free(S);
-    return n;
+    for (int v = 0; v < nV; ++v)      // what perf_init_dead_kernel writes once on the device
+        if (vtype[v] == GCS_VT_DEAD) { for (int k = 0; k < 4; ++k) { z_v[4 * v + k] = 0.0; x_v[4 * v + k] = cent[2 * v + (k & 1)]; } y_v[v] = 0.0; }
+    return ntiles;
 }
-extern "C" int gcsemu_perf_state_stride(int dcap) { return gcs_perf_state_stride(dcap); }

@@ -1,0 +1,12 @@
+// Control block of one problem (device memory; one per problem in batched mode).  Written by the control step
+// (reference admm_solver_v3.py:697-713), read by every kernel.
+#pragma once
+#define NSUMS 8   // r2, dz2, x2, z2, mu2 (pre-scale), nonfinite, spare, spare
+
+struct Ctrl {
+    double rho, mu_scale;
+    double pri, dual, eps_pri, eps_dual;
+    double sums[NSUMS];
+    unsigned long long inner_iters, skipped;
+    int it, stop, opt, diverged, inner_fail, ignore_stop;
+};

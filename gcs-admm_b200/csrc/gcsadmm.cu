@@ -1,12 +1,15 @@
 // libgcsadmm.so — kernels and C-ABI (include/gcsadmm.h).  sm_100a only; no CPU path.
 //
-//   K1  vertex_kernel   one warp per vertex, interior-point prox solve in shared memory   (vertex_update.cuh)
-//   K2-4 edge_kernel    one thread per edge: z-update (average of the two copies), dual update of both
-//                       half-edges, and the five squared norms, fused; block partials, no atomics
-//   K5  control_kernel  one block: deterministic reduction of the partials, residuals, rho adaptation,
-//                       stop rule, history (reference admm_solver_v3.py:697-713)
+//   K1  vertex_kernel        one warp per vertex, interior-point prox solve in shared memory   (vertex_update.cuh)
+//       vertex_perf_kernel   perf mode: one thread block per tile of vertices, closed-form splitting iterations (vertex_perf.cuh)
+//   K2-5 edge_kernel         one thread per (edge, consensus scalar): z-update (average of the two copies), dual update of
+//                            both half-edges, the five squared norms; block partials (no atomics on the data), and the
+//                            LAST block to finish reduces them in a fixed order and applies the control step: residuals,
+//                            rho adaptation, stop rule, history (reference admm_solver_v3.py:697-713)
+//   control_kernel           the same control step as a separate launch (multi-GPU: the sums are all-reduced in between)
 // Every kernel returns immediately once the stop flag is set, so the host can enqueue iterations in
-// chunks and poll the control block once per chunk while keeping the reference's exact stop iteration.
+// chunks (one CUDA graph per chunk) and poll the control block once per chunk while keeping the reference's exact
+// stop iteration.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -15,13 +18,13 @@
 #include <new>
 
 #include "../../include/gcsadmm.h"
+#include "gcs_ctrl.h"
 #include "vertex_update.cuh"
 #include "vertex_perf.cuh"
 
 #define GCS_VERSION "gcsadmm 0.1.0 (sm_100a)"
-#define K1_MAX_WARPS 12  // __launch_bounds__(320): <= 204 registers/thread, 10 warps fill the register file of one SM
+#define K1_MAX_WARPS 12  // __launch_bounds__(384): <= 168 registers/thread, 12 warps (18.8 KB of shared memory each) fill one SM
 #define EDGE_THREADS 256
-#define NSUMS 8   // r2, dz2, x2, z2, mu2(pre-scale), nonfinite, spare, spare
 
 static thread_local char g_err[512] = "";
 static int set_err(int code, const char *fmt, const char *a = "", const char *b = "") {
@@ -33,14 +36,6 @@ static int set_err(int code, const char *fmt, const char *a = "", const char *b 
         cudaError_t e_ = (call);                                                                   \
         if (e_ != cudaSuccess) return set_err(GCS_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
-
-struct Ctrl {
-    double rho, mu_scale;
-    double pri, dual, eps_pri, eps_dual;
-    double sums[NSUMS];
-    unsigned long long inner_iters, skipped;
-    int it, stop, opt, diverged, inner_fail, ignore_stop;
-};
 
 struct GcsHandle {
     int device;
@@ -58,6 +53,7 @@ struct GcsHandle {
     unsigned char *he_flags, *vtype, *edge_counted;
     int *vprob, *prob_eoff; long long *prob_nx, *prob_nmu;   // batched mode (nP > 1)
     int *he_prob_host;  // host: problem of each half-edge (batched mode)
+    unsigned int *ticket;   // edge_kernel: blocks finished in the current launch (the last one reduces + controls)
     double *xc, *mu, *z, *x_v, *z_v, *y_v;
     double *ws;         // [nV][gcs_ws_stride] interior-point warm-start records (null when warm_theta == 0)
     double *partials;   // [edge_blocks][NSUMS]
@@ -68,10 +64,13 @@ struct GcsHandle {
     cudaEvent_t ev[4];
     void *flush_buf; size_t flush_bytes;
     // perf mode (inexact x-update by K closed-form splitting iterations)
-    int perf_on, perf_smem, perf_warps, perf_blocks;
+    int perf_on, perf_smem;
     GcsPerfLayout PL;
     GcsPerfTables PT;
-    int *p_vclass, *p_class_koff, *p_cone_off; double *p_kinv, *p_cone, *p_state;
+    long long perf_nblocks;
+    int *p_vclass, *p_cone_off, *p_blk_off, *p_blk_he, *p_blk_info, *p_tile_voff; double *p_cls_tab, *p_cone, *p_tstate, *p_tn;
+    // one CUDA graph per chunk of `check_every` iterations (own stream only)
+    cudaGraphExec_t graph_exec; int graph_iters;
 };
 
 // ------------------------------------------------------------------------------------------ K1
@@ -94,102 +93,23 @@ vertex_kernel(GcsGraphView G, GcsStateView St, Ctrl *ctrl_all, const int *__rest
 }
 
 // ------------------------------------------------------------------------------------------ K1 (perf mode)
-#ifndef PERF_MAX_WARPS
-#define PERF_MAX_WARPS 16
-#endif
-#ifndef PERF_MIN_BLOCKS
-#define PERF_MIN_BLOCKS 2   // 64 registers/thread, 32 warps per SM: measured 1.51 ms vs 2.05 ms (128 registers, 16 warps) at 100k vertices
-#endif
-__global__ void __launch_bounds__(PERF_MAX_WARPS * 32, PERF_MIN_BLOCKS)
+// one thread block per tile of consecutive vertices (<= 256 (point, flow) pairs); ~25 KB of shared memory per block
+__global__ void __launch_bounds__(GCS_PERF_THREADS, 3)
 vertex_perf_kernel(GcsGraphView G, GcsStateView St, GcsPerfTables T, Ctrl *ctrl_all, const int *__restrict__ vprob, GcsPerfLayout L) {
-    extern __shared__ double smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int v = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (v >= G.nV) return;
-    Ctrl *ctrl = ctrl_all + (vprob ? vprob[v] : 0);
-    if (ctrl->stop && !ctrl->ignore_stop) return;
-    double *S = smem + (size_t)warp * L.total;
-    const int did = gcs_vertex_update_perf(G, St, T, v, ctrl->rho, ctrl->mu_scale, L, S, lane);
-    if (lane == 0 && did) atomicAdd(&ctrl->inner_iters, (unsigned long long)T.inner_iters);
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    if (!vprob && ctrl_all->stop && !ctrl_all->ignore_stop) return;
+    gcs_perf_tile(G, St, T, L, smem, blockIdx.x, ctrl_all, vprob, &bar);
+}
+// x_v / z_v / y_v of vertices no flow can pass are constants: written once when the mode is enabled
+__global__ void perf_init_dead_kernel(GcsGraphView G, GcsStateView St) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= G.nV || G.vtype[v] != GCS_VT_DEAD) return;
+    for (int k = 0; k < 4; ++k) { St.z_v[4 * (size_t)v + k] = 0.0; St.x_v[4 * (size_t)v + k] = G.cent[2 * (size_t)v + (k & 1)]; }
+    St.y_v[v] = 0.0;
 }
 
-// ------------------------------------------------------------------------------------------ K2-K4
-// z_e = 1/2 (xc_tail + xc_head)            reference admm_solver_v3.py:543-562 (live scalars only)
-// mu_h <- mu_scale * mu_h + (z_e - xc_h)    :590-594  (mu_scale carries the rho-adaptation rescale :705/:708)
-// partial sums of |z - xc|^2, |dz|^2, |xc|^2, |z|^2, |mu|^2     :597-614
-__global__ void __launch_bounds__(EDGE_THREADS)
-edge_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *__restrict__ edge_he_head,
-            const unsigned char *__restrict__ edge_counted, const double *__restrict__ xc, double *__restrict__ mu,
-            double *__restrict__ z, Ctrl *ctrl, double *__restrict__ partials) {
-    if (ctrl->stop && !ctrl->ignore_stop) return;
-    const double ms = ctrl->mu_scale;
-    double r2 = 0, dz2 = 0, x2 = 0, z2 = 0, m2 = 0, bad = 0;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
-        const int ht = edge_he_tail[e], hh = edge_he_head[e];
-        const double w = edge_counted ? (double)edge_counted[e] : 1.0;
-        double xt[5], xh[5], zn[5];
-#pragma unroll
-        for (int c = 0; c < 5; ++c) { xt[c] = xc[5 * (size_t)ht + c]; xh[c] = xc[5 * (size_t)hh + c]; }
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            const double zo = z[5 * (size_t)e + c];
-            zn[c] = 0.5 * (xt[c] + xh[c]);
-            const double dd = zn[c] - zo;
-            dz2 += w * dd * dd; z2 += w * zn[c] * zn[c];
-            z[5 * (size_t)e + c] = zn[c];
-        }
-        if (ht < nHown) {
-#pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                const double r = zn[c] - xt[c], mn = ms * mu[5 * (size_t)ht + c] + r;
-                mu[5 * (size_t)ht + c] = mn; r2 += r * r; x2 += xt[c] * xt[c]; m2 += mn * mn;
-            }
-        }
-        if (hh < nHown) {
-#pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                const double r = zn[c] - xh[c], mn = ms * mu[5 * (size_t)hh + c] + r;
-                mu[5 * (size_t)hh + c] = mn; r2 += r * r; x2 += xh[c] * xh[c]; m2 += mn * mn;
-            }
-        }
-    }
-    if (!isfinite(r2) || !isfinite(dz2) || !isfinite(x2) || !isfinite(z2)) bad = 1.0;
-    // block reduction (fixed order: shuffles, then warp partials in shared memory)
-    __shared__ double sh[EDGE_THREADS / 32][6];
-    double vals[6] = {r2, dz2, x2, z2, m2, bad};
-#pragma unroll
-    for (int q = 0; q < 6; ++q)
-#pragma unroll
-        for (int o = 16; o; o >>= 1) vals[q] += __shfl_xor_sync(0xffffffffu, vals[q], o);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0)
-        for (int q = 0; q < 6; ++q) sh[warp][q] = vals[q];
-    __syncthreads();
-    if (threadIdx.x < 6) {
-        double s = 0.0;
-        for (int w2 = 0; w2 < EDGE_THREADS / 32; ++w2) s += sh[w2][threadIdx.x];
-        partials[(size_t)blockIdx.x * NSUMS + threadIdx.x] = s;
-    }
-}
-
-// sums the block partials in a fixed order -> ctrl->sums  (all-reduced across ranks by the multi-GPU driver)
-__global__ void reduce_kernel(const double *__restrict__ partials, int nblocks, Ctrl *ctrl) {
-    if (ctrl->stop && !ctrl->ignore_stop) return;
-    __shared__ double sh[256][6];
-    double acc[6] = {0, 0, 0, 0, 0, 0};
-    for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
-        for (int q = 0; q < 6; ++q) acc[q] += partials[(size_t)b * NSUMS + q];
-    for (int q = 0; q < 6; ++q) sh[threadIdx.x][q] = acc[q];
-    __syncthreads();
-    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s)
-            for (int q = 0; q < 6; ++q) sh[threadIdx.x][q] += sh[threadIdx.x + s][q];
-        __syncthreads();
-    }
-    if (threadIdx.x < 6) ctrl->sums[threadIdx.x] = sh[0][threadIdx.x];
-}
-
-// ------------------------------------------------------------------------------------------ K5
+// ------------------------------------------------------------------------------------------ K5 (device function)
 // reference admm_solver_v3.py:697-713 and :733, on the reduced sums
 __device__ void control_apply(Ctrl *ctrl, const GcsParams &p, long long n_x, long long n_mu, double *hist, int hist_cap) {
     const int it = ctrl->it + 1;
@@ -209,6 +129,89 @@ __device__ void control_apply(Ctrl *ctrl, const GcsParams &p, long long n_x, lon
     if (s[5] != 0.0 || !isfinite(pri) || !isfinite(dual)) { ctrl->diverged = 1; ctrl->stop = 1; return; }  // :662-664
     const bool opt = p.abs_stop ? (fmax(pri, dual) < p.abs_tol) : (pri < eps_pri && dual < eps_dual);        // :712
     if (opt) { ctrl->opt = 1; ctrl->stop = 1; }
+}
+
+// ------------------------------------------------------------------------------------------ K2-K5
+// z_e = 1/2 (xc_tail + xc_head)            reference admm_solver_v3.py:543-562 (live scalars only)
+// mu_h <- mu_scale * mu_h + (z_e - xc_h)    :590-594  (mu_scale carries the rho-adaptation rescale :705/:708)
+// partial sums of |z - xc|^2, |dz|^2, |xc|^2, |z|^2, |mu|^2     :597-614
+// One thread per (edge, consensus scalar): z and the tail-side records are walked sequentially (edges are sorted by
+// (tail, head) and a vertex's outgoing half-edges follow that order), the head-side record is a 40-byte gather.
+// oalpha != 1 (perf mode only) over-relaxes the consensus step: xc is replaced by oalpha xc + (1 - oalpha) z_old in the
+// z- and mu-updates (Boyd et al. 3.4.3); the primal residual keeps the true xc.
+// fuse != 0: the last block to finish reduces the block partials in a fixed order and applies the control step.
+__global__ void __launch_bounds__(EDGE_THREADS)
+edge_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *__restrict__ edge_he_head,
+            const unsigned char *__restrict__ edge_counted, const double *__restrict__ xc, double *__restrict__ mu,
+            double *__restrict__ z, Ctrl *ctrl, double *__restrict__ partials, unsigned int *ticket, int fuse,
+            GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap) {
+    if (ctrl->stop && !ctrl->ignore_stop) return;
+    const double ms = ctrl->mu_scale, oa = p.outer_alpha, ob = 1.0 - p.outer_alpha;
+    double r2 = 0, dz2 = 0, x2 = 0, z2 = 0, m2 = 0, bad = 0;
+    const long long n = 5ll * nE;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(i / 5), c = (int)(i - 5ll * e);
+        const int ht = edge_he_tail[e], hh = edge_he_head[e];
+        const double xt = xc[5 * (size_t)ht + c], xh = xc[5 * (size_t)hh + c], zo = z[i];
+        const double w = edge_counted ? (double)edge_counted[e] : 1.0;
+        double at = xt, ah = xh;
+        if (oa != 1.0) { at = oa * xt + ob * zo; ah = oa * xh + ob * zo; }
+        const double zn = 0.5 * (at + ah), dd = zn - zo;
+        z[i] = zn;
+        dz2 += w * dd * dd; z2 += w * zn * zn;
+        if (ht < nHown) {
+            const double r = zn - xt, mn = ms * mu[5 * (size_t)ht + c] + (zn - at);
+            mu[5 * (size_t)ht + c] = mn; r2 += r * r; x2 += xt * xt; m2 += mn * mn;
+        }
+        if (hh < nHown) {
+            const double r = zn - xh, mn = ms * mu[5 * (size_t)hh + c] + (zn - ah);
+            mu[5 * (size_t)hh + c] = mn; r2 += r * r; x2 += xh * xh; m2 += mn * mn;
+        }
+    }
+    if (!isfinite(r2) || !isfinite(dz2) || !isfinite(x2) || !isfinite(z2)) bad = 1.0;
+    // block reduction (fixed order: shuffles, then warp partials in shared memory)
+    __shared__ double sh[EDGE_THREADS][6];
+    __shared__ int is_last;
+    double vals[6] = {r2, dz2, x2, z2, m2, bad};
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) vals[q] += __shfl_xor_sync(0xffffffffu, vals[q], o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0)
+        for (int q = 0; q < 6; ++q) sh[warp][q] = vals[q];
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double s = 0.0;
+        for (int w2 = 0; w2 < EDGE_THREADS / 32; ++w2) s += sh[w2][threadIdx.x];
+        partials[(size_t)blockIdx.x * NSUMS + threadIdx.x] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // last block: every block's partials are visible; sum them in an order that does not depend on which block is last
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+        for (int q = 0; q < 6; ++q) acc[q] += __ldcg(partials + (size_t)b * NSUMS + q);
+    for (int q = 0; q < 6; ++q) sh[threadIdx.x][q] = acc[q];
+    __syncthreads();
+    for (int st = EDGE_THREADS / 2; st > 0; st >>= 1) {
+        if (threadIdx.x < st)
+            for (int q = 0; q < 6; ++q) sh[threadIdx.x][q] += sh[threadIdx.x + st][q];
+        __syncthreads();
+    }
+    if (threadIdx.x < 6) ctrl->sums[threadIdx.x] = sh[0][threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *ticket = 0u;
+        if (fuse) control_apply(ctrl, p, n_x, n_mu, hist, hist_cap);
+    }
 }
 
 __global__ void control_kernel(Ctrl *ctrl, GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap) {
@@ -291,6 +294,7 @@ extern "C" void gcsadmm_default_params(GcsParams *p) {
     p->rho0 = 1.0; p->tau_incr = 2.0; p->tau_decr = 2.0; p->nu = 10.0; p->frac = 0.1;
     p->eps_abs = 1e-4; p->eps_rel = 1e-3; p->max_it = 1000; p->inner_tol = 1e-8; p->inner_max_iter = 60;
     p->check_every = 8; p->abs_stop = 0; p->abs_tol = 1e-4; p->warm_theta = 1e-3; p->zero_tol = 1e-12;
+    p->outer_alpha = 1.0; p->use_graph = 1;
 }
 extern "C" int gcsadmm_scratch_bytes(int max_live_degree, int max_rows) {
     return (int)(gcs_scratch_layout(max_live_degree, max_rows).total * sizeof(double));
@@ -300,7 +304,7 @@ template <typename T>
 static int upload(T **dst, const T *src, size_t n) {
     if (n == 0) n = 1, src = nullptr;
     cudaError_t e = cudaMalloc((void **)dst, n * sizeof(T));
-    if (e != cudaSuccess) return set_err(GCS_E_NOMEM, "cudaMalloc(%s bytes): %s", "", cudaGetErrorString(e));
+    if (e != cudaSuccess) { char nb[32]; snprintf(nb, sizeof nb, "%zu", n * sizeof(T)); return set_err(GCS_E_NOMEM, "cudaMalloc(%s bytes): %s", nb, cudaGetErrorString(e)); }
     if (src) { e = cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice); if (e != cudaSuccess) return set_err(GCS_E_CUDA, "cudaMemcpy H2D: %s", cudaGetErrorString(e)); }
     else cudaMemset(*dst, 0, n * sizeof(T));
     return 0;
@@ -320,6 +324,18 @@ static int reset_ctrl(GcsHandle *h) {
     return 0;
 }
 
+static void free_perf(GcsHandle *h) {
+    void *pp[] = {h->p_vclass, h->p_cone_off, h->p_blk_off, h->p_blk_he, h->p_blk_info, h->p_tile_voff, h->p_cls_tab, h->p_cone, h->p_tstate, h->p_tn};
+    for (void *q : pp) if (q) cudaFree(q);
+    h->p_vclass = h->p_cone_off = h->p_blk_off = h->p_blk_he = h->p_blk_info = h->p_tile_voff = nullptr;
+    h->p_cls_tab = h->p_cone = h->p_tstate = h->p_tn = nullptr;
+    h->perf_on = 0;
+}
+static void drop_graph(GcsHandle *h) {
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    h->graph_iters = 0;
+}
+
 extern "C" int gcsadmm_destroy(GcsHandle *h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
@@ -330,33 +346,36 @@ extern "C" int gcsadmm_destroy(GcsHandle *h) {
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
     free(h->he_prob_host);
     if (h->flush_buf) cudaFree(h->flush_buf);
-    { void *pp[] = {h->p_vclass, h->p_class_koff, h->p_cone_off, h->p_kinv, h->p_cone, h->p_state}; for (void *q : pp) if (q) cudaFree(q); }
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->ticket) cudaFree(h->ticket);
+    free_perf(h);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;
 }
 
-extern "C" int gcsadmm_create(const GcsGraph *g, const GcsParams *p, int device, GcsHandle **out) {
-    if (!g || !out) return set_err(GCS_E_INVALID, "null argument%s", "");
-    *out = nullptr;
-    if (g->n != 2) return set_err(GCS_E_INVALID, "the CUDA path is specialised to n = 2 (2-D GCS)%s", "");
-    if (g->nV <= 0 || g->nE < 0) return set_err(GCS_E_INVALID, "empty graph%s", "");
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return set_err(GCS_E_CUDA, "no CUDA device: libgcsadmm has no CPU path%s", ""); }
-    if (device < 0 || device >= ndev) return set_err(GCS_E_INVALID, "bad device index%s", "");
-    CK(cudaSetDevice(device));
-    GcsHandle *h = new (std::nothrow) GcsHandle();
-    if (!h) return set_err(GCS_E_NOMEM, "out of host memory%s", "");
-    memset(h, 0, sizeof *h);
-    h->device = device;
-    if (p) h->p = *p; else gcsadmm_default_params(&h->p);
-    if (h->p.check_every < 1) h->p.check_every = 1;
-    h->nV = g->nV; h->nE = g->nE; h->nHown = g->nH_own; h->nHghost = g->nH_ghost;
-    h->nP = g->nP > 1 ? g->nP : 1;
-    if (h->nP > 1 && (g->nH_ghost > 0 || !g->prob_voff || !g->prob_eoff)) { delete h; return set_err(GCS_E_INVALID, "batched problems need prob_voff / prob_eoff and cannot be vertex-partitioned%s", ""); }
-    h->n_x = g->n_x_global ? g->n_x_global : 9LL * g->nV + 18LL * g->nE;
-    h->n_mu = g->n_mu_global ? g->n_mu_global : 10LL * g->nE;
+// index ranges of the caller's arrays (a bad index would otherwise be an out-of-bounds access on the device)
+static int validate_graph(const GcsGraph *g) {
+    if (!g->poly_off || !g->polyA || !g->polyb || !g->he_off || !g->vtype || !g->cent) return set_err(GCS_E_INVALID, "null graph array%s", "");
+    if (g->nH_own < 0 || g->nH_ghost < 0 || g->he_off[0] != 0 || g->he_off[g->nV] != g->nH_own) return set_err(GCS_E_INVALID, "he_off does not span nH_own%s", "");
+    if (g->nH_own && (!g->he_edge || !g->he_flags)) return set_err(GCS_E_INVALID, "null half-edge array%s", "");
+    if (g->nE && (!g->edge_he_tail || !g->edge_he_head)) return set_err(GCS_E_INVALID, "null edge array%s", "");
+    if (g->poly_off[0] != 0) return set_err(GCS_E_INVALID, "poly_off[0] != 0%s", "");
+    for (int v = 0; v < g->nV; ++v) {
+        if (g->he_off[v + 1] < g->he_off[v] || g->poly_off[v + 1] < g->poly_off[v]) return set_err(GCS_E_INVALID, "offsets not monotone%s", "");
+        if (g->vtype[v] > 3) return set_err(GCS_E_INVALID, "bad vertex type%s", "");
+    }
+    for (int hh = 0; hh < g->nH_own; ++hh) if (g->he_edge[hh] < 0 || g->he_edge[hh] >= g->nE) return set_err(GCS_E_INVALID, "he_edge out of range%s", "");
+    const int nHall = g->nH_own + g->nH_ghost;
+    for (int e = 0; e < g->nE; ++e)
+        if (g->edge_he_tail[e] < 0 || g->edge_he_tail[e] >= nHall || g->edge_he_head[e] < 0 || g->edge_he_head[e] >= nHall)
+            return set_err(GCS_E_INVALID, "edge_he_tail / edge_he_head out of range%s", "");
+    return 0;
+}
+
+// everything of gcsadmm_create that can fail after the handle exists; the caller destroys the handle on failure
+static int create_impl(GcsHandle *h, const GcsGraph *g) {
     // capacity of a vertex program: live degree and polytope rows
     int dcap = 1, mcap = 1;
     for (int v = 0; v < g->nV; ++v) {
@@ -365,20 +384,17 @@ extern "C" int gcsadmm_create(const GcsGraph *g, const GcsParams *p, int device,
         if (d > dcap) dcap = d;
         int m = g->poly_off[v + 1] - g->poly_off[v];
         if (m > mcap) mcap = m;
-        if (g->vtype[v] == GCS_VT_GENERIC && d < 2) { delete h; return set_err(GCS_E_INVALID, "inconsistent presolve flags (generic vertex with < 2 live half-edges)%s", ""); }
+        if (g->vtype[v] == GCS_VT_GENERIC && d < 2) return set_err(GCS_E_INVALID, "inconsistent presolve flags (generic vertex with < 2 live half-edges)%s", "");
     }
     h->dcap = dcap; h->mcap = mcap;
     h->L = gcs_scratch_layout(dcap, mcap);
     cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
+    CK(cudaGetDeviceProperties(&prop, h->device));
     {   // as many warps per block as shared memory allows (one block per SM when the programs are large)
         const size_t per_warp = (size_t)h->L.total * sizeof(double);
         const size_t budget = prop.sharedMemPerBlockOptin;
         int w = (int)(budget / per_warp);
-        if (w < 1) {
-            delete h;
-            return set_err(GCS_E_INVALID, "vertex program too large for shared memory (max live degree / polytope rows too high)%s", "");
-        }
+        if (w < 1) return set_err(GCS_E_INVALID, "vertex program too large for shared memory (max live degree / polytope rows too high)%s", "");
         if (w > K1_MAX_WARPS) w = K1_MAX_WARPS;
         h->k1_warps = w;
         h->k1_smem = (int)(w * per_warp);
@@ -386,9 +402,11 @@ extern "C" int gcsadmm_create(const GcsGraph *g, const GcsParams *p, int device,
     CK(cudaFuncSetAttribute(vertex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k1_smem));
     CK(cudaFuncSetAttribute(vertex_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     h->k1_blocks = (g->nV + h->k1_warps - 1) / h->k1_warps;
-    int eb = (g->nE + EDGE_THREADS - 1) / EDGE_THREADS;
-    int cap = prop.multiProcessorCount * 8;
-    h->edge_blocks = eb < 1 ? 1 : (eb > cap ? cap : eb);
+    {   // edge kernel: 5 threads per edge, a whole number of waves of resident blocks (8 blocks of 256 threads per SM)
+        const long long need = (5ll * g->nE + EDGE_THREADS - 1) / EDGE_THREADS;
+        const long long cap = (long long)prop.multiProcessorCount * 8;
+        h->edge_blocks = (int)(need < 1 ? 1 : (need > cap ? cap : need));
+    }
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
     const size_t M = (size_t)g->poly_off[g->nV], Hall = (size_t)g->nH_own + g->nH_ghost;
@@ -403,16 +421,18 @@ extern "C" int gcsadmm_create(const GcsGraph *g, const GcsParams *p, int device,
     UP(x_v, (const double *)nullptr, 4 * (size_t)g->nV); UP(z_v, (const double *)nullptr, 4 * (size_t)g->nV); UP(y_v, (const double *)nullptr, g->nV);
     if (h->p.warm_theta > 0.0) UP(ws, (const double *)nullptr, (size_t)g->nV * gcs_ws_stride(h->L));
     UP(partials, (const double *)nullptr, (size_t)h->edge_blocks * NSUMS);
+    UP(ticket, (const unsigned int *)nullptr, 1);
     h->hist_cap = h->p.max_it + 2;
     UP(hist, (const double *)nullptr, 3 * (size_t)h->hist_cap * h->nP);
 #undef UP
-    if (rc) { gcsadmm_destroy(h); return rc; }
+    if (rc) return rc;
     CK(cudaMalloc((void **)&h->ctrl, sizeof(Ctrl) * h->nP));
     CK(cudaMallocHost((void **)&h->ctrl_host, sizeof(Ctrl) * h->nP));
     if (h->nP > 1) {   // per-problem maps: vertex -> problem, edge ranges, len(x_global) / len(mu_global) of each problem
         int *vp = (int *)malloc(sizeof(int) * g->nV);
         long long *nx = (long long *)malloc(sizeof(long long) * h->nP), *nm = (long long *)malloc(sizeof(long long) * h->nP);
         h->he_prob_host = (int *)malloc(sizeof(int) * (size_t)(g->nH_own > 0 ? g->nH_own : 1));
+        if (!vp || !nx || !nm || !h->he_prob_host) { free(vp); free(nx); free(nm); return set_err(GCS_E_NOMEM, "out of host memory%s", ""); }
         for (int q = 0; q < h->nP; ++q) {
             for (int v = g->prob_voff[q]; v < g->prob_voff[q + 1]; ++v) {
                 vp[v] = q;
@@ -426,11 +446,38 @@ extern "C" int gcsadmm_create(const GcsGraph *g, const GcsParams *p, int device,
         if (!rc) rc = upload(&h->prob_nx, nx, (size_t)h->nP);
         if (!rc) rc = upload(&h->prob_nmu, nm, (size_t)h->nP);
         free(vp); free(nx); free(nm);
-        if (rc) { gcsadmm_destroy(h); return rc; }
+        if (rc) return rc;
     }
     for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&h->ev[i]));
-    rc = reset_ctrl(h);
-    if (rc) { gcsadmm_destroy(h); return rc; }
+    return reset_ctrl(h);
+}
+
+extern "C" int gcsadmm_create(const GcsGraph *g, const GcsParams *p, int device, GcsHandle **out) {
+    if (!g || !out) return set_err(GCS_E_INVALID, "null argument%s", "");
+    *out = nullptr;
+    if (g->n != 2) return set_err(GCS_E_INVALID, "the CUDA path is specialised to n = 2 (2-D GCS)%s", "");
+    if (g->nV <= 0 || g->nE < 0) return set_err(GCS_E_INVALID, "empty graph%s", "");
+    int rc = validate_graph(g);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return set_err(GCS_E_CUDA, "no CUDA device: libgcsadmm has no CPU path%s", ""); }
+    if (device < 0 || device >= ndev) return set_err(GCS_E_INVALID, "bad device index%s", "");
+    const int nP = g->nP > 1 ? g->nP : 1;
+    if (nP > 1 && (g->nH_ghost > 0 || !g->prob_voff || !g->prob_eoff)) return set_err(GCS_E_INVALID, "batched problems need prob_voff / prob_eoff and cannot be vertex-partitioned%s", "");
+    CK(cudaSetDevice(device));
+    GcsHandle *h = new (std::nothrow) GcsHandle();
+    if (!h) return set_err(GCS_E_NOMEM, "out of host memory%s", "");
+    memset(h, 0, sizeof *h);
+    h->device = device;
+    if (p) h->p = *p; else gcsadmm_default_params(&h->p);
+    if (h->p.check_every < 1) h->p.check_every = 1;
+    if (!(h->p.outer_alpha > 0.0 && h->p.outer_alpha < 2.0)) h->p.outer_alpha = 1.0;
+    h->nV = g->nV; h->nE = g->nE; h->nHown = g->nH_own; h->nHghost = g->nH_ghost;
+    h->nP = nP;
+    h->n_x = g->n_x_global ? g->n_x_global : 9LL * g->nV + 18LL * g->nE;
+    h->n_mu = g->n_mu_global ? g->n_mu_global : 10LL * g->nE;
+    rc = create_impl(h, g);
+    if (rc) { gcsadmm_destroy(h); return rc; }      // single cleanup path: frees whatever was allocated so far
     *out = h;
     return 0;
 }
@@ -440,6 +487,7 @@ extern "C" int gcsadmm_set_stream(GcsHandle *h, void *s, int external) {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     h->stream = external ? (cudaStream_t)s : h->own_stream;   // a NULL external stream is the legacy default stream
+    drop_graph(h);
     return 0;
 }
 
@@ -455,26 +503,46 @@ static GcsStateView state_view(const GcsHandle *h) {
 }
 static int launch_k1(GcsHandle *h) {
     if (h->perf_on) {
-        vertex_perf_kernel<<<h->perf_blocks, h->perf_warps * 32, h->perf_smem, h->stream>>>(graph_view(h), state_view(h), h->PT, h->ctrl, h->vprob, h->PL);
+        vertex_perf_kernel<<<h->PT.ntiles, GCS_PERF_THREADS, h->perf_smem, h->stream>>>(graph_view(h), state_view(h), h->PT, h->ctrl, h->vprob, h->PL);
         return 0;
     }
     vertex_kernel<<<h->k1_blocks, h->k1_warps * 32, h->k1_smem, h->stream>>>(graph_view(h), state_view(h), h->ctrl, h->vprob, h->L, h->p.inner_tol, h->p.inner_max_iter);
     return 0;
 }
-static int launch_edge(GcsHandle *h) {
+// K2-K5.  fuse: the control step runs inside the edge kernel's last block (single GPU); otherwise only sums[] is produced
+static int launch_edge(GcsHandle *h, int fuse) {
     if (h->nP > 1) {   // edges, sums and control of every problem in one launch
         const int blocks = h->nP < 148 * 16 ? h->nP : 148 * 16;
         batched_edge_kernel<<<blocks, BATCH_THREADS, 0, h->stream>>>(h->nP, h->prob_eoff, h->nHown, h->edge_he_tail, h->edge_he_head, h->xc, h->mu, h->z,
                                                                      h->ctrl, h->p, h->prob_nx, h->prob_nmu, h->hist, h->hist_cap);
         return 0;
     }
-    edge_kernel<<<h->edge_blocks, EDGE_THREADS, 0, h->stream>>>(h->nE, h->nHown, h->edge_he_tail, h->edge_he_head, h->edge_counted, h->xc, h->mu, h->z, h->ctrl, h->partials);
-    reduce_kernel<<<1, 256, 0, h->stream>>>(h->partials, h->edge_blocks, h->ctrl);
+    edge_kernel<<<h->edge_blocks, EDGE_THREADS, 0, h->stream>>>(h->nE, h->nHown, h->edge_he_tail, h->edge_he_head, h->edge_counted, h->xc, h->mu, h->z, h->ctrl,
+                                                                h->partials, h->ticket, fuse, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap);
     return 0;
 }
 static int launch_ctrl(GcsHandle *h) {
     if (h->nP > 1) return 0;   // fused into batched_edge_kernel
     control_kernel<<<1, 32, 0, h->stream>>>(h->ctrl, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap);
+    return 0;
+}
+static void launch_iteration(GcsHandle *h) { launch_k1(h); launch_edge(h, 1); }    // 2 launches per ADMM iteration
+// `iters` iterations as one CUDA graph launch (captured once per chunk length; the kernels read rho / stop from the control block)
+static int launch_chunk(GcsHandle *h, int iters) {
+    // only whole chunks of check_every iterations are replayed (a remainder would force a re-instantiation every time)
+    if (!h->p.use_graph || h->stream != h->own_stream || iters < 2 || iters != h->p.check_every) { for (int i = 0; i < iters; ++i) launch_iteration(h); return 0; }
+    if (!h->graph_exec || h->graph_iters != iters) {
+        drop_graph(h);
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < iters; ++i) launch_iteration(h);
+        CK(cudaStreamEndCapture(h->stream, &graph));
+        cudaError_t e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { h->graph_exec = nullptr; return set_err(GCS_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+        h->graph_iters = iters;
+    }
+    CK(cudaGraphLaunch(h->graph_exec, h->stream));
     return 0;
 }
 static int set_ignore_stop(GcsHandle *h, int v) {
@@ -515,7 +583,7 @@ static bool any_diverged(const GcsHandle *h) {
 }
 
 extern "C" int gcsadmm_vertex_update(GcsHandle *h) { if (!h) return set_err(GCS_E_INVALID, "null handle%s", ""); CK(cudaSetDevice(h->device)); launch_k1(h); CK(cudaGetLastError()); return 0; }
-extern "C" int gcsadmm_edge_update(GcsHandle *h) { if (!h) return set_err(GCS_E_INVALID, "null handle%s", ""); CK(cudaSetDevice(h->device)); launch_edge(h); CK(cudaGetLastError()); return 0; }
+extern "C" int gcsadmm_edge_update(GcsHandle *h) { if (!h) return set_err(GCS_E_INVALID, "null handle%s", ""); CK(cudaSetDevice(h->device)); launch_edge(h, 0); CK(cudaGetLastError()); return 0; }
 extern "C" int gcsadmm_control(GcsHandle *h) { if (!h) return set_err(GCS_E_INVALID, "null handle%s", ""); CK(cudaSetDevice(h->device)); launch_ctrl(h); CK(cudaGetLastError()); return 0; }
 extern "C" int gcsadmm_sums_device_ptr(GcsHandle *h, void **p) { if (!h || !p) return set_err(GCS_E_INVALID, "null argument%s", ""); *p = (char *)h->ctrl + offsetof(Ctrl, sums); return 0; }
 extern "C" int gcsadmm_xc_device_ptr(GcsHandle *h, void **p) { if (!h || !p) return set_err(GCS_E_INVALID, "null argument%s", ""); *p = h->xc; return 0; }
@@ -524,7 +592,11 @@ extern "C" int gcsadmm_step(GcsHandle *h, int k) {
     if (!h) return set_err(GCS_E_INVALID, "null handle%s", "");
     CK(cudaSetDevice(h->device));
     int rc = set_ignore_stop(h, 1); if (rc) return rc;
-    for (int i = 0; i < k; ++i) { launch_k1(h); launch_edge(h); launch_ctrl(h); }
+    while (k > 0) {
+        const int chunk = k < h->p.check_every ? k : h->p.check_every;
+        rc = launch_chunk(h, chunk); if (rc) return rc;
+        k -= chunk;
+    }
     rc = set_ignore_stop(h, 0); if (rc) return rc;
     CK(cudaGetLastError());
     return fetch_ctrl(h);
@@ -538,7 +610,7 @@ extern "C" int gcsadmm_run(GcsHandle *h, int max_iters, GcsStatus *st) {
     while (done < max_iters && !all_stopped(h)) {
         int chunk = h->p.check_every;
         if (chunk > max_iters - done) chunk = max_iters - done;
-        for (int i = 0; i < chunk; ++i) { launch_k1(h); launch_edge(h); launch_ctrl(h); }
+        rc = launch_chunk(h, chunk); if (rc) return rc;
         CK(cudaGetLastError());
         rc = fetch_ctrl(h); if (rc) return rc;
         done += chunk;
@@ -637,7 +709,7 @@ extern "C" int gcsadmm_time_steps(GcsHandle *h, int k, float *ms_total, float *m
         if (split) CK(cudaEventRecord(h->ev[1], h->stream));
         launch_k1(h);
         if (split) CK(cudaEventRecord(h->ev[2], h->stream));
-        launch_edge(h); launch_ctrl(h);
+        launch_edge(h, 1);
         if (split) {
             CK(cudaEventRecord(h->ev[3], h->stream));
             CK(cudaEventSynchronize(h->ev[3]));
@@ -689,39 +761,74 @@ extern "C" int gcsadmm_flush_l2(GcsHandle *h, long long bytes) {
 }
 
 // Switches the x-update to the inexact `perf` mode (vertex_perf.cuh).  Tables are built by the host
-// (gcs-admm_b200/perf.py): the inverse K1^-1 of every vertex class and the polygon cones.
+// (gcs-admm_b200/perf.py): the structured v-step of every vertex class, the polygon cones, the block list and the tiling.
 extern "C" int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *c) {
     if (!h || !c) return set_err(GCS_E_INVALID, "null argument%s", "");
-    if (c->inner_iters < 1 || c->n_classes < 1 || !c->vclass || !c->class_koff || !c->kinv || !c->cone_off || !c->cone)
+    if (c->inner_iters < 1 || c->n_classes < 1 || c->n_tiles < 1 || c->n_blocks < 0 || !c->vclass || !c->cls_tab || !c->cone_off || !c->cone ||
+        !c->blk_off || !c->tile_voff || (c->n_blocks && (!c->blk_he || !c->blk_info)))
         return set_err(GCS_E_INVALID, "incomplete perf-mode tables%s", "");
+    if (!(c->alpha > 0.0 && c->alpha < 2.0) || !(c->kappa > 0.0)) return set_err(GCS_E_INVALID, "perf mode needs 0 < alpha < 2 and kappa > 0%s", "");
+    // consistency of the tables with the graph (bad offsets would be out-of-bounds accesses in the kernel)
+    if (c->tile_voff[0] != 0 || c->tile_voff[c->n_tiles] != h->nV || c->blk_off[0] != 0 || c->blk_off[h->nV] != c->n_blocks || c->cone_off[0] != 0)
+        return set_err(GCS_E_INVALID, "perf-mode offsets do not span the graph%s", "");
+    for (int t = 0; t < c->n_tiles; ++t) {
+        const int a = c->tile_voff[t], b = c->tile_voff[t + 1];
+        if (b <= a || b > h->nV || b - a > 255 || b - a > c->cap_verts || c->blk_off[b] - c->blk_off[a] > c->cap_blocks ||
+            c->cone_off[b] - c->cone_off[a] > c->cap_cone || c->blk_off[b] < c->blk_off[a] || c->cone_off[b] < c->cone_off[a])
+            return set_err(GCS_E_INVALID, "perf-mode tile exceeds the declared capacities%s", "");
+    }
+    for (int v = 0; v < h->nV; ++v) if (c->vclass[v] >= c->n_classes) return set_err(GCS_E_INVALID, "vclass out of range%s", "");
+    for (int b = 0; b < c->n_blocks; ++b) if (c->blk_he[b] >= h->nHown) return set_err(GCS_E_INVALID, "blk_he out of range%s", "");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
+    drop_graph(h);
+    free_perf(h);                 // a second call replaces the tables of the first
     int rc = 0;
     const size_t ncone = (size_t)c->cone_off[h->nV];
-    int kcap = 3;
-    for (int v = 0; v < h->nV; ++v) { const int k = c->cone_off[v + 1] - c->cone_off[v]; if (k > kcap) kcap = k; }
     if (!rc) rc = upload(&h->p_vclass, c->vclass, (size_t)h->nV);
-    if (!rc) rc = upload(&h->p_class_koff, c->class_koff, (size_t)c->n_classes);
-    if (!rc) rc = upload(&h->p_kinv, c->kinv, (size_t)c->kinv_len);
+    if (!rc) rc = upload(&h->p_cls_tab, c->cls_tab, (size_t)c->n_classes * GCS_CLS_STRIDE);
     if (!rc) rc = upload(&h->p_cone_off, c->cone_off, (size_t)h->nV + 1);
     if (!rc) rc = upload(&h->p_cone, c->cone, GCS_CONE_REC * ncone);
-    const int stride = gcs_perf_state_stride(h->dcap);
-    if (!rc) rc = upload(&h->p_state, (const double *)nullptr, (size_t)h->nV * stride);
-    if (rc) return rc;
-    h->PL = gcs_perf_layout(h->dcap, kcap);
-    h->PT.vclass = h->p_vclass; h->PT.class_koff = h->p_class_koff; h->PT.kinv = h->p_kinv; h->PT.cone_off = h->p_cone_off;
-    h->PT.cone = h->p_cone; h->PT.state = h->p_state; h->PT.state_stride = stride; h->PT.inner_iters = c->inner_iters;
+    if (!rc) rc = upload(&h->p_blk_off, c->blk_off, (size_t)h->nV + 1);
+    if (!rc) rc = upload(&h->p_blk_he, c->blk_he, (size_t)c->n_blocks);
+    if (!rc) rc = upload(&h->p_blk_info, c->blk_info, (size_t)c->n_blocks);
+    if (!rc) rc = upload(&h->p_tile_voff, c->tile_voff, (size_t)c->n_tiles + 1);
+    if (!rc) rc = upload(&h->p_tstate, (const double *)nullptr, 12 * (size_t)c->n_blocks);
+    if (!rc) rc = upload(&h->p_tn, (const double *)nullptr, 2 * (size_t)h->nV);
+    if (rc) { free_perf(h); return rc; }
+    h->perf_nblocks = c->n_blocks;
+    h->PL = gcs_perf_layout(c->cap_blocks, c->cap_verts, c->cap_cone);
+    h->PT.vclass = h->p_vclass; h->PT.cls_tab = h->p_cls_tab; h->PT.cone_off = h->p_cone_off; h->PT.cone = h->p_cone;
+    h->PT.blk_off = h->p_blk_off; h->PT.blk_he = h->p_blk_he; h->PT.blk_info = h->p_blk_info; h->PT.tile_voff = h->p_tile_voff;
+    h->PT.ntiles = c->n_tiles; h->PT.tstate = h->p_tstate; h->PT.tn = h->p_tn; h->PT.inner_iters = c->inner_iters;
     h->PT.alpha = c->alpha; h->PT.kappa = c->kappa;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
-    const size_t per_warp = (size_t)h->PL.total * sizeof(double);
-    int w = (int)(prop.sharedMemPerBlockOptin / per_warp);
-    if (w < 1) return set_err(GCS_E_INVALID, "perf-mode vertex state too large for shared memory%s", "");
-    if (w > PERF_MAX_WARPS) w = PERF_MAX_WARPS;
-    h->perf_warps = w; h->perf_smem = (int)(w * per_warp);
-    h->perf_blocks = (h->nV + w - 1) / w;
+    const size_t bytes = (size_t)h->PL.total * sizeof(double);
+    if (bytes > prop.sharedMemPerBlockOptin) { free_perf(h); return set_err(GCS_E_INVALID, "perf-mode tile too large for shared memory (a vertex of very high degree)%s", ""); }
+    h->perf_smem = (int)bytes;
     CK(cudaFuncSetAttribute(vertex_perf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->perf_smem));
     CK(cudaFuncSetAttribute(vertex_perf_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    perf_init_dead_kernel<<<(h->nV + 255) / 256, 256, 0, h->stream>>>(graph_view(h), state_view(h));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
     h->perf_on = 1;
+    return 0;
+}
+
+extern "C" int gcsadmm_get_perf_state(GcsHandle *h, double *tstate, double *tn) {
+    if (!h || !h->perf_on) return set_err(GCS_E_INVALID, "perf mode is not enabled%s", "");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (tstate && h->perf_nblocks) CK(cudaMemcpy(tstate, h->p_tstate, sizeof(double) * 12 * (size_t)h->perf_nblocks, cudaMemcpyDeviceToHost));
+    if (tn) CK(cudaMemcpy(tn, h->p_tn, sizeof(double) * 2 * (size_t)h->nV, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int gcsadmm_set_perf_state(GcsHandle *h, const double *tstate, const double *tn) {
+    if (!h || !h->perf_on) return set_err(GCS_E_INVALID, "perf mode is not enabled%s", "");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (tstate && h->perf_nblocks) CK(cudaMemcpy(h->p_tstate, tstate, sizeof(double) * 12 * (size_t)h->perf_nblocks, cudaMemcpyHostToDevice));
+    if (tn) CK(cudaMemcpy(h->p_tn, tn, sizeof(double) * 2 * (size_t)h->nV, cudaMemcpyHostToDevice));
     return 0;
 }

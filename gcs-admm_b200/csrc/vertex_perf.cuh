@@ -1,426 +1,380 @@
-// K1 in `perf` mode — the x-update of the full-vertex-split ADMM done INEXACTLY by K warm-started iterations
-// of an operator-splitting scheme whose steps are all closed-form (north_star: "fixed-iteration inner
-// projection / primal-dual scheme").  One warp per vertex, state in shared memory, same null-space
-// parametrisation u = N v + up as the exact kernel (vertex_ipm.cuh).
+// K1 in `perf` mode — the x-update of the full-vertex-split ADMM (reference admm_solver_v3.py:352-540) done INEXACTLY by
+// K warm-started iterations of an operator-splitting scheme whose steps are all closed-form (north_star:
+// "fixed-iteration inner projection / primal-dual scheme").
 //
-// Every inequality of the vertex program (reference admm_solver_v3.py:416-440) says that a (point, flow) pair
-// lies in the perspective cone of the vertex's polygon,  K_P = {(p, h) in R^3 : A p <= h b}:
+// Every inequality of the vertex program (:416-440) says that a (point, flow) pair lies in the perspective cone of the
+// vertex's polygon,  K_P = {(p, h) in R^3 : A p <= h b}:
 //     C3: (a_i, y_e)        C4: (x_i - a_i, 1 - y_e)        C1: (z_i, y_v)        C2: (x_i - z_i, 1 - y_v)
-// and the pairs are 0/+-1 linear images  c = M u + m0  of the variables.  Splitting  c in prod K_P  from u:
-//     v-step : minimise  rho/2 |S u - T|^2 + eps'y + sigma/2 |M u + m0 - c + lam|^2   over v   (u = N v + up)
-//              -> v <- v - (1/rho) K1^-1 G(v),  K1 = N'(S'S + kappa M'M)N  depends only on the vertex CLASS
-//              (type, #in, #out) — not on the polygon —, so its inverse is a table shared by all vertices;
-//     c-step : c <- Proj_{K_P}(alpha (M u + m0) + (1 - alpha) c + lam)   exact 3-D cone projection, O(#polygon vertices);
-//              the path-length term |z_1 - z_2| (:380-384) is a block soft-threshold with threshold 1/sigma;
-//     lam    : lam <- lam + alpha (M u + m0) + (1 - alpha) c_old - c_new.
-// sigma = kappa * rho, so the rho-adaptation rescale of the ADMM duals (:705/:708) applies to lam as well.
-// (c, lam) persist per vertex in HBM between ADMM iterations (warm start).
+// and the pairs are 0/+-1 linear images  pv = M u + m0  of the variables u = (x, z_v, y_v, (a_1, a_2, y) per live half-edge).
+// Splitting  c in prod K_P  from u, with one vector  t = c + lam  per pair kept in HBM between ADMM iterations
+// (Moreau: c = Proj_K(t), lam = t - c), one inner iteration is
+//     c-step : c = Proj_{K_P}(t), lam = t - c        exact 3-D cone projection, O(#polygon vertices); the path-length term
+//              |z_1 - z_2| (:380-384) is a block soft-threshold with threshold 1 / sigma  (sigma = kappa rho)
+//     v-step : u = argmin  rho/2 |S u - T|^2 + eps'y + sigma/2 |M u + m0 - (c - lam)|^2   over the equalities C6 / C7 (:450-464)
+//     t-step : t = alpha (M u + m0) + (1 - alpha) c + lam
+// The v-step is an equality-constrained quadratic whose matrix depends only on the vertex CLASS (type, #in, #out).  Its
+// solution has the structure  u[b, tau] = dinv[g, tau] r[b, tau] + beta[g, tau]  for the five variables tau of a
+// half-edge block b in group g (in / out), with the 19-vector (x, z_v, y_v, beta_in, beta_out) a class-constant linear
+// map of (r_x, r_z, r_yv, sum_in r, sum_out r): O(d) work per vertex instead of a dense (5d)^2 product
+// (tables: gcs-admm_b200/perf.py class_tables).
 //
-// The fixed point of the outer ADMM is unchanged (an exact minimiser of the vertex program is a fixed point of
-// the inner iteration); the trajectory is not the reference's, so this mode is validated at convergence against
-// the classic relaxation optimum (tests/test_gpu_perf.py, tools/prototypes/inner_first_order.py), not per iteration.
+// Mapping: one thread block per TILE of consecutive vertices (<= 64 blocks = 256 pairs); every phase is a flat loop
+// over (pair | block variable | vertex) items of the whole tile, so lanes stay busy whatever the degrees are; phases
+// exchange data through shared memory only.  The per-tile state t, the cone records and the path-length state are
+// contiguous in HBM and move with 1-D bulk async copies (cp.async.bulk + mbarrier).
+//
+// The fixed point of the outer ADMM is unchanged (an exact minimiser of the vertex program is a fixed point of the
+// inner iteration); the trajectory is not the reference's, so this mode is validated at convergence against the
+// classic relaxation optimum and gated by tests/test_gpu_perf.py.
+//
+// The file compiles two ways, like vertex_ipm.cuh: nvcc (device) and g++ with GCS_EMULATE (tests only: one host
+// thread plays the whole thread block, loops run serially, barriers are no-ops, bulk copies are memcpy).
 #pragma once
+#include <string.h>
+#include "gcs_ctrl.h"
 #include "vertex_update.cuh"
+
 #define GCS_CONE_REC 12   // doubles per polygon vertex in the cone table
-// the per-vertex (c, lam) records are streamed once per iteration: evict-first loads / stores keep L2 for xc, z, mu and the tables
-#if defined(__CUDA_ARCH__)
-#define GCS_LD_STREAM(p) __ldcs(p)
-#define GCS_ST_STREAM(p, x) __stcs((p), (x))
+#define GCS_NCX 19        // extended core of the v-step: x(4) z(4) y_v | beta_in(5) | beta_out(5)
+#define GCS_CLS_G0 361    // class table: G (19 x 19) | g0 (19) | dinv (2 x 5) | pad
+#define GCS_CLS_DINV 380
+#define GCS_CLS_STRIDE 392
+#define GCS_PERF_THREADS 256
+
+#ifdef GCS_EMULATE
+#define GCS_CTA_LOOP(i, n) for (int i = 0; i < (n); ++i)
+#define GCS_CTA_SYNC() ((void)0)
 #else
-#define GCS_LD_STREAM(p) (*(p))
-#define GCS_ST_STREAM(p, x) (*(p) = (x))
+#define GCS_CTA_LOOP(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
+#define GCS_CTA_SYNC() __syncthreads()
 #endif
 
 struct GcsPerfTables {
-    const int *vclass;         // [nV] class id (-1: vertex not solved here: dead)
-    const int *class_koff;     // [ncls] offset of the class's K1^-1 (n x n, row-major) in kinv
-    const double *kinv;
+    const int *vclass;         // [nV] class id (-1: dead vertex)
+    const double *cls_tab;     // [ncls][GCS_CLS_STRIDE]
     const int *cone_off;       // [nV+1] polygon vertices of vertex v: cone_off[v]..cone_off[v+1]
     const double *cone;        // GCS_CONE_REC doubles per polygon vertex (see gcs_cone_project)
-    double *state;             // [nV][state_stride]: c then lam, (3 * 4 (dcap + 1) + 2) doubles each
-    int state_stride;
+    const int *blk_off;        // [nV+1] blocks of vertex v: its live half-edges in half-edge order, then (z_v, y_v)
+    const int *blk_he;         // [B] half-edge of the block, -1 for the (z_v, y_v) block
+    const int *blk_info;       // [B] bits 0-7: vertex index inside its tile | bits 8-9: group (0 in, 1 out, 2 z-block) | bit 10: 's' / 't'
+    const int *tile_voff;      // [ntiles+1]
+    int ntiles;
+    double *tstate;            // [B][4 pairs][3]  t = c + lam of every (point, flow) pair
+    double *tn;                // [nV][2]          the same for the path-length item z_1 - z_2
     int inner_iters;           // K
     double alpha, kappa;
 };
 
-// scratch (doubles) of one warp in perf mode
-struct GcsPerfLayout { int dcap, kcap, ncap, nucap, npair, u, gu, v, gv, pv, c, lam, w, cone, tgt, ints, total; };
+// shared memory of one tile (offsets in doubles)
+struct GcsPerfLayout { int nb_cap, nvt_cap, cone_cap, tS, eS, cone, tnS, enS, T, r, cin, cout, vd, vi, bi, total; };
+#define GCS_VI_N 8        // ints per vertex of the tile
+#define GCS_VI_CONE 0     // first cone record, relative to the tile's
+#define GCS_VI_NV 1       // polygon vertices
+#define GCS_VI_CLS 2
+#define GCS_VI_TERM 3
+#define GCS_VI_BLK 4      // first block, relative to the tile's
+#define GCS_VI_NB 5       // blocks (0: dead vertex)
+#define GCS_VI_ACTIVE 6   // its problem is still iterating
+#define GCS_VI_HE 7       // first half-edge, relative to the tile's
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-static inline GcsPerfLayout gcs_perf_layout(int dcap, int kcap) {
+static inline GcsPerfLayout gcs_perf_layout(int nb_cap, int nvt_cap, int cone_cap) {
     GcsPerfLayout L;
-    if (dcap < 1) dcap = 1;
-    if (kcap < 3) kcap = 3;
-    L.dcap = dcap; L.kcap = kcap; L.ncap = 5 * dcap; L.nucap = GCS_NCORE + 5 * dcap; L.npair = 4 * (dcap + 1);
+    if (nb_cap < 1) nb_cap = 1;
+    if (nvt_cap < 1) nvt_cap = 1;
+    if (cone_cap < 1) cone_cap = 1;
+    L.nb_cap = nb_cap; L.nvt_cap = nvt_cap; L.cone_cap = cone_cap;
     int o = 0;
-    L.u = o; o += L.nucap; L.gu = o; o += L.nucap;
-    L.v = o; o += L.ncap; L.gv = o; o += L.ncap;
-    const int np3 = 3 * L.npair + 2;
-    L.pv = o; o += np3; L.c = o; o += np3; L.lam = o; o += np3; L.w = o; o += np3;
-    L.cone = o; o += GCS_CONE_REC * kcap;
-    L.tgt = o; o += 5 * dcap;
-    L.ints = o; o += (3 * dcap + 1) / 2 + 1;
-    L.total = o;
+    L.tS = o; o += 12 * nb_cap;              // bulk-copied arrays first: 16-byte aligned offsets
+    L.cone = o; o += GCS_CONE_REC * cone_cap;
+    L.tnS = o; o += 2 * nvt_cap;
+    L.eS = o; o += 12 * nb_cap;
+    L.enS = o; o += 2 * nvt_cap;
+    L.T = o; o += 5 * nb_cap;
+    L.r = o; o += 5 * nb_cap;
+    L.cin = o; o += GCS_NCX * nvt_cap;
+    L.cout = o; o += GCS_NCX * nvt_cap;
+    L.vd = o; o += 2 * nvt_cap;
+    L.vi = o; o += (GCS_VI_N * nvt_cap + 1) / 2;
+    L.bi = o; o += nb_cap;                   // 2 ints per block
+    L.total = o + (o & 1);
     return L;
 }
-#if defined(__CUDACC__)
-__host__ __device__
-#endif
-static inline int gcs_perf_state_stride(int dcap) { return 2 * (3 * 4 * (dcap + 1) + 2); }
 
 // exact projection of c onto the cone spanned by the rays r_k = (V_k, 1), k = 0..nv-1 (counter-clockwise).
 // record k: V_k (2) | unit outward normal n_k of the face between rays k and k+1 (3) | 1/|r_k|^2 | sector normals ma, mb (3 + 3)
-// The projection is c itself, or lies on a face (inside its sector), on a ray, or is the apex: take the nearest candidate.
-// Candidates are coded  -1 apex | 2k ray k | 2k+1 face k  and scanned in that order with a strict "<", so the result does
-// not depend on how the scan is split over lanes (ties go to the smallest code).
-GCS_DEV void gcs_cone_scan(const double *cone, int nv, int first, int step, double c0, double c1, double c2, double &bd, int &code, bool &inside) {
-    for (int k = first; k < nv; k += step) {
+// The projection is c itself (inside), lies on a face (then c is outside that face and its foot point is inside the
+// face's sector: unique, and no other candidate can be nearer), on a ray (the one with the largest reduction
+// tau^2 / |r|^2 of the squared distance), or is the apex.  ma, mb are orthogonal to n_k, so the sector test of the foot
+// point  c - dist n_k  is a test on c itself.
+GCS_DEV void gcs_cone_project(const double *cone, int nv, double c0, double c1, double c2, double &q0, double &q1, double &q2) {
+    double best = 0.0;
+    int code = -1;          // -1 apex | 2k ray k | 2k+1 face k
+    bool inside = true;
+    for (int k = 0; k < nv; ++k) {
         const double *ck = cone + GCS_CONE_REC * k;
-        const double rx = ck[0], ry = ck[1];
-        const double tau = (c0 * rx + c1 * ry + c2) * ck[5];                  // ray k
+        const double tau = c0 * ck[0] + c1 * ck[1] + c2;
+        const double dist = ck[2] * c0 + ck[3] * c1 + ck[4] * c2;
         if (tau > 0.0) {
-            const double e0 = c0 - tau * rx, e1 = c1 - tau * ry, e2 = c2 - tau;
-            const double dd = e0 * e0 + e1 * e1 + e2 * e2;
-            if (dd < bd) { bd = dd; code = 2 * k; }
+            const double red = tau * tau * ck[5];
+            if (red > best) { best = red; code = 2 * k; }
         }
-        const double nx = ck[2], ny = ck[3], nh = ck[4];
-        const double dist = nx * c0 + ny * c1 + nh * c2;
-        if (dist > 0.0) {                                                      // outside face k
+        if (dist > 0.0) {
             inside = false;
-            const double p0 = c0 - dist * nx, p1 = c1 - dist * ny, p2 = c2 - dist * nh;
-            if (p0 * ck[6] + p1 * ck[7] + p2 * ck[8] >= 0.0 && p0 * ck[9] + p1 * ck[10] + p2 * ck[11] >= 0.0) {
-                const double dd = dist * dist;
-                if (dd < bd) { bd = dd; code = 2 * k + 1; }
-            }
+            if (c0 * ck[6] + c1 * ck[7] + c2 * ck[8] >= 0.0 && c0 * ck[9] + c1 * ck[10] + c2 * ck[11] >= 0.0) { best = 1e300; code = 2 * k + 1; }
         }
     }
-}
-GCS_DEV void gcs_cone_point(const double *cone, int code, bool inside, double c0, double c1, double c2, double &q0, double &q1, double &q2) {
     if (inside) { q0 = c0; q1 = c1; q2 = c2; return; }
     q0 = 0.0; q1 = 0.0; q2 = 0.0;
     if (code < 0) return;
     const double *ck = cone + GCS_CONE_REC * (code >> 1);
     if (code & 1) {
-        const double nx = ck[2], ny = ck[3], nh = ck[4];
-        const double dist = nx * c0 + ny * c1 + nh * c2;
-        q0 = c0 - dist * nx; q1 = c1 - dist * ny; q2 = c2 - dist * nh;
+        const double dist = ck[2] * c0 + ck[3] * c1 + ck[4] * c2;
+        q0 = c0 - dist * ck[2]; q1 = c1 - dist * ck[3]; q2 = c2 - dist * ck[4];
     } else {
-        const double rx = ck[0], ry = ck[1];
-        const double tau = (c0 * rx + c1 * ry + c2) * ck[5];
-        q0 = tau * rx; q1 = tau * ry; q2 = tau;
+        const double tau = (c0 * ck[0] + c1 * ck[1] + c2) * ck[5];
+        q0 = tau * ck[0]; q1 = tau * ck[1]; q2 = tau;
     }
-}
-GCS_DEV void gcs_cone_project(const double *cone, int nv, double c0, double c1, double c2, double &q0, double &q1, double &q2) {
-    double bd = c0 * c0 + c1 * c1 + c2 * c2;     // the apex
-    int code = -1;
-    bool inside = true;
-    gcs_cone_scan(cone, nv, 0, 1, c0, c1, c2, bd, code, inside);
-    gcs_cone_point(cone, code, inside, c0, c1, c2, q0, q1, q2);
 }
 
-// pair values  pv = M u + m0  (3 per family slot, then the 2 entries of z_1 - z_2)
-GCS_DEV void gcs_pair_values(const double *u, double *pv, int d, bool term, int npair_cap, int lane) {
-    const int nitems = term ? 2 * (d + 1) : 4 * (d + 1);
-    GCS_LANE_LOOP(it, nitems) {
-        int fam, i, blk;
-        if (term) { fam = 0; i = it & 1; blk = it >> 1; } else { fam = it & 1; i = (it >> 1) & 1; blk = it >> 2; }
-        const int po = (blk < d ? gcs_uw(blk) : GCS_UZ) + 2 * i, yo = blk < d ? gcs_uw(blk) + 4 : GCS_UYV, xo = GCS_UX + 2 * i;
-        double *p = pv + 3 * gcs_slot(blk, i, fam);
-        p[0] = fam ? u[xo] - u[po] : u[po];
-        p[1] = fam ? u[xo + 1] - u[po + 1] : u[po + 1];
-        p[2] = fam ? 1.0 - u[yo] : u[yo];
-    }
-    if (lane == 0) {
-        pv[3 * npair_cap] = u[GCS_UZ] - u[GCS_UZ + 2];
-        pv[3 * npair_cap + 1] = u[GCS_UZ + 1] - u[GCS_UZ + 3];
-    }
-    GCS_SYNC();
+#if !defined(GCS_EMULATE) && defined(__CUDACC__)
+// 1-D bulk async copies (TMA unit, SASS UBLKCP) with an mbarrier for the loads and a bulk group for the stores
+__device__ __forceinline__ unsigned gcs_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gcs_mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gcs_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-
-// gu = M' w  (w: 3 per slot + 2)
-GCS_DEV void gcs_pair_adjoint(const double *w, double *gu, int d, bool term, int npair_cap, int lane) {
-    GCS_LANE_LOOP(q, 4 * (d + 1)) {          // point slots a_i / z_i
-        const int blk = q >> 2, i = (q >> 1) & 1, c = q & 1;
-        const double *w3 = w + 3 * gcs_slot(blk, i, 0);
-        gu[(blk < d ? gcs_uw(blk) : GCS_UZ) + 2 * i + c] = w3[c] - (term ? 0.0 : w3[3 + c]);
-    }
-    GCS_LANE_LOOP(blk, d + 1) {              // flow slots y / y_v
-        const double *w0 = w + 3 * gcs_slot(blk, 0, 0);
-        double s = w0[2] + w0[6 + 2];
-        if (!term) s -= w0[3 + 2] + w0[9 + 2];
-        gu[blk < d ? gcs_uw(blk) + 4 : GCS_UYV] = s;
-    }
-    GCS_LANE_LOOP(q, 4) {                    // x_i collects every C4 | C2 pair of point i
-        const int i = q >> 1, c = q & 1;
-        double s = 0.0;
-        if (!term) for (int blk = 0; blk <= d; ++blk) s += w[3 * gcs_slot(blk, i, 1) + c];
-        gu[GCS_UX + q] = s;
-    }
-    GCS_SYNC();
-    if (lane == 0) {
-        gu[GCS_UT] = 0.0;
-        const double n0 = w[3 * npair_cap], n1 = w[3 * npair_cap + 1];
-        gu[GCS_UZ] += n0; gu[GCS_UZ + 1] += n1; gu[GCS_UZ + 2] -= n0; gu[GCS_UZ + 3] -= n1;
-    }
-    GCS_SYNC();
+__device__ __forceinline__ void gcs_mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gcs_smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void gcs_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(gcs_smem_u32(dst)), "l"(src), "r"(bytes), "r"(gcs_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void gcs_mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(gcs_smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void gcs_bulk_s2g(void *dst, const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(gcs_smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gcs_bulk_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void gcs_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
 
-// x-update of one vertex in perf mode.  Returns 1 (the vertex did K inner iterations) or 0 (no program).
-GCS_DEV int gcs_vertex_update_perf(const GcsGraphView &G, const GcsStateView &St, const GcsPerfTables &T, int v, double rho,
-                                   double mu_scale, const GcsPerfLayout &L, double *S, int lane) {
-    const int h0 = G.he_off[v], h1 = G.he_off[v + 1];
-    const int type = G.vtype[v];
-    // Loads are issued in two dependent stages only: (flags, edge ids, cone records, stored state) -> (edge variables, duals).
-#ifndef GCS_EMULATE
-    const bool fast = h1 - h0 <= 32;           // one lane per half-edge keeps its flags / edge id in registers
-    int f = GCS_HE_ZERO, e_l = 0;
-    if (fast && lane < h1 - h0) { f = G.he_flags[h0 + lane]; e_l = G.he_edge[h0 + lane]; }
+// x-update of one tile of vertices in perf mode.  `bar` is an mbarrier in shared memory (device build only).
+GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const GcsPerfTables &T, const GcsPerfLayout &L,
+                           double *S, int tile, Ctrl *ctrl_all, const int *vprob, unsigned long long *bar) {
+    const int v0 = T.tile_voff[tile], nvt = T.tile_voff[tile + 1] - v0;
+    const int b0 = T.blk_off[v0], nb = T.blk_off[v0 + nvt] - b0;
+    const int c0 = T.cone_off[v0], ncone = T.cone_off[v0 + nvt] - c0;
+    const int h0 = G.he_off[v0], nhe = G.he_off[v0 + nvt] - h0;
+    double *tS = S + L.tS, *eS = S + L.eS, *coneS = S + L.cone, *tnS = S + L.tnS, *enS = S + L.enS, *TS = S + L.T, *rS = S + L.r;
+    double *cin = S + L.cin, *cout = S + L.cout, *vd = S + L.vd;
+    int *vi = (int *)(S + L.vi), *bhe = (int *)(S + L.bi), *binfo = bhe + L.nb_cap;
+    // ---- P0: stage the tile: state / cone records by bulk copies, per-vertex and per-block descriptors by plain loads
+#if defined(GCS_EMULATE)
+    memcpy(tS, T.tstate + 12 * (size_t)b0, sizeof(double) * 12 * nb);
+    memcpy(tnS, T.tn + 2 * (size_t)v0, sizeof(double) * 2 * nvt);
+    memcpy(coneS, T.cone + GCS_CONE_REC * (size_t)c0, sizeof(double) * GCS_CONE_REC * ncone);
 #else
-    const bool fast = false;
-    const int f = 0, e_l = 0;
+    if (threadIdx.x == 0) {
+        gcs_mbar_init(bar, 1);
+        gcs_mbar_expect_tx(bar, (unsigned)(sizeof(double) * (12 * nb + 2 * nvt + GCS_CONE_REC * ncone)));
+        if (nb) gcs_bulk_g2s(tS, T.tstate + 12 * (size_t)b0, (unsigned)(sizeof(double) * 12 * nb), bar);
+        gcs_bulk_g2s(tnS, T.tn + 2 * (size_t)v0, (unsigned)(sizeof(double) * 2 * nvt), bar);
+        if (ncone) gcs_bulk_g2s(coneS, T.cone + GCS_CONE_REC * (size_t)c0, (unsigned)(sizeof(double) * GCS_CONE_REC * ncone), bar);
+    }
 #endif
-    const int np3 = 3 * L.npair + 2;
-    const int c0 = T.cone_off[v], nv = T.cone_off[v + 1] - c0;
-    double *st = T.state + (size_t)v * T.state_stride;
-    if (type != GCS_VT_DEAD) {
-        GCS_LANE_LOOP(q, GCS_CONE_REC * nv) S[L.cone + q] = T.cone[GCS_CONE_REC * (size_t)c0 + q];
-        GCS_LANE_LOOP(q, np3) { S[L.c + q] = GCS_LD_STREAM(st + q); S[L.lam + q] = mu_scale * GCS_LD_STREAM(st + np3 + q); }    // sigma = kappa rho: lam rescales with mu
-    }
-    if (fast) {                                 // forced-zero half-edges, as in the exact kernel
-        if (lane < h1 - h0 && (f & GCS_HE_ZERO)) {
-            const int h = h0 + lane;
-            double *x = St.xc + 5 * (size_t)h;
-            double x0 = 0.0, x1 = 0.0;
-            if (!(f & GCS_HE_OUT)) {
-                x0 = St.z[5 * (size_t)e_l] + mu_scale * St.mu[5 * (size_t)h];
-                x1 = St.z[5 * (size_t)e_l + 1] + mu_scale * St.mu[5 * (size_t)h + 1];
-            }
-            x[0] = x0; x[1] = x1; x[2] = 0.0; x[3] = 0.0; x[4] = 0.0;
-        }
-    } else {
-        GCS_LANE_LOOP(i, h1 - h0) {
-            const int h = h0 + i;
-            if (G.he_flags[h] & GCS_HE_ZERO) {
-                double *x = St.xc + 5 * (size_t)h;
-                double x0 = 0.0, x1 = 0.0;
-                if (!(G.he_flags[h] & GCS_HE_OUT)) {
-                    const int e = G.he_edge[h];
-                    x0 = St.z[5 * (size_t)e] + mu_scale * St.mu[5 * (size_t)h];
-                    x1 = St.z[5 * (size_t)e + 1] + mu_scale * St.mu[5 * (size_t)h + 1];
-                }
-                x[0] = x0; x[1] = x1; x[2] = 0.0; x[3] = 0.0; x[4] = 0.0;
-            }
-        }
-    }
-    if (type == GCS_VT_DEAD) {
-        if (lane == 0) {
-            for (int k = 0; k < 4; ++k) { St.z_v[4 * (size_t)v + k] = 0.0; St.x_v[4 * (size_t)v + k] = G.cent[2 * (size_t)v + (k & 1)]; }
-            St.y_v[v] = 0.0;
-        }
-        return 0;
-    }
-    int *out = (int *)(S + L.ints), *prim = out + L.dcap, *hid = out + 2 * L.dcap;
-    int d = 0, jstar = -1;
-#ifndef GCS_EMULATE
-    if (fast) {                // live list by ballot + prefix popcount instead of a serial scan; each live lane gathers its own targets
-        const bool live = !(f & GCS_HE_ZERO);
-        const unsigned m = __ballot_sync(0xffffffffu, live);
-        if (live) {
-            const int k = __popc(m & ((1u << lane) - 1u)), h = h0 + lane;
-            out[k] = f & GCS_HE_OUT; hid[k] = h; prim[k] = (type == GCS_VT_TARGET) ? 1 : (f & GCS_HE_OUT);
-            const double *zz = St.z + 5 * (size_t)e_l, *mm = St.mu + 5 * (size_t)h;
-            double *t = S + L.tgt + 5 * k;
-            for (int c = 0; c < 5; ++c) t[c] = zz[c] + mu_scale * mm[c];
-        }
-        d = __popc(m);
-        const unsigned pm = __ballot_sync(0xffffffffu, live && ((type == GCS_VT_TARGET) || (f & GCS_HE_OUT)));
-        if (pm) jstar = __popc(m & ((1u << (31 - __clz(pm))) - 1u));      // the last primary block is the dependent one
-    } else
+    GCS_CTA_LOOP(i, nvt) {
+        const int v = v0 + i;
+        Ctrl *c = ctrl_all + (vprob ? vprob[v] : 0);
+        int *w = vi + GCS_VI_N * i;
+        w[GCS_VI_CONE] = T.cone_off[v] - c0; w[GCS_VI_NV] = T.cone_off[v + 1] - T.cone_off[v];
+        w[GCS_VI_CLS] = T.vclass[v]; w[GCS_VI_TERM] = G.vtype[v] != GCS_VT_GENERIC;
+        w[GCS_VI_BLK] = T.blk_off[v] - b0; w[GCS_VI_NB] = T.blk_off[v + 1] - T.blk_off[v];
+        w[GCS_VI_ACTIVE] = !(c->stop && !c->ignore_stop); w[GCS_VI_HE] = G.he_off[v] - h0;
+        vd[2 * i] = c->rho; vd[2 * i + 1] = c->mu_scale;
+        if (vprob && w[GCS_VI_ACTIVE] && w[GCS_VI_NB]) {
+#if defined(GCS_EMULATE)
+            c->inner_iters += (unsigned long long)T.inner_iters;
+#else
+            atomicAdd(&c->inner_iters, (unsigned long long)T.inner_iters);
 #endif
-    {
-        for (int h = h0; h < h1; ++h) {
-            const int fl = G.he_flags[h];
-            if (fl & GCS_HE_ZERO) continue;
-            if (lane == 0) { out[d] = fl & GCS_HE_OUT; hid[d] = h; prim[d] = (type == GCS_VT_TARGET) ? 1 : (fl & GCS_HE_OUT); }
-            d++;
-        }
-        GCS_SYNC();
-        for (int j = 0; j < d; ++j) if (prim[j]) jstar = j;
-        GCS_LANE_LOOP(q, 5 * d) {
-            const int j = q / 5, c = q - 5 * j, h = hid[j], e = G.he_edge[h];
-            S[L.tgt + q] = St.z[5 * (size_t)e + c] + mu_scale * St.mu[5 * (size_t)h + c];
         }
     }
-    const bool term = type != GCS_VT_GENERIC;
-    const int n = 5 * d, nu = GCS_NCORE + 5 * d;
-    GCS_SYNC();
-    double *u = S + L.u, *gu = S + L.gu, *vv = S + L.v, *gv = S + L.gv, *pv = S + L.pv, *cc = S + L.c, *lam = S + L.lam, *w = S + L.w;
-    const double *tgt = S + L.tgt;
-    const double sigma = T.kappa * rho, alpha = T.alpha;
-    const double *Kinv = T.kinv + T.class_koff[T.vclass[v]];
-    // start: v with  N v + up  closest to the stored pair copies is not needed — the v-step is an exact solve of a
-    // quadratic, so any starting v gives the same result; start from 0
-    GCS_LANE_LOOP(q, n) vv[q] = 0.0;
-    if (!term) {
-        // generic vertex: u(0) = up = 0, so the pair values are the constants  (a_i, y) = 0,  (x_i - a_i, 1 - y) = (0, 0, 1)
-        GCS_LANE_LOOP(q, nu) u[q] = 0.0;
-        GCS_LANE_LOOP(q, np3) pv[q] = 0.0;
-        GCS_SYNC();
-        GCS_LANE_LOOP(q, 2 * (d + 1)) pv[3 * gcs_slot(q >> 1, q & 1, 1) + 2] = 1.0;
-        GCS_SYNC();
-    } else {
-        GCS_SYNC();
-        gcs_forward(vv, u, d, jstar, prim, term, true, lane);
-        gcs_pair_values(u, pv, d, term, L.npair, lane);
+    GCS_CTA_LOOP(b, nb) { bhe[b] = T.blk_he[b0 + b]; binfo[b] = T.blk_info[b0 + b]; }
+    GCS_CTA_SYNC();
+    // ---- P1: consensus targets  T = z_e + mu_h  of the live half-edges; forced-zero half-edges are answered directly
+    GCS_CTA_LOOP(q, 5 * nb) {
+        const int b = q / 5, c = q - 5 * b, h = bhe[b], vl = binfo[b] & 255;
+        if (h < 0 || !vi[GCS_VI_N * vl + GCS_VI_ACTIVE]) continue;
+        TS[q] = St.z[5 * (size_t)G.he_edge[h] + c] + vd[2 * vl + 1] * St.mu[5 * (size_t)h + c];
     }
+    GCS_CTA_LOOP(q, 5 * nhe) {
+        const int hl = q / 5, c = q - 5 * hl, h = h0 + hl, f = G.he_flags[h];
+        if (!(f & GCS_HE_ZERO)) continue;
+        int vl = 0;
+        while (vl + 1 < nvt && vi[GCS_VI_N * (vl + 1) + GCS_VI_HE] <= hl) ++vl;
+        if (!vi[GCS_VI_N * vl + GCS_VI_ACTIVE]) continue;
+        // own copy and flow are 0; an incoming edge's "other copy" first point is unconstrained and sits on its target
+        double x = 0.0;
+        if (c < 2 && !(f & GCS_HE_OUT)) x = St.z[5 * (size_t)G.he_edge[h] + c] + vd[2 * vl + 1] * St.mu[5 * (size_t)h + c];
+        St.xc[5 * (size_t)h + c] = x;
+    }
+#if !defined(GCS_EMULATE)
+    gcs_mbar_wait(bar, 0);
+#endif
+    const double alpha = T.alpha, kappa = T.kappa;
     for (int it = 0; it < T.inner_iters; ++it) {
-        // G_u = rho S'(S u - T) + eps e_y + sigma M'(pv - c + lam)
-        GCS_LANE_LOOP(q, np3) w[q] = pv[q] - cc[q] + lam[q];
-        GCS_SYNC();
-        gcs_pair_adjoint(w, gu, d, term, L.npair, lane);
-        GCS_LANE_LOOP(q, nu) {
-            double g = sigma * gu[q];
-            if (q >= GCS_NCORE) {
-                const int j = (q - GCS_NCORE) / 5, c = q - GCS_NCORE - 5 * j;
-                const double *t = tgt + 5 * j;
-                if (out[j]) { if (c < 4) g += rho * (u[q] - t[c]); }
-                else if (c < 2) g += rho * (u[q] - t[2 + c]);
-                if (c == 4) g += rho * (u[q] - t[4]) + GCS_EDGE_PENALTY;
-            }
-            gu[q] = g;
+        const bool last = it + 1 == T.inner_iters;
+        // ---- P2: c-step.  d = c - lam (what the v-step sees) replaces t in place; e = (1 - alpha) c + lam waits for the t-step
+        GCS_CTA_LOOP(p, 4 * nb) {
+            const int b = p >> 2, info = binfo[b], vl = info & 255;
+            const int *w = vi + GCS_VI_N * vl;
+            if (!w[GCS_VI_ACTIVE] || ((info >> 10) & (p & 1))) continue;       // 's' / 't' have no C2 / C4 pairs
+            const double ms = it ? 1.0 : vd[2 * vl + 1];                      // sigma = kappa rho: lam rescales with mu (:705 / :708)
+            double *t = tS + 3 * p, *e = eS + 3 * p;
+            const double t0 = t[0], t1 = t[1], t2 = t[2];
+            double q0, q1, q2;
+            gcs_cone_project(coneS + GCS_CONE_REC * w[GCS_VI_CONE], w[GCS_VI_NV], t0, t1, t2, q0, q1, q2);
+            const double l0 = ms * (t0 - q0), l1 = ms * (t1 - q1), l2 = ms * (t2 - q2);
+            t[0] = q0 - l0; t[1] = q1 - l1; t[2] = q2 - l2;
+            e[0] = (1.0 - alpha) * q0 + l0; e[1] = (1.0 - alpha) * q1 + l1; e[2] = (1.0 - alpha) * q2 + l2;
         }
-        GCS_SYNC();
-        gcs_adjoint(gu, gv, d, jstar, prim, term, lane);
-        // v <- v - (1/rho) K1^-1 G_v      (dense n x n table of the vertex class)
-        const double irho = 1.0 / rho;
-#ifdef GCS_EMULATE
-        const int mv_full = n;
-#else
-        const int mv_full = n & ~31;                  // whole rounds of 32 rows: one lane per row
-#endif
-        GCS_LANE_LOOP(r, mv_full) {
-            // K1^-1 is symmetric: walk column r (= row r) so that the lanes of a warp read consecutive doubles of
-            // row k — coalesced, L1-resident table shared by every vertex of the class
-            const double *kc = Kinv + r;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int k = 0;
-            for (; k + 7 < n; k += 8) {                   // 8 independent table loads in flight per lane
-                const double a0 = kc[(size_t)k * n], a1 = kc[(size_t)(k + 1) * n], a2 = kc[(size_t)(k + 2) * n], a3 = kc[(size_t)(k + 3) * n];
-                const double a4 = kc[(size_t)(k + 4) * n], a5 = kc[(size_t)(k + 5) * n], a6 = kc[(size_t)(k + 6) * n], a7 = kc[(size_t)(k + 7) * n];
-                s0 += a0 * gv[k]; s1 += a1 * gv[k + 1]; s2 += a2 * gv[k + 2]; s3 += a3 * gv[k + 3];
-                s0 += a4 * gv[k + 4]; s1 += a5 * gv[k + 5]; s2 += a6 * gv[k + 6]; s3 += a7 * gv[k + 7];
-            }
-            for (; k < n; ++k) s0 += kc[(size_t)k * n] * gv[k];
-            w[r] = vv[r] - irho * ((s0 + s1) + (s2 + s3));            // w doubles as the new v until every lane has read gv / vv
-        }
-#ifndef GCS_EMULATE
-        if (n > mv_full) {       // the last R < 32 rows: lp = 2^k lanes per row split the columns, partial sums reduced by shuffles
-            const int R = n - mv_full;
-            int lp = 1, lg = 0;
-            while (2 * lp * R <= 32) { lp *= 2; ++lg; }
-            const int grp = lane >> lg, sub = lane & (lp - 1), r = mv_full + (grp < R ? grp : 0);
-            const double *kc = Kinv + r;
-            double s0 = 0.0, s1 = 0.0;
-            int k = sub;
-            for (; k + lp < n; k += 2 * lp) {
-                s0 += kc[(size_t)k * n] * gv[k];
-                s1 += kc[(size_t)(k + lp) * n] * gv[k + lp];
-            }
-            if (k < n) s0 += kc[(size_t)k * n] * gv[k];
-            double sum = s0 + s1;
-            for (int m = 1; m < lp; m <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
-            if (grp < R && sub == 0) w[r] = vv[r] - irho * sum;
-        }
-#endif
-        GCS_SYNC();
-        GCS_LANE_LOOP(r, n) vv[r] = (r == 4) ? 0.0 : w[r];     // the epigraph variable t is unused in this mode
-        GCS_SYNC();
-        gcs_forward(vv, u, d, jstar, prim, term, true, lane);
-        gcs_pair_values(u, pv, d, term, L.npair, lane);
-        // c-step and dual step: item idx < nitems is a (point, flow) pair, item nitems is |z_1 - z_2|
-        const int nitems = term ? 2 * (d + 1) : 4 * (d + 1);
-        auto pair_slot = [&](int idx) {
-            int fam, i, blk;
-            if (term) { fam = 0; i = idx & 1; blk = idx >> 1; } else { fam = idx & 1; i = (idx >> 1) & 1; blk = idx >> 2; }
-            return 3 * gcs_slot(blk, i, fam);
-        };
-        auto norm_item = [&]() {           // block soft-threshold, threshold 1 / sigma
-            const int o = 3 * L.npair;
-            const double r0 = alpha * pv[o] + (1.0 - alpha) * cc[o], r1 = alpha * pv[o + 1] + (1.0 - alpha) * cc[o + 1];
-            const double a0 = r0 + lam[o], a1 = r1 + lam[o + 1], nrm = hypot(a0, a1);
+        GCS_CTA_LOOP(i, nvt) {                                                // path-length item: block soft-threshold, threshold 1 / sigma
+            const int *w = vi + GCS_VI_N * i;
+            if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;
+            const double ms = it ? 1.0 : vd[2 * i + 1];
+            const double sigma = kappa * vd[2 * i] * ms;                      // the threshold of the pass that produced t (rho before its rescale)
+            const double a0 = tnS[2 * i], a1 = tnS[2 * i + 1], nrm = hypot(a0, a1);
             const double sc = nrm > 0.0 ? fmax(0.0, 1.0 - 1.0 / (sigma * nrm)) : 0.0;
-            const double q0 = sc * a0, q1 = sc * a1;
-            lam[o] += r0 - q0; lam[o + 1] += r1 - q1;
-            cc[o] = q0; cc[o + 1] = q1;
-        };
-#ifdef GCS_EMULATE
-        const int full_end = nitems + 1;
-#else
-        const int full_end = (nitems + 1) & ~31;      // whole rounds of 32 items: one lane per item
-#endif
-        GCS_LANE_LOOP(idx, full_end) {
-            if (idx < nitems) {
-                const int o = pair_slot(idx);
-                const double r0 = alpha * pv[o] + (1.0 - alpha) * cc[o], r1 = alpha * pv[o + 1] + (1.0 - alpha) * cc[o + 1],
-                             r2 = alpha * pv[o + 2] + (1.0 - alpha) * cc[o + 2];
-                double q0, q1, q2;
-                gcs_cone_project(S + L.cone, nv, r0 + lam[o], r1 + lam[o + 1], r2 + lam[o + 2], q0, q1, q2);
-                lam[o] += r0 - q0; lam[o + 1] += r1 - q1; lam[o + 2] += r2 - q2;
-                cc[o] = q0; cc[o + 1] = q1; cc[o + 2] = q2;
-            } else norm_item();
+            const double q0 = sc * a0, q1 = sc * a1, l0 = ms * (a0 - q0), l1 = ms * (a1 - q1);
+            tnS[2 * i] = q0 - l0; tnS[2 * i + 1] = q1 - l1;
+            enS[2 * i] = (1.0 - alpha) * q0 + l0; enS[2 * i + 1] = (1.0 - alpha) * q1 + l1;
         }
-#ifndef GCS_EMULATE
-        {   // the last R < 32 items: lp = 2^k lanes per item share the scan of its faces, then reduce (value, code) by shuffles
-            const int R = nitems + 1 - full_end;
-            if (R > 0) {
-                int lp = 1, lg = 0;
-                while (2 * lp * R <= 32) { lp *= 2; ++lg; }
-                const int grp = lane >> lg, sub = lane & (lp - 1), idx = full_end + grp;
-                const bool pair = grp < R && idx < nitems;
-                const int o = pair ? pair_slot(idx) : 0;
-                double r0 = 0.0, r1 = 0.0, r2 = 0.0, c0 = 0.0, c1 = 0.0, c2 = 0.0;
-                if (pair) {
-                    r0 = alpha * pv[o] + (1.0 - alpha) * cc[o]; r1 = alpha * pv[o + 1] + (1.0 - alpha) * cc[o + 1];
-                    r2 = alpha * pv[o + 2] + (1.0 - alpha) * cc[o + 2];
-                    c0 = r0 + lam[o]; c1 = r1 + lam[o + 1]; c2 = r2 + lam[o + 2];
-                }
-                double bd = c0 * c0 + c1 * c1 + c2 * c2;
-                int code = -1;
-                bool inside = true;
-                gcs_cone_scan(S + L.cone, pair ? nv : 0, sub, lp, c0, c1, c2, bd, code, inside);
-                int in_i = inside ? 1 : 0;
-                for (int m = 1; m < lp; m <<= 1) {
-                    const double obd = __shfl_xor_sync(0xffffffffu, bd, m);
-                    const int ocode = __shfl_xor_sync(0xffffffffu, code, m);
-                    in_i &= __shfl_xor_sync(0xffffffffu, in_i, m);
-                    if (obd < bd || (obd == bd && ocode < code)) { bd = obd; code = ocode; }
-                }
-                __syncwarp();
-                if (pair && sub == 0) {
-                    double q0, q1, q2;
-                    gcs_cone_point(S + L.cone, code, in_i != 0, c0, c1, c2, q0, q1, q2);
-                    lam[o] += r0 - q0; lam[o + 1] += r1 - q1; lam[o + 2] += r2 - q2;
-                    cc[o] = q0; cc[o + 1] = q1; cc[o + 2] = q2;
-                }
-                if (grp < R && idx == nitems && sub == 0) norm_item();
+        GCS_CTA_SYNC();
+        // ---- P3: right-hand side of the v-step, in units of rho:  r = S'T - (eps / rho) e_y + kappa M'(d - m0)
+        GCS_CTA_LOOP(q, 5 * nb) {
+            const int b = q / 5, tau = q - 5 * b, info = binfo[b], vl = info & 255, grp = (info >> 8) & 3;
+            if (!vi[GCS_VI_N * vl + GCS_VI_ACTIVE]) continue;
+            const bool term = (info >> 10) & 1;
+            const double *d = tS + 12 * b;                                    // pair (i, fam) at 3 (2 i + fam)
+            double val;
+            if (tau < 4) {
+                const int i = tau >> 1, c = tau & 1;
+                val = d[6 * i + c];
+                if (!term) val -= d[6 * i + 3 + c];
+                val *= kappa;
+                if (grp == 1) val += TS[q];                                    // out-edge: both points carry the rho-quadratic
+                else if (grp == 0) { if (tau < 2) val += TS[q + 2]; }          // in-edge: own first point (edge-canonical slots 2, 3)
+                else val += (i ? -kappa : kappa) * tnS[2 * vl + c];            // (z_v, y_v) block: the path-length item
+            } else {
+                val = d[2] + d[8];
+                if (!term) val += (1.0 - d[5]) + (1.0 - d[11]);
+                val *= kappa;
+                if (grp < 2) val += TS[q] - GCS_EDGE_PENALTY / vd[2 * vl];
+            }
+            rS[q] = val;
+        }
+        GCS_CTA_SYNC();
+        // ---- P4: inputs of the extended core: r_x, r_z, r_yv, sums of r over the in- and the out-blocks
+        GCS_CTA_LOOP(q, GCS_NCX * nvt) {
+            const int vl = q / GCS_NCX, k = q - GCS_NCX * vl;
+            const int *w = vi + GCS_VI_N * vl;
+            if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;
+            const int bl = w[GCS_VI_BLK], zb = bl + w[GCS_VI_NB] - 1;
+            double s = 0.0;
+            if (k < 4) {
+                if (!w[GCS_VI_TERM]) { for (int b = bl; b <= zb; ++b) s += tS[12 * b + 6 * (k >> 1) + 3 + (k & 1)]; s *= kappa; }
+            } else if (k < 9) s = rS[5 * zb + k - 4];
+            else {
+                const int g = k >= 14, tau = k - 9 - 5 * g;
+                for (int b = bl; b < zb; ++b) if (((binfo[b] >> 8) & 3) == g) s += rS[5 * b + tau];
+            }
+            cin[q] = s;
+        }
+        GCS_CTA_SYNC();
+        // ---- P5: extended core  (x, z_v, y_v, beta_in, beta_out) = G (inputs) + g0
+        GCS_CTA_LOOP(q, GCS_NCX * nvt) {
+            const int vl = q / GCS_NCX, k = q - GCS_NCX * vl;
+            const int *w = vi + GCS_VI_N * vl;
+            if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;
+            const double *tab = T.cls_tab + (size_t)GCS_CLS_STRIDE * w[GCS_VI_CLS], *gk = tab + GCS_NCX * k, *in = cin + GCS_NCX * vl;
+            double s0 = tab[GCS_CLS_G0 + k], s1 = 0.0;
+#pragma unroll
+            for (int j = 0; j + 1 < GCS_NCX; j += 2) { s0 += gk[j] * in[j]; s1 += gk[j + 1] * in[j + 1]; }
+            cout[q] = s0 + s1 + gk[GCS_NCX - 1] * in[GCS_NCX - 1];
+        }
+        GCS_CTA_SYNC();
+        // ---- P6: block variables  u = dinv r + beta  (in place of r); vertex outputs on the last pass
+        GCS_CTA_LOOP(q, 5 * nb) {
+            const int b = q / 5, tau = q - 5 * b, info = binfo[b], vl = info & 255, grp = (info >> 8) & 3;
+            const int *w = vi + GCS_VI_N * vl;
+            if (!w[GCS_VI_ACTIVE]) continue;
+            const double *co = cout + GCS_NCX * vl;
+            if (grp == 2) rS[q] = co[4 + tau];
+            else rS[q] = T.cls_tab[(size_t)GCS_CLS_STRIDE * w[GCS_VI_CLS] + GCS_CLS_DINV + 5 * grp + tau] * rS[q] + co[9 + 5 * grp + tau];
+        }
+        if (last) {
+            GCS_CTA_LOOP(q, 9 * nvt) {
+                const int vl = q / 9, k = q - 9 * vl;
+                const int *w = vi + GCS_VI_N * vl;
+                if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;
+                const double val = cout[GCS_NCX * vl + k];
+                const size_t v = (size_t)(v0 + vl);
+                if (k < 4) St.x_v[4 * v + k] = val; else if (k < 8) St.z_v[4 * v + k - 4] = val; else St.y_v[v] = val;
             }
         }
+        GCS_CTA_SYNC();
+        // ---- P7: t-step  t = alpha (M u + m0) + e;  on the last pass the consensus copies xc in edge-canonical order (:492-522)
+        GCS_CTA_LOOP(p, 4 * nb) {
+            const int b = p >> 2, i = (p >> 1) & 1, fam = p & 1, info = binfo[b], vl = info & 255;
+            if (!vi[GCS_VI_N * vl + GCS_VI_ACTIVE] || ((info >> 10) & fam)) continue;
+            const double *ub = rS + 5 * b, *x = cout + GCS_NCX * vl + 2 * i, *e = eS + 3 * p;
+            double p0 = ub[2 * i], p1 = ub[2 * i + 1], p2 = ub[4];
+            if (fam) { p0 = x[0] - p0; p1 = x[1] - p1; p2 = 1.0 - p2; }
+            double *t = tS + 3 * p;
+            t[0] = alpha * p0 + e[0]; t[1] = alpha * p1 + e[1]; t[2] = alpha * p2 + e[2];
+        }
+        GCS_CTA_LOOP(i, nvt) {
+            const int *w = vi + GCS_VI_N * i;
+            if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;
+            const double *zz = cout + GCS_NCX * i + 4;
+            tnS[2 * i] = alpha * (zz[0] - zz[2]) + enS[2 * i]; tnS[2 * i + 1] = alpha * (zz[1] - zz[3]) + enS[2 * i + 1];
+        }
+        if (last) {
+            GCS_CTA_LOOP(q, 5 * nb) {
+                const int b = q / 5, c = q - 5 * b, h = bhe[b], info = binfo[b], vl = info & 255;
+                if (h < 0 || !vi[GCS_VI_N * vl + GCS_VI_ACTIVE]) continue;
+                double x;
+                if ((info >> 8) & 1) x = rS[q];                                 // out-edge: own first point | other's first point == own second point (C5)
+                else x = c < 2 ? TS[q] : (c < 4 ? rS[q - 2] : rS[q]);           // in-edge: other's first point is free -> its target | own first point
+                St.xc[5 * (size_t)h + c] = x;
+            }
+        }
+        GCS_CTA_SYNC();
+    }
+    // ---- P8: the new state goes back with bulk stores
+#if defined(GCS_EMULATE)
+    memcpy(T.tstate + 12 * (size_t)b0, tS, sizeof(double) * 12 * nb);
+    memcpy(T.tn + 2 * (size_t)v0, tnS, sizeof(double) * 2 * nvt);
+    if (!vprob) ctrl_all->inner_iters += (unsigned long long)T.inner_iters * (unsigned long long)nvt;
+#else
+    gcs_fence_async_smem();
+    GCS_CTA_SYNC();
+    if (threadIdx.x == 0) {
+        if (nb) gcs_bulk_s2g(T.tstate + 12 * (size_t)b0, tS, (unsigned)(sizeof(double) * 12 * nb));
+        gcs_bulk_s2g(T.tn + 2 * (size_t)v0, tnS, (unsigned)(sizeof(double) * 2 * nvt));
+        gcs_bulk_commit_wait();
+        if (!vprob) atomicAdd(&ctrl_all->inner_iters, (unsigned long long)T.inner_iters * (unsigned long long)nvt);
+    }
 #endif
-        GCS_SYNC();
-    }
-    GCS_LANE_LOOP(q, np3) { GCS_ST_STREAM(st + q, cc[q]); GCS_ST_STREAM(st + np3 + q, lam[q]); }
-    GCS_LANE_LOOP(j, d) {     // scatter, edge-canonical order (same as the exact kernel)
-        const double *wj = u + gcs_uw(j), *t = tgt + 5 * j;
-        double *x = St.xc + 5 * (size_t)hid[j];
-        if (out[j]) { x[0] = wj[0]; x[1] = wj[1]; x[2] = wj[2]; x[3] = wj[3]; }
-        else        { x[0] = t[0]; x[1] = t[1]; x[2] = wj[0]; x[3] = wj[1]; }
-        x[4] = wj[4];
-    }
-    if (lane == 0) {
-        for (int k = 0; k < 4; ++k) { St.x_v[4 * (size_t)v + k] = u[GCS_UX + k]; St.z_v[4 * (size_t)v + k] = u[GCS_UZ + k]; }
-        St.y_v[v] = u[GCS_UYV];
-    }
-    GCS_SYNC();
-    return 1;
 }

@@ -1,5 +1,6 @@
-"""bench.py for N > 1: the same 100k-vertex grid, vertex-partitioned into strips across N GPUs
-(strong scaling), one process per GPU, halo exchange + 6-double all-reduce over NCCL."""
+"""bench.py for N > 1: the same workload on N GPUs of one box, one process per GPU (strong scaling).
+Grids are vertex-partitioned into strips (halo exchange of the cut half-edges + 6-double all-reduce per iteration);
+a query batch is sharded rank::world with no communication at all (independent problems: replicas only)."""
 from __future__ import annotations
 
 import json
@@ -23,18 +24,29 @@ def main(args):
     os.environ.setdefault("MASTER_PORT", "29511")
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    import bench
     W = max(3, args.warmup)
-    burn = max(W, args.grid + 10 if args.burn_in < 0 else args.burn_in)
-    g = grid_packed_graph(args.grid)
+    if args.workload.startswith("batch"):
+        return batch_main(args, rank, world, local_rank, W)
+    G = bench.WORKLOADS[args.workload]
+    burn = max(W, G + 10 if args.burn_in < 0 else args.burn_in)
+    g = grid_packed_graph(G)
     lp = split_graph(g, partition_vertices(g, world), world)[rank]
-    tables = None
-    if args.mode == "perf" or args.perf_report:
-        from . import perf as perf_mod
-        tables = perf_mod.local_tables(perf_mod.perf_tables(g), lp)
+    from . import perf as perf_mod
+    tables = perf_mod.local_tables(dict(zip(("cone_off", "cone"), perf_mod.cone_table(g)), kappa=1.0), lp)
+    # headline mode: perf only if the parity gate passes in this run (rank 0 runs it on its GPU, everybody follows)
+    flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", local_rank))
+    gate = None
+    if args.mode in ("auto", "perf") and not args.no_gate:
+        if rank == 0:
+            gate = bench.parity_gate()
+            flag[0] = 1 if gate["passed"] else 0
+        dist.broadcast(flag, 0)
+    headline = "perf" if int(flag.item()) == 1 else "parity"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=torch.device("cuda", local_rank))
 
     def measure(mode, inner):
-        """-> (ms per iteration [max over ranks], clocks, e2e seconds [max over ranks])"""
+        """-> (ms per iteration [max over ranks], clocks, e2e seconds [max over ranks], residual history)"""
         pf = dict(inner_iters=inner, tables=tables) if mode == "perf" else None
         be = CudaBackend(lp, local_rank, perf=pf, max_it=max(1000, args.steps + burn + 8), eps_abs=0.0, eps_rel=0.0)
         drv = DistributedADMM(lp, be, graph=args.dist_graph)
@@ -61,6 +73,7 @@ def main(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_max = float(t.item())
         clocks = sampler.finish() if sampler else None
+        hist = be.history()
         drv.release_graph()
         be.close()
         # end to end: local graph upload + K iterations + local solution download, wall clock, max over ranks
@@ -76,18 +89,32 @@ def main(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         drv2.release_graph()
         be2.close()
-        return ms_max / args.steps, clocks, float(t.item())
+        return ms_max / args.steps, clocks, float(t.item()), hist
 
     n_e2e = burn + args.steps
-    per, clocks, e2e = measure(args.mode, args.inner)
-    perf_rep = None
-    if args.mode == "parity" and args.perf_report:
-        perf_rep = {"what": "same partition and timing protocol with the inexact x-update (gcsadmm_enable_perf); see the 1-GPU line / DESIGN.md 5a"}
-        for K in (3, 1):
-            p_ms, p_clk, p_e2e = measure("perf", K)
-            perf_rep[f"K={K}"] = {"value": 1e3 / p_ms, "unit": "it/s", "ms_per_step": p_ms, "e2e": n_e2e / p_e2e, "clocks": p_clk}
+    per, clocks, e2e, hist = measure(headline, args.inner)
+    other_rep = None
+    if not args.no_other_mode:
+        other = "parity" if headline == "perf" else "perf"
+        o_ms, o_clk, o_e2e, _ = measure(other, args.inner)
+        other_rep = {"what": "the other mode on the same partition with the same timing protocol", "mode": bench.MODE_TEXT[other],
+                     "value": 1e3 / o_ms, "unit": "it/s", "ms_per_step": o_ms, "e2e": n_e2e / o_e2e, "clocks": o_clk}
+    check = None
     if rank == 0:
-        import bench
+        # correctness of the partitioned run: the same iterations on ONE GPU (rank 0 replays them) give the same residual history
+        from . import lib
+        s1 = lib.Solver(g, device=local_rank, max_it=max(1000, args.steps + burn + 8), eps_abs=0.0, eps_rel=0.0)
+        if headline == "perf":
+            s1.enable_perf(inner_iters=args.inner, tables=perf_mod.perf_tables(g))
+        s1.step(burn + args.steps)
+        r1, p1, d1 = s1.history()
+        s1.close()
+        n = min(len(p1), len(hist[1]))
+        scale = max(1.0, float(np.max(np.abs(p1[:n]))))
+        check = {"iterations_compared": n - 1, "max_abs_diff_pri": float(np.max(np.abs(p1[:n] - hist[1][:n]))),
+                 "max_abs_diff_dual": float(np.max(np.abs(d1[:n] - hist[2][:n]))), "max_abs_diff_rho": float(np.max(np.abs(r1[:n] - hist[0][:n]))),
+                 "scale": scale, "what": "residual history of the N-GPU run vs a 1-GPU replay of the same iterations on rank 0"}
+    if rank == 0:
         k1b, k2b = bench.algorithmic_bytes(g)
         peaks = {}
         try:
@@ -100,19 +127,92 @@ def main(args):
         out_bytes = 8 * (9 * lp.nV + 5 * lp.nE)
         line = {"metric": bench.METRIC, "value": 1e3 / per, "unit": bench.UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": per, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"grid{args.grid}x{args.grid} 2-D GCS: {g.nV} vertices, {g.nE} directed edges, strips over {world} GPUs",
-                           "mode": bench.MODE_TEXT[args.mode] + (f", K={args.inner}" if args.mode == "perf" else ""), "l2": "flushed (256 MiB) before every timed iteration", "burn_in_iterations": burn,
+                "config": {"workload": f"grid{G}x{G} 2-D GCS: {g.nV} vertices, {g.nE} directed edges, strips over {world} GPUs",
+                           "mode": bench.MODE_TEXT[headline] + (f", K={args.inner}" if headline == "perf" else ""), "l2": "flushed (256 MiB) before every timed iteration", "burn_in_iterations": burn,
                            "halo_half_edges_rank0": int(lp.nH_ghost), "collectives": "all_to_all_single(halo) + all_reduce(8 doubles) per iteration, NCCL",
                            "cuda_graph": bool(args.dist_graph)},
                 "clocks": clocks,
                 "e2e": {"value": n_e2e / e2e, "unit": bench.UNIT, "h2d_bytes_per_step": gs_bytes / n_e2e,
                         "d2h_bytes_per_step": out_bytes / n_e2e, "note": "per rank, from a cold start: local graph upload + (burn_in + K) iterations + solution download; max over ranks"},
-                "gpu_launches": 4 * args.steps,
+                "gpu_launches": 3 * args.steps,
                 "roofline": {"bound": "hbm", "achieved": (k1b + k2b) / world / (per * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": (k1b + k2b) / world / (per * 1e-3) / 1e9 / peak, "traffic": None,
                              "note": "whole iteration, algorithmic bytes per GPU / max-over-ranks time"}}
-        if perf_rep is not None:
-            line["perf_mode"] = perf_rep
+        if gate is not None:
+            line["parity_gate"] = gate
+        if other_rep is not None:
+            line[("parity" if headline == "perf" else "perf") + "_mode"] = other_rep
+        line["consistency_vs_1gpu"] = check
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def batch_main(args, rank, world, local_rank, W):
+    """BASELINE config 4: independent queries sharded rank::world — no data-path collective (replicas only).  A step = one ADMM
+    iteration of every query of the batch; value = batch iterations/s = 1 / (max over ranks of the time per iteration)."""
+    import bench
+    from . import lib
+    g, desc = bench.build_workload(args.workload, rank, world)
+    dev = torch.device("cuda", local_rank)
+    gate, flag = None, torch.zeros(1, dtype=torch.int32, device=dev)
+    if args.mode in ("auto", "perf") and not args.no_gate:
+        if rank == 0:
+            gate = bench.parity_gate()
+            flag[0] = 1 if gate["passed"] else 0
+        dist.broadcast(flag, 0)
+    headline = "perf" if int(flag.item()) == 1 else "parity"
+    burn = max(W, 100 if args.burn_in < 0 else args.burn_in)
+    s = lib.Solver(g, device=local_rank, max_it=max(1000, burn + args.steps + 8), eps_abs=0.0, eps_rel=0.0)
+    if headline == "perf":
+        s.enable_perf(inner_iters=args.inner)
+    s.step(burn)
+    sampler = None
+    if rank == 0:
+        sampler = bench.ClockSampler(local_rank)
+        sampler.start()
+    dist.barrier()
+    tot = 0.0
+    for _ in range(args.steps):
+        s.flush_l2()
+        a, _, _ = s.time_steps(1)
+        tot += a
+    dist.barrier()
+    t = torch.tensor([tot], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    per = float(t.item()) / args.steps
+    clocks = sampler.finish() if sampler else None
+    state = list(s.state()) + (list(s.perf_state()) if headline == "perf" else [])
+    s.close()
+    # end to end on every rank: upload of its share + warm state, K iterations, download; max over ranks
+    dist.barrier()
+    t0 = time.perf_counter()
+    s2 = lib.Solver(g, device=local_rank, max_it=max(1000, state[4] + args.steps + 8), check_every=max(1, min(64, args.steps)), eps_abs=0.0, eps_rel=0.0)
+    if headline == "perf":
+        s2.enable_perf(inner_iters=args.inner)
+    s2.set_state(state[0], state[1], state[2], state[3], state[4])
+    if headline == "perf":
+        s2.set_perf_state(state[5], state[6])
+    s2.run(args.steps)
+    s2.solution()
+    e2e = time.perf_counter() - t0
+    s2.close()
+    t = torch.tensor([e2e], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    nq = torch.tensor([g.prob_voff.shape[0] - 1], dtype=torch.float64, device=dev)
+    dist.all_reduce(nq)
+    if rank == 0:
+        line = {"metric": bench.METRIC, "value": 1e3 / per, "unit": bench.UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": per, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc.split(":")[0] + f", {int(nq.item())} queries sharded rank::world over {world} GPUs, no communication",
+                           "mode": bench.MODE_TEXT[headline] + (f", K={args.inner}" if headline == "perf" else ""), "l2": "flushed (256 MiB) before every timed iteration",
+                           "burn_in_iterations": burn},
+                "problem_iterations_per_second": nq.item() * 1e3 / per, "clocks": clocks,
+                "e2e": {"value": args.steps / float(t.item()), "unit": bench.UNIT, "seconds": float(t.item()),
+                        "note": "per rank: upload of its queries + warm state, K iterations, solution download; max over ranks"},
+                "gpu_launches": 2 * args.steps}
+        if gate is not None:
+            line["parity_gate"] = gate
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()

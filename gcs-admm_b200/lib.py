@@ -21,6 +21,7 @@ EXPORTS = [
     "gcsadmm_sums_device_ptr", "gcsadmm_xc_device_ptr", "gcsadmm_get_history", "gcsadmm_get_solution",
     "gcsadmm_get_state", "gcsadmm_set_state", "gcsadmm_time_steps", "gcsadmm_solve_host",
     "gcsadmm_scratch_bytes", "gcsadmm_flush_l2", "gcsadmm_get_problem_status", "gcsadmm_get_problem_history", "gcsadmm_enable_perf",
+    "gcsadmm_get_perf_state", "gcsadmm_set_perf_state",
 ]
 
 
@@ -38,13 +39,16 @@ class GcsParams(C.Structure):
     _fields_ = [("rho0", C.c_double), ("tau_incr", C.c_double), ("tau_decr", C.c_double), ("nu", C.c_double),
                 ("frac", C.c_double), ("eps_abs", C.c_double), ("eps_rel", C.c_double), ("max_it", C.c_int32),
                 ("inner_tol", C.c_double), ("inner_max_iter", C.c_int32), ("check_every", C.c_int32),
-                ("abs_stop", C.c_int32), ("abs_tol", C.c_double), ("warm_theta", C.c_double), ("zero_tol", C.c_double)]
+                ("abs_stop", C.c_int32), ("abs_tol", C.c_double), ("warm_theta", C.c_double), ("zero_tol", C.c_double),
+                ("outer_alpha", C.c_double), ("use_graph", C.c_int32)]
 
 
 class GcsPerfConfig(C.Structure):
     _fields_ = [("inner_iters", C.c_int32), ("alpha", C.c_double), ("kappa", C.c_double), ("n_classes", C.c_int32),
-                ("vclass", C.c_void_p), ("class_koff", C.c_void_p), ("kinv", C.c_void_p), ("kinv_len", C.c_int64),
-                ("cone_off", C.c_void_p), ("cone", C.c_void_p)]
+                ("vclass", C.c_void_p), ("cls_tab", C.c_void_p), ("cone_off", C.c_void_p), ("cone", C.c_void_p),
+                ("n_blocks", C.c_int32), ("blk_off", C.c_void_p), ("blk_he", C.c_void_p), ("blk_info", C.c_void_p),
+                ("n_tiles", C.c_int32), ("tile_voff", C.c_void_p),
+                ("cap_blocks", C.c_int32), ("cap_verts", C.c_int32), ("cap_cone", C.c_int32)]
 
 
 class GcsStatus(C.Structure):
@@ -94,6 +98,8 @@ def load():
     L.gcsadmm_solve_host.argtypes = [C.POINTER(GcsGraph), C.POINTER(GcsParams), C.c_int, C.c_int, C.POINTER(GcsStatus),
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.gcsadmm_enable_perf.argtypes = [C.c_void_p, C.POINTER(GcsPerfConfig)]
+    L.gcsadmm_get_perf_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gcsadmm_set_perf_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.gcsadmm_scratch_bytes.argtypes = [C.c_int, C.c_int]
     L.gcsadmm_flush_l2.argtypes = [C.c_void_p, C.c_longlong]
     _LIB = L
@@ -106,8 +112,14 @@ class GcsError(RuntimeError):
         self.code = code
 
 
-def _check(rc):
-    if rc < 0:
+GCS_E_DIVERGED = -4
+
+
+def _check(rc, allow_diverged=False):
+    """Negative codes raise, except GCS_E_DIVERGED where the caller asked for it: the reference breaks out of its loop on
+    non-finite iterates (``admm_solver_v3.py:662-664, :679-681``) and still reports / rounds / pickles the last iterates, so
+    ``run`` and ``solve_host`` return normally with ``status['diverged'] = 1`` (the library has copied everything back)."""
+    if rc < 0 and not (allow_diverged and rc == GCS_E_DIVERGED):
         raise GcsError(rc, load().gcsadmm_last_error().decode())
     return rc
 
@@ -173,20 +185,34 @@ class Solver:
         self._h = h
         self.nHall = self._gs.nH_own + self._gs.nH_ghost
 
-    def enable_perf(self, inner_iters=3, alpha=1.6, kappa=1.0, tables=None):
+    def enable_perf(self, inner_iters=1, alpha=1.6, kappa=1.0, tables=None):
         """Switch the x-update to the inexact `perf` mode (K closed-form splitting iterations per ADMM iteration)."""
         from . import perf
         T = tables if tables is not None else perf.perf_tables(self.g, kappa)
-        keep = dict(vclass=np.ascontiguousarray(T["vclass"], np.int32), class_koff=np.ascontiguousarray(T["class_koff"], np.int32),
-                    kinv=np.ascontiguousarray(T["kinv"], np.float64), cone_off=np.ascontiguousarray(T["cone_off"], np.int32),
-                    cone=np.ascontiguousarray(T["cone"], np.float64))
+        i32, f64 = np.int32, np.float64
+        keep = dict(vclass=np.ascontiguousarray(T["vclass"], i32), cls_tab=np.ascontiguousarray(T["cls_tab"], f64),
+                    cone_off=np.ascontiguousarray(T["cone_off"], i32), cone=np.ascontiguousarray(T["cone"], f64),
+                    blk_off=np.ascontiguousarray(T["blk_off"], i32), blk_he=np.ascontiguousarray(T["blk_he"], i32),
+                    blk_info=np.ascontiguousarray(T["blk_info"], i32), tile_voff=np.ascontiguousarray(T["tile_voff"], i32))
         c = GcsPerfConfig()
-        c.inner_iters, c.alpha, c.kappa, c.n_classes = int(inner_iters), float(alpha), float(T["kappa"]), int(keep["class_koff"].shape[0])
-        c.vclass, c.class_koff, c.kinv, c.kinv_len = _ptr(keep["vclass"]), _ptr(keep["class_koff"]), _ptr(keep["kinv"]), int(keep["kinv"].shape[0])
-        c.cone_off, c.cone = _ptr(keep["cone_off"]), _ptr(keep["cone"])
+        c.inner_iters, c.alpha, c.kappa, c.n_classes = int(inner_iters), float(alpha), float(T["kappa"]), len(T["classes"])
+        for k in ("vclass", "cls_tab", "cone_off", "cone", "blk_off", "blk_he", "blk_info", "tile_voff"):
+            setattr(c, k, _ptr(keep[k]))
+        c.n_blocks, c.n_tiles = int(keep["blk_he"].shape[0]), int(keep["tile_voff"].shape[0] - 1)
+        c.cap_blocks, c.cap_verts, c.cap_cone = int(T["caps"]["nb"]), int(T["caps"]["nvt"]), int(T["caps"]["cone"])
         _check(load().gcsadmm_enable_perf(self._h, C.byref(c)))
-        self.perf = dict(inner_iters=int(inner_iters), alpha=float(alpha), kappa=float(T["kappa"]), classes=len(T["classes"]))
+        self.perf = dict(inner_iters=int(inner_iters), alpha=float(alpha), kappa=float(T["kappa"]), classes=len(T["classes"]),
+                         n_blocks=c.n_blocks, n_tiles=c.n_tiles)
         return self
+
+    def perf_state(self):
+        t, tn = np.zeros((self.perf["n_blocks"], 12)), np.zeros((self.g.nV, 2))
+        _check(load().gcsadmm_get_perf_state(self._h, _ptr(t), _ptr(tn)))
+        return t, tn
+
+    def set_perf_state(self, tstate, tn):
+        a, b = np.ascontiguousarray(tstate, np.float64), np.ascontiguousarray(tn, np.float64)
+        _check(load().gcsadmm_set_perf_state(self._h, _ptr(a), _ptr(b)))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -200,7 +226,7 @@ class Solver:
 
     def run(self, max_iters=None):
         st = GcsStatus()
-        _check(load().gcsadmm_run(self._h, int(max_iters or self.params.max_it), C.byref(st)))
+        _check(load().gcsadmm_run(self._h, int(max_iters or self.params.max_it), C.byref(st)), allow_diverged=True)
         return st.as_dict()
 
     def step(self, k=1):
@@ -284,7 +310,7 @@ def solve_host(g, device=0, max_iters=None, **params):
     rho, pri, dual = np.zeros(cap), np.zeros(cap), np.zeros(cap)
     st = GcsStatus()
     _check(L.gcsadmm_solve_host(C.byref(gs), C.byref(p), int(device), int(max_iters or p.max_it), C.byref(st),
-                                _ptr(x_v), _ptr(z_v), _ptr(y_v), _ptr(z_e), _ptr(rho), _ptr(pri), _ptr(dual), cap))
+                                _ptr(x_v), _ptr(z_v), _ptr(y_v), _ptr(z_e), _ptr(rho), _ptr(pri), _ptr(dual), cap), allow_diverged=True)
     n = st.iterations + 1
     return dict(status=st.as_dict(), x_v=x_v, z_v=z_v, y_v=y_v, z_e=z_e, rho_seq=rho[:n].copy(),
                 pri_res_seq=pri[:n].copy(), dual_res_seq=dual[:n].copy())

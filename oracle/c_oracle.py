@@ -46,8 +46,16 @@ def lib():
         L.gcso_cost.restype = C.c_double
         L.gcso_cost.argtypes = [C.c_void_p]
         L.gcso_num_threads.restype = C.c_int
+        L.gcso_set_num_threads.argtypes = [C.c_int]
         _LIB = L
     return _LIB
+
+
+def use_all_cores():
+    """OpenMP threads = host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1); returns the count"""
+    n = os.cpu_count() or 1
+    lib().gcso_set_num_threads(n)
+    return lib().gcso_num_threads()
 
 
 class COracle:

@@ -754,6 +754,13 @@ double gcso_cost(const Oracle *o) { /* GCS_utils.py:184-211 */
     for (int e = 0; e < o->nE; ++e) c += EDGE_PENALTY * o->z[5 * e + 4];
     return c;
 }
+void gcso_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int gcso_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

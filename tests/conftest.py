@@ -19,6 +19,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need a CUDA device: without one they are skipped (plain `pytest` on a CPU box stays green) instead of
+    failing in gcsadmm_create with "no CUDA device"."""
+    gpu_items = [it for it in items if it.get_closest_marker("gpu")]
+    if not gpu_items:
+        return
+    try:
+        from gcs_admm_b200 import lib
+        ndev = lib.load().gcsadmm_device_count()
+    except Exception:
+        ndev = 0
+    if ndev == 0:
+        skip = pytest.mark.skip(reason="no CUDA device (gpu tests run on the B200 box)")
+        for it in gpu_items:
+            it.add_marker(skip)
+
+
 def load_golden(name):
     """Problem + stored reference run from tests/golden/<name>.npz
     (made by tools/export_golden.py from the reference's test_data and pickles)."""
@@ -32,3 +49,17 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+def build_emu():
+    """Compiles gcs-admm_b200/csrc/emulate.cpp (the kernel sources with GCS_EMULATE: test infrastructure only) and returns
+    the path of libgcsemu.so."""
+    import subprocess
+    csrc = os.path.join(ROOT, "gcs-admm_b200", "csrc")
+    so, src = os.path.join(csrc, "libgcsemu.so"), os.path.join(csrc, "emulate.cpp")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        base = ["g++", "-O2", "-fPIC", "-shared", "-o", so, src]
+        if subprocess.call(base[:2] + ["-fopenmp"] + base[2:], stderr=subprocess.DEVNULL) != 0:
+            subprocess.check_call(base)
+    return so

@@ -28,8 +28,13 @@ def test_classic_optimum_matches_reference_pickle(name, tol):
     gold_on = {k for k, y in zip(keys, d["classic_y_v_rounded"]) if y > 0.5}
     gold_len = sum(np.linalg.norm(x[:2] - x[2:]) for x, y in zip(d["classic_x_v_rounded"], d["classic_y_v_rounded"]) if y > 0.5)
     assert abs(r["final_cost"] - gold_len) <= 1e-6 * gold_len
-    # (benchmark3: the stored path visits one more region at zero extra length — the vertex sets differ, the cost does not)
-    assert set(r["path"]) == gold_on or set(r["path"]) < gold_on
+    # same curve; the vertex labels can differ where a stretch lies in several overlapping regions (benchmark2: s-5-0 vs s-2-0,
+    # benchmark3: 4-t vs 4-18-t) — see the tie policy in gcs_admm_b200.rounding.rounding
+    from path_utils import gold_path, hausdorff, polyline
+    gpath, gx, _ = gold_path(As, d, keys, "classic")
+    assert hausdorff(polyline(r["x_v_rounded"], r["path"]), polyline(gx, gpath)) <= 1e-3
+    if name in ("benchmark1", "benchmark4"):
+        assert r["path"] == gpath
     # flows: conservation and bounds
     y_e, y_v = r["y_e_sol"], r["y_v_sol"]
     assert all(-1e-9 <= y <= 1 + 1e-9 for y in y_e.values())

@@ -15,56 +15,108 @@ def _cost(s):
     return float(np.sum(np.linalg.norm(z_v[:, :2] - z_v[:, 2:], axis=1)) + 1e-4 * np.sum(z_e[:, 4]))
 
 
-@pytest.mark.parametrize("name,K,iters,tol", [("benchmark1", 3, 500, 1e-5), ("benchmark2", 3, 3000, 1e-4), ("benchmark4", 3, 6000, 2e-2),
-                                              ("benchmark1", 1, 1500, 1e-5), ("benchmark2", 1, 8000, 1e-4), ("benchmark4", 1, 15000, 2e-2)])
-def test_perf_mode_converges_to_classic_optimum(name, K, iters, tol):
-    from gcs_admm_b200.lib import Solver
+from path_utils import gold_path as _gold_path, hausdorff as _hausdorff, polyline as _polyline  # noqa: E402
+
+
+PERF_GATE = ["test1", "test2", "test3", "test_autogen1", "test_autogen2", "benchmark1", "benchmark2", "benchmark3", "benchmark4"]
+# vertex labels of the rounded path are compared where the optimum curve has ONE labelling; benchmark3's stored v3 and
+# classic results already label the last stretch differently (4-14-t vs 4-18-t: the segment lies in all three regions),
+# so there the gate is the curve itself
+SAME_LABELS = {"benchmark1", "benchmark4"}
+# benchmark3's relaxation is loose (s->8 0.53 / s->6 0.47 and more splits downstream): with the reference's N=5 / M=20 the
+# seeded walk reaches the optimal curve for seeds 1, 3, 4 but not 0 or 2 (the reference's own unseeded run was one lucky
+# draw); the gate searches wider there so that its result does not depend on the seed
+ROUND_KW = {"benchmark3": dict(N=20, M=100)}
+
+
+@pytest.mark.parametrize("name", PERF_GATE)
+def test_perf_mode_parity_gate(name):
+    """The contract of the perf mode (north_star tolerances) under its defined stop rule max(pri, dual) < PERF_ABS_TOL:
+    relaxed cost within 1e-4 relative of the classic optimum; rounded result = the reference's stored one (final cost
+    within 1e-4 relative — measured ~1e-8 —, waypoints within 1e-3 as a curve and at the terminals, vertex path identical)."""
+    from gcs_admm_b200.classic import solve_classic
+    from gcs_admm_b200.solver import solve
     As, bs, n, d, keys = load_golden(name)
-    s = Solver(pack_graph(As, bs), max_it=iters + 10, eps_abs=0.0, eps_rel=0.0).enable_perf(inner_iters=K)
-    s.step(iters)
-    st = s.status()
-    assert not st["diverged"] and np.isfinite(st["pri_res"])
-    assert abs(_cost(s) - float(d["classic_cost"])) <= tol * float(d["classic_cost"])
-    s.close()
+    from gcs_admm_b200.solver import PERF_ABS_TOL
+    res = solve(As, bs, n, mode="perf", seed=0, rounding_kw=ROUND_KW.get(name))
+    assert res["converged"] and not res["diverged"], res["status"]
+    assert max(res["status"]["pri_res"], res["status"]["dual_res"]) < PERF_ABS_TOL
+    ours = solve_classic(As, bs, n, seed=0)                       # Drake-free classic_solver (reference classic_solver.py:47-171)
+    assert ours["status"] == "optimal"
+    assert abs(res["cost"] - ours["cost"]) <= 1e-4 * ours["cost"], (res["cost"], ours["cost"])
+    if "classic_cost" in d.files:
+        assert abs(res["cost"] - float(d["classic_cost"])) <= 1e-4 * float(d["classic_cost"]), (res["cost"], float(d["classic_cost"]))
+    P = _polyline(res["x_v_rounded"], res["path"])
+    if "v3_y_v_rounded" in d.files:
+        for tag in ("v3", "classic"):
+            gpath, gx, gcost = _gold_path(As, d, keys, tag)
+            assert abs(res["final_cost"] - gcost) <= 1e-6 * gcost, (tag, res["final_cost"], gcost)
+            assert _hausdorff(P, _polyline(gx, gpath)) <= 1e-3, tag
+            for v in ("s", "t"):
+                assert np.max(np.abs(np.asarray(res["x_v_rounded"][v]) - gx[v])) <= 1e-3
+            if name in SAME_LABELS:       # elsewhere several labellings describe the optimal curve (equal cost, Hausdorff distance ~1e-6)
+                assert res["path"] == gpath, (tag, res["path"], gpath)
+    else:                                                         # no stored run: our classic solver's rounded result
+        assert abs(res["final_cost"] - ours["final_cost"]) <= 1e-6 * max(1.0, ours["final_cost"])
+        assert _hausdorff(P, _polyline(ours["x_v_rounded"], ours["path"])) <= 1e-3
+    if name == "test2":                                           # the one known answer in the reference (test_data/test2.py:47-52)
+        assert res["path"] == ["s", 0, 1, "t"]
+        assert np.allclose(res["x_v_rounded"][0], [0, 1, 0.95, 0.05], atol=1e-3) and np.allclose(res["x_v_rounded"][1], [0.95, 0.05, 1.9, 1], atol=1e-3)
 
 
-def test_perf_kernel_equals_cpu_emulation():
+@pytest.mark.parametrize("name", ["benchmark1", "benchmark2", "benchmark3", "benchmark4"])
+def test_parity_mode_rounds_gpu_flows_to_the_stored_result(name):
+    """parity mode (the reference's trajectory and stop rule), flows from the GPU: rounding gives the stored v3 result"""
+    from gcs_admm_b200.solver import solve
+    As, bs, n, d, keys = load_golden(name)
+    res = solve(As, bs, n, seed=0, rounding_kw=ROUND_KW.get(name))
+    assert res["iterations"] == int(d["v3_iterations"])
+    gpath, gx, gcost = _gold_path(As, d, keys, "v3")
+    assert abs(res["final_cost"] - gcost) <= 1e-6 * gcost
+    assert _hausdorff(_polyline(res["x_v_rounded"], res["path"]), _polyline(gx, gpath)) <= 1e-3
+    if name in SAME_LABELS:
+        assert res["path"] == gpath
+
+
+@pytest.mark.parametrize("name,K,adapt", [("benchmark4", 3, False), ("benchmark3", 1, True), ("test_autogen2", 2, True)])
+def test_perf_kernel_equals_cpu_emulation(name, K, adapt):
+    """the CUDA kernel against the same source compiled for the host, iterate by iterate — with the rho adaptation on
+    (adapt=True: the lam / mu rescale paths are exercised) and off"""
     import test_perf_mode as T
-    import ctypes as C, os, subprocess
-    so = os.path.join(T.CSRC, "libgcsemu.so")
-    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-o", so, os.path.join(T.CSRC, "emulate.cpp")])
-    lib = C.CDLL(so)
-    lib.gcsemu_vertex_update_perf_all.restype = C.c_int
-    lib.gcsemu_vertex_update_perf_all.argtypes = [C.c_int, C.c_int, T._ip, T._dp, T._dp, T._ip, T._ip, T._bp, T._bp, T._dp, T._dp, T._dp, T._dp, T._dp, T._dp, T._dp,
-                                                  C.c_double, C.c_double, C.c_int, T._ip, T._ip, T._dp, T._ip, T._dp, T._dp, C.c_int, C.c_double, C.c_double]
-    lib.gcsemu_perf_state_stride.restype = C.c_int
     from gcs_admm_b200.lib import Solver
-    g = pack_graph(*load_golden("benchmark4")[:2])
-    a = T.EmuPerfADMM(lib, g, K=3)
-    s = Solver(g, frac=0.0).enable_perf(inner_iters=3)          # frac = 0: no rho adaptation, like the emulation driver
-    for it in range(30):
+    g = pack_graph(*load_golden(name)[:2])
+    a = T.EmuPerfADMM(T.load_emu(), g, K=K, adapt=adapt)
+    s = Solver(g, frac=1.0 if adapt else 0.0, max_it=1000, use_graph=0).enable_perf(inner_iters=K)
+    for it in range(60):
         a.step()
         s.step(1)
         xc, mu, z, rho, k = s.state()
-        assert np.max(np.abs(xc - a.xc)) < 1e-9 and np.max(np.abs(z - a.z)) < 1e-9, it
+        assert rho == a.rho, it
+        assert np.max(np.abs(xc - a.xc)) < 1e-9 and np.max(np.abs(z - a.z)) < 1e-9 and np.max(np.abs(mu - a.ms * a.mu)) < 1e-9, it
+    t, tn = s.perf_state()
+    assert np.max(np.abs(t - a.tstate)) < 1e-9 and np.max(np.abs(tn - a.tn)) < 1e-9
     s.close()
 
 
-def test_perf_mode_rounds_to_the_reference_path():
-    """After convergence the flows of the inexact mode round to the same vertex path as the reference's stored run."""
-    from gcs_admm_b200.graph import build_graph
+def test_perf_state_round_trip_resumes_the_run():
+    """get_state + get_perf_state -> a fresh handle -> the same iterates as the uninterrupted run (checkpoint / resume, and what
+    the end-to-end bench leg uploads)"""
     from gcs_admm_b200.lib import Solver
-    from gcs_admm_b200.rounding import rounding
-    As, bs, n, d, keys = load_golden("benchmark4")
-    V, E, I_in, I_out = build_graph(As, bs)
-    s = Solver(pack_graph(As, bs, V, E), max_it=3010, eps_abs=0.0, eps_rel=0.0).enable_perf(inner_iters=3)
-    s.step(3000)
-    _, _, _, z_e = s.solution()
-    y_e = {e: float(z_e[i, 4]) for i, e in enumerate(E)}
-    cost, x_r, y_r, path = rounding(y_e, V, E, I_out, As, bs, n, rng=0, return_path=True)
-    gold_on = {k for k, y in zip(keys, d["v3_y_v_rounded"]) if y > 0.5}
-    assert set(path) == gold_on
+    g = pack_graph(*load_golden("benchmark4")[:2])
+    s = Solver(g, max_it=1000, frac=0.0).enable_perf(inner_iters=1)
+    s.step(100)
+    xc, mu, z, rho, it = s.state()
+    t, tn = s.perf_state()
+    s.step(50)
+    ref = s.state()
     s.close()
+    s2 = Solver(g, max_it=1000, frac=0.0).enable_perf(inner_iters=1)
+    s2.set_state(xc, mu, z, rho, it)
+    s2.set_perf_state(t, tn)
+    s2.step(50)
+    got = s2.state()
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[2], ref[2]) and got[4] == ref[4]
+    s2.close()
 
 
 def test_grid_fixed_point_equals_our_classic_solver():
@@ -76,9 +128,10 @@ def test_grid_fixed_point_equals_our_classic_solver():
     As, bs = packed_to_dicts(off, A, b)
     ref = solve_classic(As, bs, 2, round_solution=False)
     assert ref["status"] == "optimal"
-    s = Solver(pack_graph(As, bs), max_it=40010, eps_abs=0.0, eps_rel=0.0).enable_perf(inner_iters=1)
-    s.step(40000)
-    assert abs(_cost(s) - ref["cost"]) <= 1e-3 * ref["cost"]
+    s = Solver(pack_graph(As, bs), max_it=400000, abs_stop=1, abs_tol=2e-5, frac=0.0, check_every=64).enable_perf(inner_iters=1)
+    st = s.run()
+    assert st["converged"]
+    assert abs(_cost(s) - ref["cost"]) <= 1e-4 * ref["cost"]
     s.close()
 
 

@@ -67,12 +67,14 @@ def test_write_then_load_roundtrip(tmp_path):
     assert list(A2.keys()) == keys and all(np.array_equal(A2[k], As[k]) and np.array_equal(b2[k], bs[k]) for k in keys)
 
 
-@pytest.mark.parametrize("name", ["benchmark1", "benchmark2", "benchmark4"])
+@pytest.mark.parametrize("name", ["benchmark1", "benchmark2", "benchmark3", "benchmark4"])
 def test_rounding_reproduces_stored_path(name):
     """Flows from the (pinned) oracle -> randomized DFS + convex restriction = the reference's stored rounded
-    solution: same vertex set on the path, waypoints within 1e-3 (north-star tolerance)."""
+    solution: same curve (Hausdorff distance <= 1e-3, the north-star waypoint tolerance), same final cost, and the same
+    vertex labels where the optimal curve has one labelling (benchmark1 through the tie policy, benchmark4)."""
     from c_oracle import COracle
     from gcs_admm_b200.rounding import rounding
+    from path_utils import gold_path, hausdorff, polyline
     As, bs, n, d, keys = load_golden(name)
     V, E, I_in, I_out = build_graph(As, bs)
     g = pack_graph(As, bs, V, E)
@@ -80,16 +82,14 @@ def test_rounding_reproduces_stored_path(name):
     o.run()
     _, _, z = o.state()
     y_e = {e: float(z[i, 4]) for i, e in enumerate(E)}
-    cost, x_r, y_r, path = rounding(y_e, V, E, I_out, As, bs, n, rng=0, return_path=True)
-    gold_on = [k for k, y in zip(keys, d["v3_y_v_rounded"]) if y > 0.5]
-    gold_x = {k: d["v3_x_v_rounded"][i] for i, k in enumerate(keys)}
-    gold_cost = sum(np.linalg.norm(gold_x[k][:2] - gold_x[k][2:]) for k in gold_on)
+    kw = dict(N=20, M=100) if name == "benchmark3" else {}      # loose relaxation: see tests/test_gpu_perf.py ROUND_KW
+    cost, x_r, y_r, path = rounding(y_e, V, E, I_out, As, bs, n, rng=0, return_path=True, **kw)
+    gpath, gold_x, gold_cost = gold_path(As, d, keys, "v3")
     assert path[0] == 's' and path[-1] == 't'
-    assert abs(cost - gold_cost) < 1e-4 * max(1.0, gold_cost)
-    if name != "benchmark1":                       # benchmark1 has an exact left/right tie (two optimal paths)
-        assert set(path) == set(gold_on)
-    else:
-        assert set(path) in ({'s', 0, 1, 2, 't'}, {'s', 0, 3, 2, 't'})
+    assert abs(cost - gold_cost) < 1e-6 * max(1.0, gold_cost)
+    assert hausdorff(polyline(x_r, path), polyline(gold_x, gpath)) <= 1e-3
+    if name in ("benchmark1", "benchmark4"):
+        assert path == gpath
     # waypoints: feasible, continuous, same length as the stored solution.  (Interior waypoints of collinear
     # stretches can slide along the line at equal cost, so they are compared through the length, and point-wise
     # only at the terminals.)

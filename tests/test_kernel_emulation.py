@@ -19,9 +19,8 @@ _bp = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 
 @pytest.fixture(scope="module")
 def emu():
-    so = os.path.join(CSRC, "libgcsemu.so")
-    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-o", so, os.path.join(CSRC, "emulate.cpp")])
-    lib = C.CDLL(so)
+    from conftest import build_emu
+    lib = C.CDLL(build_emu())
     lib.gcsemu_vertex_update_all.restype = C.c_int
     lib.gcsemu_vertex_update_all.argtypes = [C.c_int, C.c_int, _ip, _dp, _dp, _ip, _ip, _bp, _bp, _dp, _dp, _dp, _dp,
                                              _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,

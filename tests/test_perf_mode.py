@@ -21,44 +21,64 @@ _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 _bp = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 
 
-@pytest.fixture(scope="module")
-def emu():
-    so = os.path.join(CSRC, "libgcsemu.so")
-    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-o", so, os.path.join(CSRC, "emulate.cpp")])
-    lib = C.CDLL(so)
+def load_emu():
+    from conftest import build_emu
+    lib = C.CDLL(build_emu())
     lib.gcsemu_vertex_update_perf_all.restype = C.c_int
     lib.gcsemu_vertex_update_perf_all.argtypes = [C.c_int, C.c_int, _ip, _dp, _dp, _ip, _ip, _bp, _bp, _dp, _dp, _dp, _dp, _dp, _dp, _dp,
-                                                  C.c_double, C.c_double, C.c_int, _ip, _ip, _dp, _ip, _dp, _dp, C.c_int, C.c_double, C.c_double]
-    lib.gcsemu_perf_state_stride.restype = C.c_int
+                                                  C.c_double, C.c_double, _ip, _dp, _ip, _dp, _ip, _ip, _ip, _ip, C.c_int,
+                                                  C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_double]
     return lib
 
 
-class EmuPerfADMM:
-    """Outer ADMM (numpy edge / dual / residual arithmetic of the kernels) around the emulated perf K1."""
+@pytest.fixture(scope="module")
+def emu():
+    return load_emu()
 
-    def __init__(self, lib, g, K, kappa=1.0, alpha=1.6):
-        self.lib, self.g, self.K, self.alpha = lib, g, K, alpha
+
+class EmuPerfADMM:
+    """Outer ADMM (numpy edge / dual / residual / rho arithmetic of the kernels) around the emulated perf K1."""
+
+    def __init__(self, lib, g, K, kappa=1.0, alpha=1.6, outer_alpha=1.0, adapt=False, nu=10.0, tau=2.0):
+        self.lib, self.g, self.K, self.alpha, self.oa, self.adapt, self.nu, self.tau = lib, g, K, alpha, outer_alpha, adapt, nu, tau
         self.T = perf.perf_tables(g, kappa)
-        self.dcap = max(1, g.max_live_degree)
-        self.state = np.zeros((g.nV, lib.gcsemu_perf_state_stride(self.dcap)))
+        self.tstate, self.tn = np.zeros((self.T["blk_he"].shape[0], 12)), np.zeros((g.nV, 2))
         self.xc, self.mu, self.z = np.zeros((g.H, 5)), np.zeros((g.H, 5)), np.zeros((g.nE, 5))
         self.x_v, self.z_v, self.y_v = np.zeros((g.nV, 4)), np.zeros((g.nV, 4)), np.zeros(g.nV)
         self.cent = np.ascontiguousarray(g.interior_points())
-        self.rho, self.pri, self.dual = 1.0, [0.0], [0.0]
+        self.rho, self.ms, self.pri, self.dual = 1.0, 1.0, [0.0], [0.0]
 
-    def step(self):
+    def vertex_update(self):
         g, T = self.g, self.T
         self.lib.gcsemu_vertex_update_perf_all(g.nV, g.nE, g.poly_off, g.polyA.reshape(-1), g.polyb, g.he_off, g.he_edge, g.he_flags,
                                                g.vtype, self.cent.reshape(-1), self.xc.reshape(-1), self.mu.reshape(-1), self.z.reshape(-1),
-                                               self.x_v.reshape(-1), self.z_v.reshape(-1), self.y_v, self.rho, 1.0, self.dcap,
-                                               T["vclass"], T["class_koff"], T["kinv"], T["cone_off"], T["cone"].reshape(-1),
-                                               self.state.reshape(-1), self.K, self.alpha, T["kappa"])
-        zn = 0.5 * (self.xc[g.edge_he_tail] + self.xc[g.edge_he_head])
+                                               self.x_v.reshape(-1), self.z_v.reshape(-1), self.y_v, self.rho, self.ms,
+                                               T["vclass"], T["cls_tab"], T["cone_off"], T["cone"].reshape(-1), T["blk_off"], T["blk_he"],
+                                               T["blk_info"], T["tile_voff"], T["tile_voff"].shape[0] - 1, T["caps"]["nb"], T["caps"]["nvt"],
+                                               T["caps"]["cone"], self.tstate.reshape(-1), self.tn.reshape(-1), self.K, self.alpha, T["kappa"])
+
+    def step(self):
+        g = self.g
+        self.vertex_update()
+        xt, xh = self.xc[g.edge_he_tail], self.xc[g.edge_he_head]
+        at, ah = (xt, xh) if self.oa == 1.0 else (self.oa * xt + (1 - self.oa) * self.z, self.oa * xh + (1 - self.oa) * self.z)
+        zn = 0.5 * (at + ah)
         dz = zn - self.z
         self.z = zn
         r = zn[g.he_edge] - self.xc
-        self.mu += r
-        self.pri.append(float(np.sqrt(np.sum(r * r)))); self.dual.append(self.rho * float(np.sqrt(2 * np.sum(dz * dz))))
+        hat = self.xc if self.oa == 1.0 else None
+        if hat is None:
+            hat = np.empty_like(self.xc)
+            hat[g.edge_he_tail] = at; hat[g.edge_he_head] = ah
+        self.mu = self.ms * self.mu + (zn[g.he_edge] - hat)
+        pri, dual = float(np.sqrt(np.sum(r * r))), self.rho * float(np.sqrt(2 * np.sum(dz * dz)))
+        self.pri.append(pri); self.dual.append(dual)
+        self.ms = 1.0
+        if self.adapt:                       # reference rho rule (:703-709) over the whole run; the rescale of mu is deferred like on the device
+            if pri >= self.nu * dual:
+                self.rho *= self.tau; self.ms = 1.0 / self.tau
+            elif dual >= self.nu * pri:
+                self.rho /= self.tau; self.ms = self.tau
 
     def cost(self):
         return float(np.sum(np.linalg.norm(self.z_v[:, :2] - self.z_v[:, 2:], axis=1)) + 1e-4 * np.sum(self.z[:, 4]))
@@ -120,21 +140,57 @@ def test_inexact_admm_converges_to_classic_optimum(emu):
 
 
 def test_local_tables_slice_the_global_ones():
-    """multi-GPU perf mode: a rank's tables are the global class inverses + its own vertices' class ids / cone records"""
-    from gcs_admm_b200 import perf
+    """multi-GPU perf mode: a rank's tables = its own vertices' cone records (sliced from the global table), and blocks /
+    tiles / classes rebuilt for the local half-edge layout with the same class tables as the global graph"""
     from gcs_admm_b200.generator import grid_packed_graph
     from gcs_admm_b200.partition import partition_vertices, split_graph
     g = grid_packed_graph(10)
     T = perf.perf_tables(g)
+    inv = {c: k for k, c in T["classes"].items()}
     seen = 0
     for lp in split_graph(g, partition_vertices(g, 3), 3):
         L = perf.local_tables(T, lp)
-        assert L["kinv"] is T["kinv"] and L["cone_off"][-1] == L["cone"].shape[0] and L["cone_off"].shape[0] == lp.nV + 1
+        linv = {c: k for k, c in L["classes"].items()}
+        assert L["cone_off"][-1] == L["cone"].shape[0] and L["cone_off"].shape[0] == lp.nV + 1
+        assert L["tile_voff"][0] == 0 and L["tile_voff"][-1] == lp.nV and L["blk_off"][-1] == L["blk_he"].shape[0]
         for i, v in enumerate(lp.global_vertices):
-            assert L["vclass"][i] == T["vclass"][v]
+            assert (L["vclass"][i] < 0) == (T["vclass"][v] < 0)
+            if L["vclass"][i] >= 0:
+                assert linv[L["vclass"][i]] == inv[T["vclass"][v]]
+                a, b = L["vclass"][i] * perf.CLS_STRIDE, T["vclass"][v] * perf.CLS_STRIDE
+                assert np.array_equal(L["cls_tab"][a:a + perf.CLS_STRIDE], T["cls_tab"][b:b + perf.CLS_STRIDE])
             assert np.array_equal(L["cone"][L["cone_off"][i]:L["cone_off"][i + 1]], T["cone"][T["cone_off"][v]:T["cone_off"][v + 1]])
+            assert L["blk_off"][i + 1] - L["blk_off"][i] == T["blk_off"][v + 1] - T["blk_off"][v]
         seen += lp.nV
     assert seen == g.nV
+
+
+@pytest.mark.parametrize("key", [(0, 4, 4), (0, 1, 1), (0, 2, 1), (0, 1, 3), (1, 0, 3), (1, 0, 1), (2, 2, 0), (2, 1, 0), (0, 5, 7)])
+@pytest.mark.parametrize("kappa", [1.0, 0.3])
+def test_structured_vstep_equals_dense_solution_operator(key, kappa):
+    """the class tables (G, g0, dinv) the kernel uses reproduce the dense solution operator of the v-step"""
+    T = perf.class_tables(*key, kappa)
+    rng = np.random.default_rng(1)
+    for _ in range(4):
+        r = rng.normal(size=perf.NCORE + 5 * T["d"]); r[perf.UT] = 0.0
+        assert np.max(np.abs(T["Phi"] @ r + T["g0u"] - perf.structured_vstep(T, r))) < 1e-12
+
+
+def test_tiles_respect_their_limits():
+    from gcs_admm_b200.generator import generate_test_2D
+    As, bs, s_pt, t_pt = generate_test_2D(None, -20, 20, 1, 0.9, 60, seed=3)
+    g = pack_graph(As, bs)
+    T = perf.perf_tables(g)
+    tv = T["tile_voff"].astype(np.int64)
+    assert np.all(np.diff(tv) >= 1) and tv[0] == 0 and tv[-1] == g.nV
+    nb = T["blk_off"].astype(np.int64)[tv[1:]] - T["blk_off"].astype(np.int64)[tv[:-1]]
+    single = np.diff(tv) == 1
+    assert np.all((nb <= perf.TILE_BLOCKS) | single) and np.all(np.diff(tv) <= perf.TILE_VERTS)
+    # block list: live half-edges of a vertex in half-edge order, then its (z_v, y_v) block
+    for v in range(g.nV):
+        bl = list(T["blk_he"][T["blk_off"][v]:T["blk_off"][v + 1]])
+        live = [h for h in range(g.he_off[v], g.he_off[v + 1]) if not (g.he_flags[h] & 2)]
+        assert bl == ((live + [-1]) if g.vtype[v] != 3 else [])
 
 
 def test_emulated_perf_mode_reaches_our_classic_optimum_on_a_generated_problem(emu):

@@ -18,32 +18,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import utils  # noqa: E402,F401
-from gcs_admm_b200.graph import convert_pt_to_polytope, pack_batch, pack_graph  # noqa: E402
-from gcs_admm_b200.problem_io import load_test_file  # noqa: E402
-
-
-def make_queries(n, seed=1):
-    As, bs, _ = load_test_file("benchmark4")
-    regions = [k for k in As if not isinstance(k, str)]
-    lo = np.min([np.min(bs[k]) for k in regions]) * 0 - 25.0
-    hi = 25.0
-    rng = np.random.default_rng(seed)
-
-    def sample(k):
-        A, b = As[k], bs[k]
-        while True:
-            p = rng.uniform(lo, hi, size=2)
-            if np.all(A @ p <= b - 1e-3):
-                return p
-    out = []
-    for _ in range(n):
-        a, c = rng.choice(len(regions), size=2, replace=False)
-        s, t = sample(regions[a]), sample(regions[c])
-        Aq, bq = dict(As), dict(bs)
-        Aq["s"], bq["s"] = convert_pt_to_polytope(s)
-        Aq["t"], bq["t"] = convert_pt_to_polytope(t)
-        out.append((Aq, bq))
-    return out
+from gcs_admm_b200.graph import pack_batch, pack_graph  # noqa: E402
+from gcs_admm_b200.queries import make_queries  # noqa: E402
 
 
 def main():
@@ -54,12 +30,13 @@ def main():
     ap.add_argument("--inner", type=int, default=1, help="K of the perf mode")
     ap.add_argument("--eps-rel", type=float, default=1e-3, help="reference stop rule (1e-3); perf mode wants a tighter one")
     ap.add_argument("--eps-abs", type=float, default=1e-4)
+    ap.add_argument("--all-pairs", action="store_true", help="draw (s, t) from any two regions (46 %% of the pairs then have no path); default: same component")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     from gcs_admm_b200 import lib
     t0 = time.perf_counter()
-    qs = make_queries(args.queries)[rank::world]
+    qs = make_queries(args.queries, feasible_only=not args.all_pairs)[rank::world]
     graphs = [pack_graph(A, b) for A, b in qs]
     big = pack_batch(graphs)
     t_build = time.perf_counter() - t0
