@@ -28,6 +28,9 @@ def main(argv=None):
     parser.add_argument("--show_plot", type=str, default=True, help="Whether to display plot.")
     parser.add_argument("--seed", type=int, default=None, help="seed of the rounding walk (reference: unseeded)")
     parser.add_argument("--device", type=int, default=0)
+    parser.add_argument("--mode", type=str, default="parity", choices=["parity", "perf"],
+                        help="parity: exact vertex programs, the reference's trajectory and stop rule; perf: inexact x-update iterated to the shared fixed point")
+    parser.add_argument("--out_dir", type=str, default=None, help="directory of the result pickle (default: benchmark_data/ next to this script)")
     args = parser.parse_args(argv)
 
     print("=======================================================================")
@@ -38,7 +41,7 @@ def main(argv=None):
     sys.path.insert(0, here)
     import utils
     from gcs_admm_b200.problem_io import load_test_file
-    from gcs_admm_b200.solver import solve, MAX_IT
+    from gcs_admm_b200.solver import MAX_IT
     test_data_path = os.path.join(here, "test_data")
     try:
         As, bs, n = load_test_file(args.test_file, test_data_path)
@@ -51,13 +54,18 @@ def main(argv=None):
     print(f"E: {E}")
     from gcs_admm_b200.graph import pack_graph
     g = pack_graph(As, bs, V, E)
-    res = solve(As, bs, n, device=args.device, seed=args.seed, graph=(V, E, I_v_in, I_v_out, g))
+    import gcs_admm_b200.solver as solver_mod
+    res = solver_mod.solve(As, bs, n, device=args.device, seed=args.seed, graph=(V, E, I_v_in, I_v_out, g), mode=args.mode)
     it = res["iterations"]
     # progress lines of the reference loop (:716-718): every 100 iterations, at MAX_IT and at the stop iteration — replayed
     # from the residual history the device kept; a diverged pass breaks before its line is printed (:662-664)
     last_printed = it - 1 if res["diverged"] else it
+    if args.mode == "perf":           # the perf mode iterates to a much tighter residual: fewer progress lines, its own cap
+        MAX_IT, every = solver_mod.PERF_MAX_IT, 10000
+    else:
+        every = 100
     for k in range(1, last_printed + 1):
-        if k % 100 == 0 or k == MAX_IT or (k == it and res["converged"]):
+        if k % every == 0 or k == MAX_IT or (k == it and res["converged"]):
             print(f"it = {k}/{MAX_IT}, pri_res_seq[-1]={res['pri_res_seq'][k]}, dual_res_seq[-1]={res['dual_res_seq'][k]}")
     if res["diverged"]:
         print("BREAKING FOR Divergence")
@@ -77,7 +85,9 @@ def main(argv=None):
     print(f"{y_v_rounded=}\n")
     if args.show_plot == True:  # noqa: E712  (reference semantics)
         utils.visualize_results(As, bs, res["x_v_sol"], res["y_v_sol"], x_v_rounded, y_v_rounded)
-    utils.save_data(os.path.join(here, f"benchmark_data/admm_solver_v3_{args.test_file}.pkl"), As, bs, res["solve_time"],
+    out_dir = args.out_dir or os.path.join(here, "benchmark_data")
+    os.makedirs(out_dir, exist_ok=True)
+    utils.save_data(os.path.join(out_dir, f"admm_solver_v3_{args.test_file}.pkl"), As, bs, res["solve_time"],
                     res["cost"], res["x_v_sol"], res["y_v_sol"], x_v_rounded, y_v_rounded, True, it,
                     np.asarray(res["rho_seq"]), np.asarray(res["pri_res_seq"]), np.asarray(res["dual_res_seq"]))
     return res

@@ -84,3 +84,75 @@ def test_properties_at_full_size():
             assert abs(st["pri_res"] - np.sqrt(np.sum(r * r))) <= 1e-9 * max(1.0, st["pri_res"])
         s.close()
     assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
+
+
+@pytest.mark.parametrize("G,burn", [(100, 110), (316, 326)])
+def test_bench_workload_matches_oracle_per_iteration(G, burn):
+    """The bench configurations themselves (BASELINE config 3 and the metric's 100k-vertex grid), pinned to the oracle: after the
+    bench's burn-in on the GPU the state is injected into the C oracle and both advance two iterations, glued."""
+    from c_oracle import COracle, use_all_cores
+    from gcs_admm_b200.generator import grid_packed_graph
+    from gcs_admm_b200.lib import Solver
+    use_all_cores()
+    g = grid_packed_graph(G)
+    s = Solver(g, max_it=1000, eps_abs=0.0, eps_rel=0.0)
+    s.step(burn)
+    xc, mu, z, rho, it = s.state()
+    assert s.status()["skipped"] < burn * g.nV          # the cold-start wave has passed: vertex programs are real solves now
+    o = COracle(g, max_it=1000, eps_abs=0.0, eps_rel=0.0)
+    o.set_state(xc, mu, z, rho, it)
+    for k in range(2):
+        s.step(1)
+        o.step(1)
+        xg, mg, zg, rho_g, it_g = s.state()
+        xo, mo, zo = o.state()
+        assert np.max(np.abs(xg - xo)) < 1e-4 and np.max(np.abs(zg - zo)) < 1e-4, (G, k)
+        assert rho_g == o.info()["rho"]
+        s.set_state(xo, mo, zo, rho=rho_g, it=it_g)
+    _, p1, d1 = s.history()
+    _, p2, d2 = o.history()
+    assert abs(p1[-1] - p2[-1]) < 1e-4 * max(1.0, p2[-1]) and abs(d1[-1] - d2[-1]) < 1e-4 * max(1.0, d2[-1])
+    assert s.status()["inner_fail"] == 0
+    s.close()
+
+
+def test_divergence_is_a_status_not_an_exception():
+    """reference :662-664 / :679-681: non-finite iterates break the loop, the script still reports and pickles.  Here:
+    run() returns normally with diverged = 1 and the last iterates can be read back."""
+    from gcs_admm_b200.graph import pack_graph
+    from gcs_admm_b200.lib import Solver
+    As, bs, n, d, keys = load_golden("benchmark2")
+    g = pack_graph(As, bs)
+    s = Solver(g)
+    s.step(3)
+    xc, mu, z, rho, it = s.state()
+    mu[0, 0] = np.nan
+    s.set_state(xc, mu, z, rho, it)
+    st = s.run()
+    assert st["diverged"] == 1 and st["converged"] == 0 and st["iterations"] == it + 1
+    x_v, z_v, y_v, z_e = s.solution()
+    r, p, dl = s.history()
+    assert len(p) == it + 2 and not np.isfinite(p[-1])
+    s.close()
+
+
+def test_over_relaxed_consensus_step_vs_numpy():
+    """outer_alpha != 1 (perf-mode option): z and mu use alpha xc + (1 - alpha) z_old, the primal residual the true xc"""
+    from gcs_admm_b200.graph import pack_graph
+    from gcs_admm_b200.lib import Solver
+    g = pack_graph(*load_golden("benchmark4")[:2])
+    rng = np.random.default_rng(2)
+    xc, mu0, z0 = rng.normal(size=(g.H, 5)), rng.normal(size=(g.H, 5)), rng.normal(size=(g.nE, 5))
+    al = 1.7
+    s = Solver(g, outer_alpha=al, frac=0.0)
+    s.set_state(xc, mu0, z0, rho=1.0, it=0)
+    s.edge_update()
+    s.control()
+    xc1, mu1, z1, rho, it = s.state()
+    hat = al * xc + (1 - al) * z0[g.he_edge]
+    z_ref = 0.5 * (hat[g.edge_he_tail] + hat[g.edge_he_head])
+    assert np.allclose(z1, z_ref, rtol=0, atol=1e-15)
+    assert np.allclose(mu1, mu0 + z_ref[g.he_edge] - hat, rtol=0, atol=1e-14)
+    st = s.status()
+    assert abs(st["pri_res"] - np.sqrt(np.sum((z_ref[g.he_edge] - xc) ** 2))) < 1e-12 * st["pri_res"]
+    s.close()

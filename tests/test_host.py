@@ -144,3 +144,46 @@ def test_bench_reference_arm_prints_the_contract_line():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_cli_divergence_landmarks_and_pickle(tmp_path, monkeypatch, capsys):
+    """reference :662-664 then :745-775: after "BREAKING FOR Divergence" the script still prints the cost, rounds and pickles.
+    The GPU loop is replaced by a canned diverged result here (the device side is tests/test_gpu_solve.py)."""
+    import importlib
+    import pickle
+    import gcs_admm_b200.solver as solver_mod
+    cli = importlib.import_module("admm_solver_v3")
+
+    def fake_solve(As, bs, n, **kw):
+        V, E, I_in, I_out, g = kw["graph"]
+        nan = float("nan")
+        return dict(cost=nan, x_v_sol={v: np.zeros(4) for v in V}, y_v_sol={v: nan for v in V}, iterations=7, converged=False, diverged=True,
+                    rho_seq=np.ones(8), pri_res_seq=np.r_[0.0, np.ones(6), nan], dual_res_seq=np.r_[0.0, np.ones(6), nan], solve_time=0.1,
+                    x_v_rounded=None, y_v_rounded=None, final_cost=float("inf"), path=None)
+    monkeypatch.setattr(solver_mod, "solve", fake_solve)
+    cli.main(["--test_file=benchmark1", "--show_plot=False", f"--out_dir={tmp_path}"])
+    out = capsys.readouterr().out
+    assert "BREAKING FOR Divergence" in out and "BREAKING FOR OPT" not in out and "it = 7/1000" not in out
+    assert "Cost before rounding" in out and "POST-ROUNDING" in out
+    d = pickle.load(open(tmp_path / "admm_solver_v3_benchmark1.pkl", "rb"))
+    assert d["iterations"] == 7 and d["ADMM"] is True and len(d["pri_res_seq"]) == 8
+
+
+def test_cli_pickles_max_it_plus_one_when_exhausted(tmp_path, monkeypatch, capsys):
+    """the reference leaves `while it <= MAX_IT` with it = MAX_IT + 1 and pickles that (:733, :775); progress lines every 100 (:716-718)"""
+    import importlib
+    import pickle
+    import gcs_admm_b200.solver as solver_mod
+    cli = importlib.import_module("admm_solver_v3")
+
+    def fake_solve(As, bs, n, **kw):
+        V, E, I_in, I_out, g = kw["graph"]
+        return dict(cost=1.0, x_v_sol={v: np.zeros(4) for v in V}, y_v_sol={v: 0.0 for v in V}, iterations=1000, converged=False, diverged=False,
+                    rho_seq=np.ones(1001), pri_res_seq=np.r_[0.0, np.full(1000, 0.5)], dual_res_seq=np.r_[0.0, np.full(1000, 0.25)], solve_time=0.1,
+                    x_v_rounded={v: np.zeros(4) for v in V}, y_v_rounded={v: 0 for v in V}, final_cost=1.0, path=["s", "t"])
+    monkeypatch.setattr(solver_mod, "solve", fake_solve)
+    cli.main(["--test_file=benchmark1", "--show_plot=False", f"--out_dir={tmp_path}"])
+    out = capsys.readouterr().out
+    assert out.count("it = ") == 10 and "it = 100/1000, pri_res_seq[-1]=0.5, dual_res_seq[-1]=0.25" in out and "it = 1000/1000" in out
+    d = pickle.load(open(tmp_path / "admm_solver_v3_benchmark1.pkl", "rb"))
+    assert d["iterations"] == 1001
