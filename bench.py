@@ -216,7 +216,10 @@ def main():
     ap.add_argument("--inner", type=int, default=1, help="K of the perf mode")
     ap.add_argument("--no-gate", action="store_true", help="skip the parity gate (then --mode auto means parity)")
     ap.add_argument("--no-other-mode", action="store_true", help="do not also time the non-headline mode as a nested report")
-    ap.add_argument("--dist-graph", action="store_true", help="N > 1: replay one captured CUDA graph per ADMM iteration (kernels + NCCL collectives)")
+    ap.add_argument("--dist", type=str, default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer = halos and residual sums as flag-ordered peer-memory stores over NVLink (no collective call in the iteration); "
+                         "nccl = all_to_all_single + all_reduce per iteration")
+    ap.add_argument("--dist-graph", action="store_true", help="N > 1, --dist nccl: replay one captured CUDA graph per ADMM iteration (kernels + NCCL collectives)")
     ap.add_argument("--residual-budget", type=float, default=-1.0,
                     help="seconds allowed for the time-to-residual-1e-4 run (perf mode, cold start); -1: 240 for the metric workload on 1 GPU, else 0")
     ap.add_argument("--outer-alpha", type=float, default=1.0, help="over-relaxation of the consensus step in the time-to-residual run")

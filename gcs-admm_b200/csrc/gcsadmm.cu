@@ -37,6 +37,33 @@ static int set_err(int code, const char *fmt, const char *a = "", const char *b 
         if (e_ != cudaSuccess) return set_err(GCS_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
+// ------------------------------------------------------------------------------------------ peer mode (types)
+// Vertex-partitioned graph, one process per GPU of one NVSwitch box.  Per ADMM iteration k a rank
+//   K1 -> peer_push_kernel: stores the 5 consensus scalars of every cut half-edge straight into the neighbour's ghost
+//         slot (peer pointer over NVLink), system fence, then raises halo_flag[me] = k in the neighbour's block
+//   peer_wait_kernel: spins until every neighbour's flag has reached k
+//   edge_kernel (fuse = 2): its last block stores this rank's 6 partial sums into EVERY rank's block and raises sums_flag[me] = k
+//   peer_control_kernel: waits for all ranks' sums, adds them in rank order (identical on every rank) and applies the control step
+// No NCCL call and no host round trip inside the iteration; the five launches are replayed from one CUDA graph.
+// Ghost slots and the sums inbox are double-buffered by the parity of k, so a fast neighbour's iteration k + 1 never
+// overwrites what iteration k still reads (it cannot reach k + 2 before this rank has raised its k + 1 flags).
+#define GCS_MAX_PEERS 8
+#define GCS_PEER_TIMEOUT_NS 20000000000ull
+struct PeerComm {
+    int halo_flag[GCS_MAX_PEERS];             // written by peer p: its halo of iteration k has landed here
+    int sums_flag[GCS_MAX_PEERS];
+    double sums_in[2][GCS_MAX_PEERS][NSUMS];  // [parity][source rank]
+    int k;                                    // peer iterations completed by this rank
+    int error;                                // a wait timed out
+};
+struct PeerView {
+    int rank, world;
+    unsigned neighbours;                      // bit p: ranks exchanging halos with this one
+    double *xc[GCS_MAX_PEERS];                // every rank's xc buffer (own included)
+    PeerComm *comm[GCS_MAX_PEERS];            // every rank's block
+    int nHown[GCS_MAX_PEERS], nHghost[GCS_MAX_PEERS];
+};
+
 struct GcsHandle {
     int device;
     cudaStream_t stream, own_stream;
@@ -68,9 +95,15 @@ struct GcsHandle {
     GcsPerfLayout PL;
     GcsPerfTables PT;
     long long perf_nblocks;
-    int *p_vclass, *p_cone_off, *p_blk_off, *p_blk_he, *p_blk_info, *p_tile_voff; double *p_cls_tab, *p_cone, *p_tstate, *p_tn;
+    int *p_vclass, *p_cone_off, *p_blk_off, *p_blk_he, *p_blk_edge, *p_blk_info, *p_tile_voff; double *p_cls_tab, *p_cone, *p_tstate, *p_tn;
     // one CUDA graph per chunk of `check_every` iterations (own stream only)
     cudaGraphExec_t graph_exec; int graph_iters;
+    // peer mode (multi-GPU over NVLink peer memory, one process per GPU): see the "peer mode" section
+    int peer_on, rank, world, nsend;
+    PeerView PV; PeerView *PV_dev;        // host copy / device copy (the kernels index it at run time)
+    PeerComm *comm;                       // own block (peers write their flags / partial sums into it)
+    void *ipc_opened[2 * GCS_MAX_PEERS];  // mappings of the other ranks' xc / comm blocks
+    int *send_he, *send_rank, *send_slot;
 };
 
 // ------------------------------------------------------------------------------------------ K1
@@ -94,7 +127,7 @@ vertex_kernel(GcsGraphView G, GcsStateView St, Ctrl *ctrl_all, const int *__rest
 
 // ------------------------------------------------------------------------------------------ K1 (perf mode)
 // one thread block per tile of consecutive vertices (<= 256 (point, flow) pairs); ~25 KB of shared memory per block
-__global__ void __launch_bounds__(GCS_PERF_THREADS, 3)
+__global__ void __launch_bounds__(GCS_PERF_THREADS, 4)
 vertex_perf_kernel(GcsGraphView G, GcsStateView St, GcsPerfTables T, Ctrl *ctrl_all, const int *__restrict__ vprob, GcsPerfLayout L) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) unsigned long long bar;
@@ -118,8 +151,11 @@ __device__ void control_apply(Ctrl *ctrl, const GcsParams &p, long long n_x, lon
     const double pri = sqrt(s[0]);                       // :598  ||A x + B z - c||
     const double dual = rho * sqrt(2.0 * s[1]);          // :602  rho ||A'B dz|| = rho sqrt2 ||dz||
     double rho_new = rho, scale = 1.0;
-    if (pri >= p.nu * dual && it < p.frac * p.max_it) { rho_new = rho * p.tau_incr; scale = 1.0 / p.tau_incr; }        // :703-705
-    else if (dual >= p.nu * pri && it < p.frac * p.max_it) { rho_new = rho * (1.0 / p.tau_decr); scale = p.tau_incr; } // :706-708
+    // adapt_every > 1 (perf-mode option): the balancing test is applied on every adapt_every-th iteration only — per-iteration
+    // balancing over a long window reacts to the noise of nearly converged residuals and can keep rho oscillating
+    const bool may = it < p.frac * p.max_it && (p.adapt_every <= 1 || it % p.adapt_every == 0);
+    if (pri >= p.nu * dual && may) { rho_new = rho * p.tau_incr; scale = 1.0 / p.tau_incr; }        // :703-705
+    else if (dual >= p.nu * pri && may) { rho_new = rho * (1.0 / p.tau_decr); scale = p.tau_incr; } // :706-708
     const double nAx = sqrt(s[2]), nBz = sqrt(2.0 * s[3]), nmu = scale * sqrt(s[4]);
     const double eps_pri = sqrt((double)n_x) * p.eps_abs + p.eps_rel * fmax(nAx, nBz);   // :605-610
     const double eps_dual = sqrt((double)n_mu) * p.eps_abs + p.eps_rel * nmu;            // :613-614
@@ -140,33 +176,33 @@ __device__ void control_apply(Ctrl *ctrl, const GcsParams &p, long long n_x, lon
 // oalpha != 1 (perf mode only) over-relaxes the consensus step: xc is replaced by oalpha xc + (1 - oalpha) z_old in the
 // z- and mu-updates (Boyd et al. 3.4.3); the primal residual keeps the true xc.
 // fuse != 0: the last block to finish reduces the block partials in a fixed order and applies the control step.
-__global__ void __launch_bounds__(EDGE_THREADS)
+__global__ void __launch_bounds__(EDGE_THREADS, 6)
 edge_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *__restrict__ edge_he_head,
             const unsigned char *__restrict__ edge_counted, const double *__restrict__ xc, double *__restrict__ mu,
             double *__restrict__ z, Ctrl *ctrl, double *__restrict__ partials, unsigned int *ticket, int fuse,
-            GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap) {
+            GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap, int nHghost, const PeerView *PVp) {
     if (ctrl->stop && !ctrl->ignore_stop) return;
     const double ms = ctrl->mu_scale, oa = p.outer_alpha, ob = 1.0 - p.outer_alpha;
+    // peer mode: the ghost slots of this iteration's parity (PVp lives in device memory: indexed at run time)
+    const int gpar = fuse == 2 ? ((PVp->comm[PVp->rank]->k + 1) & 1) * nHghost : 0;
     double r2 = 0, dz2 = 0, x2 = 0, z2 = 0, m2 = 0, bad = 0;
-    const long long n = 5ll * nE;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int e = (int)(i / 5), c = (int)(i - 5ll * e);
+    // 40 registers per thread (6 blocks of 256 per SM), each thread with its index loads and then five independent data loads in flight
+    const unsigned n = 5u * (unsigned)nE, stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned e = i / 5u, c = i - 5u * e;
         const int ht = edge_he_tail[e], hh = edge_he_head[e];
-        const double xt = xc[5 * (size_t)ht + c], xh = xc[5 * (size_t)hh + c], zo = z[i];
+        const bool ot = ht < nHown, oh = hh < nHown;
+        const unsigned it_ = 5u * (unsigned)(ot ? ht : ht + gpar) + c, ih_ = 5u * (unsigned)(oh ? hh : hh + gpar) + c;
+        const double xt = xc[it_], xh = xc[ih_], zo = z[i];
+        const double mt = ot ? mu[it_] : 0.0, mh = oh ? mu[ih_] : 0.0;       // issued with the xc loads, not after the arithmetic
         const double w = edge_counted ? (double)edge_counted[e] : 1.0;
         double at = xt, ah = xh;
         if (oa != 1.0) { at = oa * xt + ob * zo; ah = oa * xh + ob * zo; }
         const double zn = 0.5 * (at + ah), dd = zn - zo;
         z[i] = zn;
         dz2 += w * dd * dd; z2 += w * zn * zn;
-        if (ht < nHown) {
-            const double r = zn - xt, mn = ms * mu[5 * (size_t)ht + c] + (zn - at);
-            mu[5 * (size_t)ht + c] = mn; r2 += r * r; x2 += xt * xt; m2 += mn * mn;
-        }
-        if (hh < nHown) {
-            const double r = zn - xh, mn = ms * mu[5 * (size_t)hh + c] + (zn - ah);
-            mu[5 * (size_t)hh + c] = mn; r2 += r * r; x2 += xh * xh; m2 += mn * mn;
-        }
+        if (ot) { const double r = zn - xt, mn = ms * mt + (zn - at); mu[it_] = mn; r2 += r * r; x2 += xt * xt; m2 += mn * mn; }
+        if (oh) { const double r = zn - xh, mn = ms * mh + (zn - ah); mu[ih_] = mn; r2 += r * r; x2 += xh * xh; m2 += mn * mn; }
     }
     if (!isfinite(r2) || !isfinite(dz2) || !isfinite(x2) || !isfinite(z2)) bad = 1.0;
     // block reduction (fixed order: shuffles, then warp partials in shared memory)
@@ -179,6 +215,7 @@ edge_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *
         for (int o = 16; o; o >>= 1) vals[q] += __shfl_xor_sync(0xffffffffu, vals[q], o);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0)
+#pragma unroll
         for (int q = 0; q < 6; ++q) sh[warp][q] = vals[q];
     __syncthreads();
     if (threadIdx.x < 6) {
@@ -198,19 +235,88 @@ edge_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *
     // last block: every block's partials are visible; sum them in an order that does not depend on which block is last
     double acc[6] = {0, 0, 0, 0, 0, 0};
     for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+#pragma unroll
         for (int q = 0; q < 6; ++q) acc[q] += __ldcg(partials + (size_t)b * NSUMS + q);
+#pragma unroll
     for (int q = 0; q < 6; ++q) sh[threadIdx.x][q] = acc[q];
     __syncthreads();
     for (int st = EDGE_THREADS / 2; st > 0; st >>= 1) {
         if (threadIdx.x < st)
+#pragma unroll
             for (int q = 0; q < 6; ++q) sh[threadIdx.x][q] += sh[threadIdx.x + st][q];
         __syncthreads();
     }
     if (threadIdx.x < 6) ctrl->sums[threadIdx.x] = sh[0][threadIdx.x];
     __syncthreads();
+    if (fuse == 2) {       // peer mode: this rank's sums into every rank's inbox, then the flag
+        const int me = PVp->rank, world = PVp->world, k = PVp->comm[me]->k + 1, par = k & 1;
+        if (threadIdx.x < 6)
+            for (int q = 0; q < world; ++q) PVp->comm[q]->sums_in[par][me][threadIdx.x] = sh[0][threadIdx.x];
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < world) { *(volatile int *)&PVp->comm[threadIdx.x]->sums_flag[me] = k; }
+        if (threadIdx.x == 0) *ticket = 0u;
+        return;
+    }
     if (threadIdx.x == 0) {
         *ticket = 0u;
         if (fuse) control_apply(ctrl, p, n_x, n_mu, hist, hist_cap);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ peer mode (kernels)
+__device__ __forceinline__ unsigned long long gcs_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
+// one block: cut half-edges -> the neighbours' ghost slots of this iteration's parity, then the flags
+__global__ void __launch_bounds__(1024)
+peer_push_kernel(const double *__restrict__ xc, const int *__restrict__ send_he, const int *__restrict__ send_rank,
+                 const int *__restrict__ send_slot, int nsend, Ctrl *ctrl, const PeerView *PVp) {
+    if (ctrl->stop && !ctrl->ignore_stop) return;
+    const PeerView &PV = *PVp;
+    const int k = PV.comm[PV.rank]->k + 1, par = k & 1;
+    for (int i = threadIdx.x; i < 5 * nsend; i += blockDim.x) {
+        const int j = i / 5, c = i - 5 * j, q = send_rank[j];
+        PV.xc[q][5 * ((size_t)PV.nHown[q] + (size_t)par * PV.nHghost[q] + send_slot[j]) + c] = xc[5 * (size_t)send_he[j] + c];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < PV.world && ((PV.neighbours >> threadIdx.x) & 1u)) *(volatile int *)&PV.comm[threadIdx.x]->halo_flag[PV.rank] = k;
+}
+// one warp: lane p waits for neighbour p's halo of this iteration
+__global__ void peer_wait_kernel(Ctrl *ctrl, const PeerView *PVp) {
+    if (ctrl->stop && !ctrl->ignore_stop) return;
+    const PeerView &PV = *PVp;
+    PeerComm *me = PV.comm[PV.rank];
+    const int k = me->k + 1, p = threadIdx.x;
+    if (p < PV.world && ((PV.neighbours >> p) & 1u)) {
+        const unsigned long long t0 = gcs_globaltimer();
+        while (*(volatile int *)&me->halo_flag[p] < k)
+            if (gcs_globaltimer() - t0 > GCS_PEER_TIMEOUT_NS) { me->error = 1; break; }
+    }
+    __threadfence_system();
+}
+// one warp: waits for every rank's sums, adds them in rank order, control step, advances the peer iteration counter
+__global__ void peer_control_kernel(Ctrl *ctrl, GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap, const PeerView *PVp) {
+    if (ctrl->stop && !ctrl->ignore_stop) return;
+    const PeerView &PV = *PVp;
+    PeerComm *me = PV.comm[PV.rank];
+    const int k = me->k + 1, par = k & 1, q = threadIdx.x;
+    if (q < PV.world) {
+        const unsigned long long t0 = gcs_globaltimer();
+        while (*(volatile int *)&me->sums_flag[q] < k)
+            if (gcs_globaltimer() - t0 > GCS_PEER_TIMEOUT_NS) { me->error = 1; break; }
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < 6; ++j) {
+            double s = 0.0;
+            for (int r = 0; r < PV.world; ++r) s += *(volatile double *)&me->sums_in[par][r][j];
+            ctrl->sums[j] = s;
+        }
+        if (me->error) { ctrl->diverged = 1; ctrl->stop = 1; }
+        else control_apply(ctrl, p, n_x, n_mu, hist, hist_cap);
+        me->k = k;
     }
 }
 
@@ -294,7 +400,7 @@ extern "C" void gcsadmm_default_params(GcsParams *p) {
     p->rho0 = 1.0; p->tau_incr = 2.0; p->tau_decr = 2.0; p->nu = 10.0; p->frac = 0.1;
     p->eps_abs = 1e-4; p->eps_rel = 1e-3; p->max_it = 1000; p->inner_tol = 1e-8; p->inner_max_iter = 60;
     p->check_every = 8; p->abs_stop = 0; p->abs_tol = 1e-4; p->warm_theta = 1e-3; p->zero_tol = 1e-12;
-    p->outer_alpha = 1.0; p->use_graph = 1;
+    p->outer_alpha = 1.0; p->use_graph = 1; p->adapt_every = 1;
 }
 extern "C" int gcsadmm_scratch_bytes(int max_live_degree, int max_rows) {
     return (int)(gcs_scratch_layout(max_live_degree, max_rows).total * sizeof(double));
@@ -325,9 +431,9 @@ static int reset_ctrl(GcsHandle *h) {
 }
 
 static void free_perf(GcsHandle *h) {
-    void *pp[] = {h->p_vclass, h->p_cone_off, h->p_blk_off, h->p_blk_he, h->p_blk_info, h->p_tile_voff, h->p_cls_tab, h->p_cone, h->p_tstate, h->p_tn};
+    void *pp[] = {h->p_vclass, h->p_cone_off, h->p_blk_off, h->p_blk_he, h->p_blk_edge, h->p_blk_info, h->p_tile_voff, h->p_cls_tab, h->p_cone, h->p_tstate, h->p_tn};
     for (void *q : pp) if (q) cudaFree(q);
-    h->p_vclass = h->p_cone_off = h->p_blk_off = h->p_blk_he = h->p_blk_info = h->p_tile_voff = nullptr;
+    h->p_vclass = h->p_cone_off = h->p_blk_off = h->p_blk_he = h->p_blk_edge = h->p_blk_info = h->p_tile_voff = nullptr;
     h->p_cls_tab = h->p_cone = h->p_tstate = h->p_tn = nullptr;
     h->perf_on = 0;
 }
@@ -347,6 +453,8 @@ extern "C" int gcsadmm_destroy(GcsHandle *h) {
     free(h->he_prob_host);
     if (h->flush_buf) cudaFree(h->flush_buf);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    for (void *m : h->ipc_opened) if (m) cudaIpcCloseMemHandle(m);
+    { void *pp[] = {h->comm, h->send_he, h->send_rank, h->send_slot, h->PV_dev}; for (void *q : pp) if (q) cudaFree(q); }
     if (h->ticket) cudaFree(h->ticket);
     free_perf(h);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -404,7 +512,7 @@ static int create_impl(GcsHandle *h, const GcsGraph *g) {
     h->k1_blocks = (g->nV + h->k1_warps - 1) / h->k1_warps;
     {   // edge kernel: 5 threads per edge, a whole number of waves of resident blocks (8 blocks of 256 threads per SM)
         const long long need = (5ll * g->nE + EDGE_THREADS - 1) / EDGE_THREADS;
-        const long long cap = (long long)prop.multiProcessorCount * 8;
+        const long long cap = (long long)prop.multiProcessorCount * 6 * 4;   // 4 waves of the 6 resident blocks per SM
         h->edge_blocks = (int)(need < 1 ? 1 : (need > cap ? cap : need));
     }
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -417,7 +525,7 @@ static int create_impl(GcsHandle *h, const GcsGraph *g) {
     UP(edge_he_tail, g->edge_he_tail, g->nE); UP(edge_he_head, g->edge_he_head, g->nE);
     UP(vtype, g->vtype, g->nV); UP(cent, g->cent, 2 * (size_t)g->nV);
     if (g->edge_counted) UP(edge_counted, g->edge_counted, g->nE);
-    UP(xc, (const double *)nullptr, 5 * Hall); UP(mu, (const double *)nullptr, 5 * (size_t)g->nH_own); UP(z, (const double *)nullptr, 5 * (size_t)g->nE);
+    UP(xc, (const double *)nullptr, 5 * (Hall + (size_t)g->nH_ghost));      // ghost slots twice: double-buffered in peer mode UP(mu, (const double *)nullptr, 5 * (size_t)g->nH_own); UP(z, (const double *)nullptr, 5 * (size_t)g->nE);
     UP(x_v, (const double *)nullptr, 4 * (size_t)g->nV); UP(z_v, (const double *)nullptr, 4 * (size_t)g->nV); UP(y_v, (const double *)nullptr, g->nV);
     if (h->p.warm_theta > 0.0) UP(ws, (const double *)nullptr, (size_t)g->nV * gcs_ws_stride(h->L));
     UP(partials, (const double *)nullptr, (size_t)h->edge_blocks * NSUMS);
@@ -518,7 +626,7 @@ static int launch_edge(GcsHandle *h, int fuse) {
         return 0;
     }
     edge_kernel<<<h->edge_blocks, EDGE_THREADS, 0, h->stream>>>(h->nE, h->nHown, h->edge_he_tail, h->edge_he_head, h->edge_counted, h->xc, h->mu, h->z, h->ctrl,
-                                                                h->partials, h->ticket, fuse, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap);
+                                                                h->partials, h->ticket, fuse, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, h->nHghost, h->PV_dev);
     return 0;
 }
 static int launch_ctrl(GcsHandle *h) {
@@ -526,7 +634,14 @@ static int launch_ctrl(GcsHandle *h) {
     control_kernel<<<1, 32, 0, h->stream>>>(h->ctrl, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap);
     return 0;
 }
-static void launch_iteration(GcsHandle *h) { launch_k1(h); launch_edge(h, 1); }    // 2 launches per ADMM iteration
+static void launch_iteration(GcsHandle *h) {
+    launch_k1(h);
+    if (!h->peer_on) { launch_edge(h, 1); return; }          // single GPU: 2 launches per ADMM iteration
+    peer_push_kernel<<<1, 1024, 0, h->stream>>>(h->xc, h->send_he, h->send_rank, h->send_slot, h->nsend, h->ctrl, h->PV_dev);
+    peer_wait_kernel<<<1, 32, 0, h->stream>>>(h->ctrl, h->PV_dev);
+    launch_edge(h, 2);
+    peer_control_kernel<<<1, 32, 0, h->stream>>>(h->ctrl, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, h->PV_dev);
+}
 // `iters` iterations as one CUDA graph launch (captured once per chunk length; the kernels read rho / stop from the control block)
 static int launch_chunk(GcsHandle *h, int iters) {
     // only whole chunks of check_every iterations are replayed (a remainder would force a re-instantiation every time)
@@ -707,9 +822,9 @@ extern "C" int gcsadmm_time_steps(GcsHandle *h, int k, float *ms_total, float *m
     CK(cudaEventRecord(h->ev[0], h->stream));
     for (int i = 0; i < k; ++i) {
         if (split) CK(cudaEventRecord(h->ev[1], h->stream));
-        launch_k1(h);
+        if (h->peer_on) launch_iteration(h); else launch_k1(h);
         if (split) CK(cudaEventRecord(h->ev[2], h->stream));
-        launch_edge(h, 1);
+        if (!h->peer_on) launch_edge(h, 1);
         if (split) {
             CK(cudaEventRecord(h->ev[3], h->stream));
             CK(cudaEventSynchronize(h->ev[3]));
@@ -743,6 +858,71 @@ extern "C" int gcsadmm_solve_host(const GcsGraph *g, const GcsParams *p, int dev
     }
     gcsadmm_destroy(h);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------ peer mode (host)
+// Every rank exports two CUDA IPC handles (its xc buffer and its PeerComm block); the host layer gathers them over its own
+// channel (torch.distributed in gcs-admm_b200/dist.py) and hands every rank the full table.
+extern "C" int gcsadmm_peer_export(GcsHandle *h, void *handles128) {
+    if (!h || !handles128) return set_err(GCS_E_INVALID, "null argument%s", "");
+    CK(cudaSetDevice(h->device));
+    if (!h->comm) {
+        CK(cudaMalloc((void **)&h->comm, sizeof(PeerComm)));
+        CK(cudaMemset(h->comm, 0, sizeof(PeerComm)));
+    }
+    cudaIpcMemHandle_t a, b;
+    CK(cudaIpcGetMemHandle(&a, h->xc));
+    CK(cudaIpcGetMemHandle(&b, h->comm));
+    memcpy(handles128, &a, 64); memcpy((char *)handles128 + 64, &b, 64);
+    return 0;
+}
+extern "C" int gcsadmm_peer_connect(GcsHandle *h, int rank, int world, const void *all_handles, const int *peer_nHown, const int *peer_nHghost,
+                                    int nsend, const int *send_he, const int *send_rank, const int *send_slot) {
+    if (!h || !all_handles || !peer_nHown || !peer_nHghost || (nsend && (!send_he || !send_rank || !send_slot))) return set_err(GCS_E_INVALID, "null argument%s", "");
+    if (world < 1 || world > GCS_MAX_PEERS || rank < 0 || rank >= world) return set_err(GCS_E_INVALID, "peer mode supports 1..8 ranks%s", "");
+    if (h->nP > 1) return set_err(GCS_E_INVALID, "batched problems are not vertex-partitioned%s", "");
+    if (!h->comm) return set_err(GCS_E_INVALID, "call gcsadmm_peer_export first%s", "");
+    if (peer_nHown[rank] != h->nHown || peer_nHghost[rank] != h->nHghost) return set_err(GCS_E_INVALID, "peer table disagrees with this rank's sizes%s", "");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    drop_graph(h);
+    PeerView V;
+    memset(&V, 0, sizeof V);
+    V.rank = rank; V.world = world;
+    for (int j = 0; j < nsend; ++j) {
+        const int q = send_rank[j];
+        if (q < 0 || q >= world || q == rank || send_he[j] < 0 || send_he[j] >= h->nHown || send_slot[j] < 0 || send_slot[j] >= peer_nHghost[q])
+            return set_err(GCS_E_INVALID, "bad halo send table%s", "");
+        V.neighbours |= 1u << q;
+    }
+    for (int q = 0; q < world; ++q) {
+        V.nHown[q] = peer_nHown[q]; V.nHghost[q] = peer_nHghost[q];
+        if (q == rank) { V.xc[q] = h->xc; V.comm[q] = h->comm; continue; }
+        cudaIpcMemHandle_t a, b;
+        memcpy(&a, (const char *)all_handles + 128 * q, 64); memcpy(&b, (const char *)all_handles + 128 * q + 64, 64);
+        void *px = nullptr, *pc = nullptr;
+        CK(cudaIpcOpenMemHandle(&px, a, cudaIpcMemLazyEnablePeerAccess));
+        h->ipc_opened[2 * q] = px;
+        CK(cudaIpcOpenMemHandle(&pc, b, cudaIpcMemLazyEnablePeerAccess));
+        h->ipc_opened[2 * q + 1] = pc;
+        V.xc[q] = (double *)px; V.comm[q] = (PeerComm *)pc;
+    }
+    int rc = 0;
+    if (!rc) rc = upload(&h->send_he, send_he, (size_t)nsend);
+    if (!rc) rc = upload(&h->send_rank, send_rank, (size_t)nsend);
+    if (!rc) rc = upload(&h->send_slot, send_slot, (size_t)nsend);
+    if (rc) return rc;
+    if (!h->PV_dev) CK(cudaMalloc((void **)&h->PV_dev, sizeof(PeerView)));
+    CK(cudaMemcpy(h->PV_dev, &V, sizeof(PeerView), cudaMemcpyHostToDevice));
+    h->nsend = nsend; h->rank = rank; h->world = world; h->PV = V; h->peer_on = 1;
+    return 0;
+}
+extern "C" int gcsadmm_peer_error(GcsHandle *h) {
+    if (!h || !h->comm) return 0;
+    int e = 0;
+    cudaSetDevice(h->device);
+    cudaMemcpy(&e, (char *)h->comm + offsetof(PeerComm, error), sizeof(int), cudaMemcpyDeviceToHost);
+    return e;
 }
 
 // Evicts the L2 (126 MB on B200) by overwriting a scratch buffer larger than it, on the handle's stream.
@@ -792,6 +972,14 @@ extern "C" int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *c) {
     if (!rc) rc = upload(&h->p_blk_off, c->blk_off, (size_t)h->nV + 1);
     if (!rc) rc = upload(&h->p_blk_he, c->blk_he, (size_t)c->n_blocks);
     if (!rc) rc = upload(&h->p_blk_info, c->blk_info, (size_t)c->n_blocks);
+    if (!rc) {        // edge of every block's half-edge, so that the kernel's gather has one dependent load less
+        int *be = (int *)malloc(sizeof(int) * (size_t)(c->n_blocks > 0 ? c->n_blocks : 1)), *he = (int *)malloc(sizeof(int) * (size_t)(h->nHown > 0 ? h->nHown : 1));
+        if (!be || !he) { free(be); free(he); free_perf(h); return set_err(GCS_E_NOMEM, "out of host memory%s", ""); }
+        cudaMemcpy(he, h->he_edge, sizeof(int) * (size_t)h->nHown, cudaMemcpyDeviceToHost);
+        for (int b = 0; b < c->n_blocks; ++b) be[b] = c->blk_he[b] >= 0 ? he[c->blk_he[b]] : -1;
+        rc = upload(&h->p_blk_edge, be, (size_t)c->n_blocks);
+        free(be); free(he);
+    }
     if (!rc) rc = upload(&h->p_tile_voff, c->tile_voff, (size_t)c->n_tiles + 1);
     if (!rc) rc = upload(&h->p_tstate, (const double *)nullptr, 12 * (size_t)c->n_blocks);
     if (!rc) rc = upload(&h->p_tn, (const double *)nullptr, 2 * (size_t)h->nV);
@@ -799,7 +987,7 @@ extern "C" int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *c) {
     h->perf_nblocks = c->n_blocks;
     h->PL = gcs_perf_layout(c->cap_blocks, c->cap_verts, c->cap_cone);
     h->PT.vclass = h->p_vclass; h->PT.cls_tab = h->p_cls_tab; h->PT.cone_off = h->p_cone_off; h->PT.cone = h->p_cone;
-    h->PT.blk_off = h->p_blk_off; h->PT.blk_he = h->p_blk_he; h->PT.blk_info = h->p_blk_info; h->PT.tile_voff = h->p_tile_voff;
+    h->PT.blk_off = h->p_blk_off; h->PT.blk_he = h->p_blk_he; h->PT.blk_edge = h->p_blk_edge; h->PT.blk_info = h->p_blk_info; h->PT.tile_voff = h->p_tile_voff;
     h->PT.ntiles = c->n_tiles; h->PT.tstate = h->p_tstate; h->PT.tn = h->p_tn; h->PT.inner_iters = c->inner_iters;
     h->PT.alpha = c->alpha; h->PT.kappa = c->kappa;
     cudaDeviceProp prop;

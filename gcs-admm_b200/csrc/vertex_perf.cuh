@@ -56,6 +56,7 @@ struct GcsPerfTables {
     const double *cone;        // GCS_CONE_REC doubles per polygon vertex (see gcs_cone_project)
     const int *blk_off;        // [nV+1] blocks of vertex v: its live half-edges in half-edge order, then (z_v, y_v)
     const int *blk_he;         // [B] half-edge of the block, -1 for the (z_v, y_v) block
+    const int *blk_edge;       // [B] edge of that half-edge (-1 for the (z_v, y_v) block)
     const int *blk_info;       // [B] bits 0-7: vertex index inside its tile | bits 8-9: group (0 in, 1 out, 2 z-block) | bit 10: 's' / 't'
     const int *tile_voff;      // [ntiles+1]
     int ntiles;
@@ -97,7 +98,7 @@ static inline GcsPerfLayout gcs_perf_layout(int nb_cap, int nvt_cap, int cone_ca
     L.cout = o; o += GCS_NCX * nvt_cap;
     L.vd = o; o += 2 * nvt_cap;
     L.vi = o; o += (GCS_VI_N * nvt_cap + 1) / 2;
-    L.bi = o; o += nb_cap;                   // 2 ints per block
+    L.bi = o; o += nb_cap + (nb_cap + 1) / 2; // 3 ints per block: half-edge, descriptor, edge
     L.total = o + (o & 1);
     return L;
 }
@@ -113,16 +114,23 @@ GCS_DEV void gcs_cone_project(const double *cone, int nv, double c0, double c1, 
     int code = -1;          // -1 apex | 2k ray k | 2k+1 face k
     bool inside = true;
     for (int k = 0; k < nv; ++k) {
-        const double *ck = cone + GCS_CONE_REC * k;
-        const double tau = c0 * ck[0] + c1 * ck[1] + c2;
-        const double dist = ck[2] * c0 + ck[3] * c1 + ck[4] * c2;
+#if defined(GCS_EMULATE)
+        const double *r = cone + GCS_CONE_REC * k;
+        const double vx = r[0], vy = r[1], nx = r[2], ny = r[3], nh = r[4], inv = r[5], a0 = r[6], a1 = r[7], a2 = r[8], b0 = r[9], b1 = r[10], b2 = r[11];
+#else
+        const double2 *r = reinterpret_cast<const double2 *>(cone + GCS_CONE_REC * k);     // records are 96 bytes, 16-byte aligned: 6 LDS.128
+        const double2 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], r4 = r[4], r5 = r[5];
+        const double vx = r0.x, vy = r0.y, nx = r1.x, ny = r1.y, nh = r2.x, inv = r2.y, a0 = r3.x, a1 = r3.y, a2 = r4.x, b0 = r4.y, b1 = r5.x, b2 = r5.y;
+#endif
+        const double tau = c0 * vx + c1 * vy + c2;
+        const double dist = nx * c0 + ny * c1 + nh * c2;
         if (tau > 0.0) {
-            const double red = tau * tau * ck[5];
+            const double red = tau * tau * inv;
             if (red > best) { best = red; code = 2 * k; }
         }
         if (dist > 0.0) {
             inside = false;
-            if (c0 * ck[6] + c1 * ck[7] + c2 * ck[8] >= 0.0 && c0 * ck[9] + c1 * ck[10] + c2 * ck[11] >= 0.0) { best = 1e300; code = 2 * k + 1; }
+            if (c0 * a0 + c1 * a1 + c2 * a2 >= 0.0 && c0 * b0 + c1 * b1 + c2 * b2 >= 0.0) { best = 1e300; code = 2 * k + 1; }
         }
     }
     if (inside) { q0 = c0; q1 = c1; q2 = c2; return; }
@@ -169,6 +177,30 @@ __device__ __forceinline__ void gcs_bulk_commit_wait() {
 __device__ __forceinline__ void gcs_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
+#define GCS_PF 3   // consensus targets a thread keeps in registers between issuing their loads and using them (device build)
+
+// input k of the extended core of vertex vl:  r_x (4) | r_z, r_yv (5) | sum of r over the in-blocks (5) | over the out-blocks (5)
+GCS_DEV double gcs_core_input(const double *tS, const double *rS, const int *binfo, const int *w, int k, double kappa) {
+    const int bl = w[GCS_VI_BLK], zb = bl + w[GCS_VI_NB] - 1;
+    double s = 0.0;
+    if (k < 4) {
+        if (!w[GCS_VI_TERM]) { for (int b = bl; b <= zb; ++b) s += tS[12 * b + 6 * (k >> 1) + 3 + (k & 1)]; s *= kappa; }
+    } else if (k < 9) s = rS[5 * zb + k - 4];
+    else {
+        const int g = k >= 14, tau = k - 9 - 5 * g;
+        for (int b = bl; b < zb; ++b) if (((binfo[b] >> 8) & 3) == g) s += rS[5 * b + tau];
+    }
+    return s;
+}
+// output k of the extended core:  (x, z_v, y_v, beta_in, beta_out)[k] = g0[k] + G[k, :] . in
+GCS_DEV double gcs_core_output(const double *tab, const double *in, int k) {
+    const double *gk = tab + GCS_NCX * k;
+    double s0 = tab[GCS_CLS_G0 + k], s1 = 0.0;
+#pragma unroll
+    for (int j = 0; j + 1 < GCS_NCX; j += 2) { s0 += gk[j] * in[j]; s1 += gk[j + 1] * in[j + 1]; }
+    return s0 + s1 + gk[GCS_NCX - 1] * in[GCS_NCX - 1];
+}
+
 // x-update of one tile of vertices in perf mode.  `bar` is an mbarrier in shared memory (device build only).
 GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const GcsPerfTables &T, const GcsPerfLayout &L,
                            double *S, int tile, Ctrl *ctrl_all, const int *vprob, unsigned long long *bar) {
@@ -178,7 +210,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
     const int h0 = G.he_off[v0], nhe = G.he_off[v0 + nvt] - h0;
     double *tS = S + L.tS, *eS = S + L.eS, *coneS = S + L.cone, *tnS = S + L.tnS, *enS = S + L.enS, *TS = S + L.T, *rS = S + L.r;
     double *cin = S + L.cin, *cout = S + L.cout, *vd = S + L.vd;
-    int *vi = (int *)(S + L.vi), *bhe = (int *)(S + L.bi), *binfo = bhe + L.nb_cap;
+    int *vi = (int *)(S + L.vi), *bhe = (int *)(S + L.bi), *binfo = bhe + L.nb_cap, *bedge = binfo + L.nb_cap;
     // ---- P0: stage the tile: state / cone records by bulk copies, per-vertex and per-block descriptors by plain loads
 #if defined(GCS_EMULATE)
     memcpy(tS, T.tstate + 12 * (size_t)b0, sizeof(double) * 12 * nb);
@@ -210,14 +242,23 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
 #endif
         }
     }
-    GCS_CTA_LOOP(b, nb) { bhe[b] = T.blk_he[b0 + b]; binfo[b] = T.blk_info[b0 + b]; }
+    GCS_CTA_LOOP(b, nb) { bhe[b] = T.blk_he[b0 + b]; binfo[b] = T.blk_info[b0 + b]; bedge[b] = T.blk_edge[b0 + b]; }
     GCS_CTA_SYNC();
-    // ---- P1: consensus targets  T = z_e + mu_h  of the live half-edges; forced-zero half-edges are answered directly
-    GCS_CTA_LOOP(q, 5 * nb) {
-        const int b = q / 5, c = q - 5 * b, h = bhe[b], vl = binfo[b] & 255;
-        if (h < 0 || !vi[GCS_VI_N * vl + GCS_VI_ACTIVE]) continue;
-        TS[q] = St.z[5 * (size_t)G.he_edge[h] + c] + vd[2 * vl + 1] * St.mu[5 * (size_t)h + c];
+    // ---- P1: consensus targets  T = z_e + mu_h  of the live half-edges.  Device build: the gathers are only ISSUED here — the
+    // values stay in registers while the thread does its cone projections and are combined after them, so the DRAM / L2
+    // latency of the gather hides behind the c-step instead of stalling the block; forced-zero half-edges are answered directly
+#if !defined(GCS_EMULATE)
+    double pz[GCS_PF], pm[GCS_PF];
+#pragma unroll
+    for (int j = 0; j < GCS_PF; ++j) {
+        const int q = threadIdx.x + j * blockDim.x;
+        pz[j] = 0.0; pm[j] = 0.0;
+        if (q < 5 * nb) {
+            const int b = q / 5, c = q - 5 * b, h = bhe[b];
+            if (h >= 0 && vi[GCS_VI_N * (binfo[b] & 255) + GCS_VI_ACTIVE]) { pz[j] = St.z[5 * (size_t)bedge[b] + c]; pm[j] = St.mu[5 * (size_t)h + c]; }
+        }
     }
+#endif
     GCS_CTA_LOOP(q, 5 * nhe) {
         const int hl = q / 5, c = q - 5 * hl, h = h0 + hl, f = G.he_flags[h];
         if (!(f & GCS_HE_ZERO)) continue;
@@ -260,6 +301,22 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
             tnS[2 * i] = q0 - l0; tnS[2 * i + 1] = q1 - l1;
             enS[2 * i] = (1.0 - alpha) * q0 + l0; enS[2 * i + 1] = (1.0 - alpha) * q1 + l1;
         }
+        if (it == 0) {        // the targets whose loads were issued in P1
+#if !defined(GCS_EMULATE)
+#pragma unroll
+            for (int j = 0; j < GCS_PF; ++j) {
+                const int q = threadIdx.x + j * blockDim.x;
+                if (q < 5 * nb) TS[q] = pz[j] + vd[2 * (binfo[q / 5] & 255) + 1] * pm[j];
+            }
+            for (int q = threadIdx.x + GCS_PF * blockDim.x; q < 5 * nb; q += blockDim.x) {
+#else
+            for (int q = 0; q < 5 * nb; ++q) {
+#endif
+                const int b = q / 5, c = q - 5 * b, h = bhe[b], vl = binfo[b] & 255;
+                if (h < 0 || !vi[GCS_VI_N * vl + GCS_VI_ACTIVE]) continue;
+                TS[q] = St.z[5 * (size_t)bedge[b] + c] + vd[2 * vl + 1] * St.mu[5 * (size_t)h + c];
+            }
+        }
         GCS_CTA_SYNC();
         // ---- P3: right-hand side of the v-step, in units of rho:  r = S'T - (eps / rho) e_y + kappa M'(d - m0)
         GCS_CTA_LOOP(q, 5 * nb) {
@@ -285,34 +342,26 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
             rS[q] = val;
         }
         GCS_CTA_SYNC();
-        // ---- P4: inputs of the extended core: r_x, r_z, r_yv, sums of r over the in- and the out-blocks
-        GCS_CTA_LOOP(q, GCS_NCX * nvt) {
-            const int vl = q / GCS_NCX, k = q - GCS_NCX * vl;
+        // ---- P4 + P5: extended core of every vertex: its 19 inputs (r_x, r_z, r_yv, sums of r over the in- and the out-blocks),
+        // then (x, z_v, y_v, beta_in, beta_out) = G (inputs) + g0.  Device build: one warp per vertex, lane k owns input and
+        // output k, so the two steps are separated by a warp barrier only
+#if defined(GCS_EMULATE)
+        for (int vl = 0; vl < nvt; ++vl) {
             const int *w = vi + GCS_VI_N * vl;
             if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;
-            const int bl = w[GCS_VI_BLK], zb = bl + w[GCS_VI_NB] - 1;
-            double s = 0.0;
-            if (k < 4) {
-                if (!w[GCS_VI_TERM]) { for (int b = bl; b <= zb; ++b) s += tS[12 * b + 6 * (k >> 1) + 3 + (k & 1)]; s *= kappa; }
-            } else if (k < 9) s = rS[5 * zb + k - 4];
-            else {
-                const int g = k >= 14, tau = k - 9 - 5 * g;
-                for (int b = bl; b < zb; ++b) if (((binfo[b] >> 8) & 3) == g) s += rS[5 * b + tau];
-            }
-            cin[q] = s;
+            for (int k = 0; k < GCS_NCX; ++k) cin[GCS_NCX * vl + k] = gcs_core_input(tS, rS, binfo, w, k, kappa);
+            for (int k = 0; k < GCS_NCX; ++k) cout[GCS_NCX * vl + k] = gcs_core_output(T.cls_tab + (size_t)GCS_CLS_STRIDE * w[GCS_VI_CLS], cin + GCS_NCX * vl, k);
         }
-        GCS_CTA_SYNC();
-        // ---- P5: extended core  (x, z_v, y_v, beta_in, beta_out) = G (inputs) + g0
-        GCS_CTA_LOOP(q, GCS_NCX * nvt) {
-            const int vl = q / GCS_NCX, k = q - GCS_NCX * vl;
+#else
+        for (int vl = threadIdx.x >> 5; vl < nvt; vl += blockDim.x >> 5) {
             const int *w = vi + GCS_VI_N * vl;
-            if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;
-            const double *tab = T.cls_tab + (size_t)GCS_CLS_STRIDE * w[GCS_VI_CLS], *gk = tab + GCS_NCX * k, *in = cin + GCS_NCX * vl;
-            double s0 = tab[GCS_CLS_G0 + k], s1 = 0.0;
-#pragma unroll
-            for (int j = 0; j + 1 < GCS_NCX; j += 2) { s0 += gk[j] * in[j]; s1 += gk[j + 1] * in[j + 1]; }
-            cout[q] = s0 + s1 + gk[GCS_NCX - 1] * in[GCS_NCX - 1];
+            const int k = threadIdx.x & 31;
+            const bool on = w[GCS_VI_ACTIVE] && w[GCS_VI_NB] && k < GCS_NCX;
+            if (on) cin[GCS_NCX * vl + k] = gcs_core_input(tS, rS, binfo, w, k, kappa);
+            __syncwarp();
+            if (on) cout[GCS_NCX * vl + k] = gcs_core_output(T.cls_tab + (size_t)GCS_CLS_STRIDE * w[GCS_VI_CLS], cin + GCS_NCX * vl, k);
         }
+#endif
         GCS_CTA_SYNC();
         // ---- P6: block variables  u = dinv r + beta  (in place of r); vertex outputs on the last pass
         GCS_CTA_LOOP(q, 5 * nb) {

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["CudaBackend", "DistributedADMM"]
+__all__ = ["CudaBackend", "DistributedADMM", "PeerADMM", "peer_send_table"]
 
 
 class _DevArray:
@@ -144,3 +144,65 @@ class DistributedADMM:
             done += k
             st = self.be.status()
         return st
+
+
+def peer_send_table(rank, send_counts, recv_counts_all):
+    """(send_rank, send_slot) of a rank's halo items, in the order of ``LocalProblem.send_idx`` (grouped by destination rank).
+    ``recv_counts_all[q][p]`` = ghost slots rank q keeps for rank p; q's ghost range is ordered by source rank, and inside one
+    source by global half-edge id — the order the source's send list has as well (``partition.split_graph``)."""
+    send_rank, send_slot = [], []
+    for q, n in enumerate(send_counts):
+        base = int(sum(recv_counts_all[q][:rank]))
+        send_rank += [q] * int(n)
+        send_slot += list(range(base, base + int(n)))
+    return np.asarray(send_rank, np.int32), np.asarray(send_slot, np.int32)
+
+
+class PeerADMM:
+    """The partitioned iteration with NO collective call inside it (``gcsadmm_peer_connect``): halos and residual sums travel as
+    peer-memory stores over NVLink, ordered by flags; every rank replays its own CUDA graph.  ``torch.distributed`` is used once,
+    to exchange the CUDA IPC handles and the partition sizes."""
+
+    def __init__(self, lp, device, perf=None, group=None, **params):
+        from . import lib
+        self.lp, self.group = lp, group
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        self.solver = lib.Solver(lp, device=device, **params)
+        if perf is not None:
+            self.solver.enable_perf(inner_iters=perf.get("inner_iters", 1), tables=perf["tables"])
+        mine = torch.from_numpy(self.solver.peer_export()).to(self.device)
+        handles = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(handles, mine, group=group)
+        meta = torch.tensor([int(lp.he_off[-1]), int(lp.nH_ghost)] + [int(x) for x in lp.recv_counts], dtype=torch.int64, device=self.device)
+        metas = [torch.empty_like(meta) for _ in range(world)]
+        dist.all_gather(metas, meta, group=group)
+        metas = [m.cpu().numpy() for m in metas]
+        send_rank, send_slot = peer_send_table(rank, lp.send_counts, [m[2:] for m in metas])
+        self.solver.peer_connect(rank, world, np.stack([h.cpu().numpy() for h in handles]), [m[0] for m in metas], [m[1] for m in metas],
+                                 np.asarray(lp.send_idx, np.int32), send_rank, send_slot)
+        dist.barrier(group=group)                 # nobody iterates before everybody is connected
+
+    def iterate(self, k=1):
+        self.solver.step(k)
+
+    def run(self, max_iters):
+        st = self.solver.run(max_iters)
+        if self.solver.peer_error():
+            raise RuntimeError("peer wait timed out: a rank fell out of step")
+        return st
+
+    def status(self):
+        return self.solver.status()
+
+    def history(self):
+        return self.solver.history()
+
+    def solution(self):
+        return self.solver.solution()
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)            # peers may still be storing into this rank's buffers
+        self.solver.close()

@@ -14,7 +14,7 @@ import torch.distributed as dist
 
 def main(args):
     import utils  # noqa: F401
-    from .dist import CudaBackend, DistributedADMM
+    from .dist import CudaBackend, DistributedADMM, PeerADMM
     from .generator import grid_packed_graph
     from .partition import partition_vertices, split_graph
     rank = int(os.environ.get("RANK", "0"))
@@ -45,49 +45,68 @@ def main(args):
     headline = "perf" if int(flag.item()) == 1 else "parity"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=torch.device("cuda", local_rank))
 
+    use_peer = args.dist == "peer"
+
     def measure(mode, inner):
         """-> (ms per iteration [max over ranks], clocks, e2e seconds [max over ranks], residual history)"""
         pf = dict(inner_iters=inner, tables=tables) if mode == "perf" else None
-        be = CudaBackend(lp, local_rank, perf=pf, max_it=max(1000, args.steps + burn + 8), eps_abs=0.0, eps_rel=0.0)
-        drv = DistributedADMM(lp, be, graph=args.dist_graph)
+        kw = dict(max_it=max(1000, args.steps + burn + 8), eps_abs=0.0, eps_rel=0.0)
+        if use_peer:
+            drv = PeerADMM(lp, local_rank, perf=pf, **kw)
+            be = drv
+        else:
+            be = CudaBackend(lp, local_rank, perf=pf, **kw)
+            drv = DistributedADMM(lp, be, graph=args.dist_graph)
         drv.iterate(burn)
         torch.cuda.synchronize()
-        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
         sampler = None
         if rank == 0:
-            import bench
             sampler = bench.ClockSampler(local_rank)
             sampler.start()
         dist.barrier()
         torch.cuda.synchronize()
-        for i in range(args.steps):
-            flush.zero_()                     # L2 eviction, outside the timed pair
-            ev0[i].record()
-            drv.iterate(1)
-            ev1[i].record()
-        torch.cuda.synchronize()
+        ms = 0.0
+        if use_peer:                          # CUDA events on the library's own stream, L2 flushed before every timed iteration
+            for i in range(args.steps):
+                drv.solver.flush_l2()
+                ms += drv.solver.time_steps(1)[0]
+        else:
+            ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+            ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+            for i in range(args.steps):
+                flush.zero_()                     # L2 eviction, outside the timed pair
+                ev0[i].record()
+                drv.iterate(1)
+                ev1[i].record()
+            torch.cuda.synchronize()
+            ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
         dist.barrier()
-        ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
-        t = torch.tensor([ms], dtype=torch.float64, device=be.device)
+        t = torch.tensor([ms], dtype=torch.float64, device=torch.device("cuda", local_rank))
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_max = float(t.item())
         clocks = sampler.finish() if sampler else None
         hist = be.history()
-        drv.release_graph()
+        if not use_peer:
+            drv.release_graph()
         be.close()
         # end to end: local graph upload + K iterations + local solution download, wall clock, max over ranks
         dist.barrier()
         t0 = time.perf_counter()
-        be2 = CudaBackend(lp, local_rank, perf=pf, max_it=max(1000, n_e2e + 8), eps_abs=0.0, eps_rel=0.0)
-        drv2 = DistributedADMM(lp, be2, graph=args.dist_graph)
+        kw2 = dict(max_it=max(1000, n_e2e + 8), eps_abs=0.0, eps_rel=0.0)
+        if use_peer:
+            drv2 = PeerADMM(lp, local_rank, perf=pf, **kw2)
+            be2 = drv2
+        else:
+            be2 = CudaBackend(lp, local_rank, perf=pf, **kw2)
+            drv2 = DistributedADMM(lp, be2, graph=args.dist_graph)
         drv2.iterate(n_e2e)
         be2.solution()
         be2.history()
         e2e = time.perf_counter() - t0
-        t = torch.tensor([e2e], dtype=torch.float64, device=be2.device)
+        t = torch.tensor([e2e], dtype=torch.float64, device=torch.device("cuda", local_rank))
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        drv2.release_graph()
+        if not use_peer:
+            drv2.release_graph()
         be2.close()
         return ms_max / args.steps, clocks, float(t.item()), hist
 
@@ -129,12 +148,14 @@ def main(args):
                 "ms_per_step": per, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"grid{G}x{G} 2-D GCS: {g.nV} vertices, {g.nE} directed edges, strips over {world} GPUs",
                            "mode": bench.MODE_TEXT[headline] + (f", K={args.inner}" if headline == "perf" else ""), "l2": "flushed (256 MiB) before every timed iteration", "burn_in_iterations": burn,
-                           "halo_half_edges_rank0": int(lp.nH_ghost), "collectives": "all_to_all_single(halo) + all_reduce(8 doubles) per iteration, NCCL",
-                           "cuda_graph": bool(args.dist_graph)},
+                           "halo_half_edges_rank0": int(lp.nH_ghost),
+                           "exchange": ("peer memory: cut half-edges and residual sums stored straight into the neighbours' buffers over NVLink, flag-ordered; "
+                                        "no collective call inside the iteration; one CUDA graph per 8 iterations") if use_peer else
+                                       "all_to_all_single(halo) + all_reduce(8 doubles) per iteration, NCCL" + (", one CUDA graph per iteration" if args.dist_graph else "")},
                 "clocks": clocks,
                 "e2e": {"value": n_e2e / e2e, "unit": bench.UNIT, "h2d_bytes_per_step": gs_bytes / n_e2e,
                         "d2h_bytes_per_step": out_bytes / n_e2e, "note": "per rank, from a cold start: local graph upload + (burn_in + K) iterations + solution download; max over ranks"},
-                "gpu_launches": 3 * args.steps,
+                "gpu_launches": (5 if use_peer else 3) * args.steps,
                 "roofline": {"bound": "hbm", "achieved": (k1b + k2b) / world / (per * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": (k1b + k2b) / world / (per * 1e-3) / 1e9 / peak, "traffic": None,
                              "note": "whole iteration, algorithmic bytes per GPU / max-over-ranks time"}}

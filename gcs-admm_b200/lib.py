@@ -21,7 +21,7 @@ EXPORTS = [
     "gcsadmm_sums_device_ptr", "gcsadmm_xc_device_ptr", "gcsadmm_get_history", "gcsadmm_get_solution",
     "gcsadmm_get_state", "gcsadmm_set_state", "gcsadmm_time_steps", "gcsadmm_solve_host",
     "gcsadmm_scratch_bytes", "gcsadmm_flush_l2", "gcsadmm_get_problem_status", "gcsadmm_get_problem_history", "gcsadmm_enable_perf",
-    "gcsadmm_get_perf_state", "gcsadmm_set_perf_state",
+    "gcsadmm_get_perf_state", "gcsadmm_set_perf_state", "gcsadmm_peer_export", "gcsadmm_peer_connect", "gcsadmm_peer_error",
 ]
 
 
@@ -40,7 +40,7 @@ class GcsParams(C.Structure):
                 ("frac", C.c_double), ("eps_abs", C.c_double), ("eps_rel", C.c_double), ("max_it", C.c_int32),
                 ("inner_tol", C.c_double), ("inner_max_iter", C.c_int32), ("check_every", C.c_int32),
                 ("abs_stop", C.c_int32), ("abs_tol", C.c_double), ("warm_theta", C.c_double), ("zero_tol", C.c_double),
-                ("outer_alpha", C.c_double), ("use_graph", C.c_int32)]
+                ("outer_alpha", C.c_double), ("use_graph", C.c_int32), ("adapt_every", C.c_int32)]
 
 
 class GcsPerfConfig(C.Structure):
@@ -100,6 +100,9 @@ def load():
     L.gcsadmm_enable_perf.argtypes = [C.c_void_p, C.POINTER(GcsPerfConfig)]
     L.gcsadmm_get_perf_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.gcsadmm_set_perf_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gcsadmm_peer_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.gcsadmm_peer_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gcsadmm_peer_error.argtypes = [C.c_void_p]
     L.gcsadmm_scratch_bytes.argtypes = [C.c_int, C.c_int]
     L.gcsadmm_flush_l2.argtypes = [C.c_void_p, C.c_longlong]
     _LIB = L
@@ -288,6 +291,20 @@ class Solver:
     def set_state(self, xc=None, mu=None, z=None, rho=1.0, it=0):
         a = [None if x is None else np.ascontiguousarray(x, np.float64) for x in (xc, mu, z)]
         _check(load().gcsadmm_set_state(self._h, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), float(rho), int(it)))
+
+    def peer_export(self):
+        """128 bytes: the CUDA IPC handles of this rank's xc buffer and flag / inbox block (to be all-gathered by the caller)"""
+        buf = np.zeros(128, dtype=np.uint8)
+        _check(load().gcsadmm_peer_export(self._h, _ptr(buf)))
+        return buf
+
+    def peer_connect(self, rank, world, all_handles, nHown, nHghost, send_he, send_rank, send_slot):
+        a = np.ascontiguousarray(all_handles, np.uint8)
+        i = [np.ascontiguousarray(x, np.int32) for x in (nHown, nHghost, send_he, send_rank, send_slot)]
+        _check(load().gcsadmm_peer_connect(self._h, int(rank), int(world), _ptr(a), _ptr(i[0]), _ptr(i[1]), int(i[2].shape[0]), _ptr(i[2]), _ptr(i[3]), _ptr(i[4])))
+
+    def peer_error(self):
+        return int(load().gcsadmm_peer_error(self._h))
 
     def flush_l2(self, nbytes=0):
         _check(load().gcsadmm_flush_l2(self._h, int(nbytes)))

@@ -95,6 +95,7 @@ typedef struct GcsParams {       /* literals of admm_solver_v3.py:621-651 */
     double outer_alpha;          /* over-relaxation of the consensus step (1 = the reference's plain ADMM; 1.5-1.8 is the usual
                                     accelerated choice, Boyd et al. 3.4.3) — perf-mode runs only, the parity mode keeps 1 */
     int32_t use_graph;           /* 1: gcsadmm_run replays one CUDA graph per chunk of check_every iterations (own stream only) */
+    int32_t adapt_every;         /* 1 = the reference's per-iteration rho test (:703-709); N > 1: tested on every N-th iteration only */
 } GcsParams;
 
 typedef struct GcsStatus {
@@ -176,6 +177,21 @@ int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *cfg);
  * path-length item): with gcsadmm_get_state / _set_state a run can be checkpointed and resumed from host buffers */
 int gcsadmm_get_perf_state(GcsHandle *h, double *tstate, double *tn);
 int gcsadmm_set_perf_state(GcsHandle *h, const double *tstate, const double *tn);
+
+/* Multi-GPU over NVLink peer memory (one process per GPU of one box; the graph vertex-partitioned by the host layer, ghost
+ * slots as in GcsGraph.nH_ghost).  After connecting, gcsadmm_step / gcsadmm_run execute the partitioned iteration with no
+ * collective library call inside it: cut half-edges are stored straight into the neighbours' ghost slots, the 6 residual
+ * sums straight into every rank's inbox, flags in peer memory order the steps (gcsadmm.cu "peer mode").  Every rank must run
+ * the same number of iterations.
+ *   gcsadmm_peer_export: writes 128 bytes (two CUDA IPC handles: the xc buffer, the flag / inbox block) for the caller to
+ *                        all-gather over its own channel;
+ *   gcsadmm_peer_connect: all_handles = the gathered [world][128] table; peer_nHown / peer_nHghost = every rank's sizes;
+ *                        send_he[j] = own half-edge j-th item of the halo, send_rank[j] = destination rank, send_slot[j] = index
+ *                        of its ghost slot at the destination (0-based inside the destination's ghost range). */
+int gcsadmm_peer_export(GcsHandle *h, void *handles128);
+int gcsadmm_peer_connect(GcsHandle *h, int rank, int world, const void *all_handles, const int32_t *peer_nHown, const int32_t *peer_nHghost,
+                         int nsend, const int32_t *send_he, const int32_t *send_rank, const int32_t *send_slot);
+int gcsadmm_peer_error(GcsHandle *h);                           /* 1 if a peer wait timed out (a rank fell out of step) */
 
 /* bytes of shared memory one vertex program needs (diagnostics) */
 int gcsadmm_scratch_bytes(int max_live_degree, int max_rows);

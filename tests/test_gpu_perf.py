@@ -40,7 +40,7 @@ def test_perf_mode_parity_gate(name):
     from gcs_admm_b200.solver import PERF_ABS_TOL
     res = solve(As, bs, n, mode="perf", seed=0, rounding_kw=ROUND_KW.get(name))
     assert res["converged"] and not res["diverged"], res["status"]
-    assert max(res["status"]["pri_res"], res["status"]["dual_res"]) < PERF_ABS_TOL
+    assert max(res["status"]["pri_res"], res["status"]["dual_res"]) < PERF_ABS_TOL      # (scaled down for problems shorter than 3: solver.perf_abs_tol)
     ours = solve_classic(As, bs, n, seed=0)                       # Drake-free classic_solver (reference classic_solver.py:47-171)
     assert ours["status"] == "optimal"
     assert abs(res["cost"] - ours["cost"]) <= 1e-4 * ours["cost"], (res["cost"], ours["cost"])

@@ -117,3 +117,24 @@ def test_two_ranks_over_gloo(tmp_path):
         assert int(d["it"]) == its
         assert np.array_equal(d["z"], z[d["ge"]])
         assert np.allclose(d["pri"], pri, rtol=1e-12, atol=0)
+
+
+def test_peer_send_table_matches_the_ghost_order():
+    """peer mode: slot j of what rank r sends to rank q is the ghost slot q keeps for that half-edge"""
+    from gcs_admm_b200.dist import peer_send_table
+    from gcs_admm_b200.generator import grid_packed_graph
+    from gcs_admm_b200.partition import partition_vertices, split_graph
+    g = grid_packed_graph(12)
+    for R in (2, 3, 4):
+        lps = split_graph(g, partition_vertices(g, R), R)
+        rc = [lp.recv_counts for lp in lps]
+        for q, lq in enumerate(lps):
+            nH = int(lq.he_off[-1])
+            ghost_gid = -np.ones(lq.nH_ghost, dtype=np.int64)
+            for arr, garr in ((lq.edge_he_tail, g.edge_he_tail), (lq.edge_he_head, g.edge_he_head)):
+                m = arr >= nH
+                ghost_gid[arr[m] - nH] = garr[lq.global_edges[m]]
+            for r, lp in enumerate(lps):
+                sr, ss = peer_send_table(r, lp.send_counts, rc)
+                sel = sr == q
+                assert np.array_equal(ghost_gid[ss[sel]], lp.global_he[lp.send_idx][sel])

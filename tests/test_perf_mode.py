@@ -26,7 +26,7 @@ def load_emu():
     lib = C.CDLL(build_emu())
     lib.gcsemu_vertex_update_perf_all.restype = C.c_int
     lib.gcsemu_vertex_update_perf_all.argtypes = [C.c_int, C.c_int, _ip, _dp, _dp, _ip, _ip, _bp, _bp, _dp, _dp, _dp, _dp, _dp, _dp, _dp,
-                                                  C.c_double, C.c_double, _ip, _dp, _ip, _dp, _ip, _ip, _ip, _ip, C.c_int,
+                                                  C.c_double, C.c_double, _ip, _dp, _ip, _dp, _ip, _ip, _ip, _ip, _ip, C.c_int,
                                                   C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_double]
     return lib
 
@@ -43,6 +43,7 @@ class EmuPerfADMM:
         self.lib, self.g, self.K, self.alpha, self.oa, self.adapt, self.nu, self.tau = lib, g, K, alpha, outer_alpha, adapt, nu, tau
         self.T = perf.perf_tables(g, kappa)
         self.tstate, self.tn = np.zeros((self.T["blk_he"].shape[0], 12)), np.zeros((g.nV, 2))
+        self.blk_edge = np.where(self.T["blk_he"] >= 0, g.he_edge[np.maximum(self.T["blk_he"], 0)], -1).astype(np.int32)
         self.xc, self.mu, self.z = np.zeros((g.H, 5)), np.zeros((g.H, 5)), np.zeros((g.nE, 5))
         self.x_v, self.z_v, self.y_v = np.zeros((g.nV, 4)), np.zeros((g.nV, 4)), np.zeros(g.nV)
         self.cent = np.ascontiguousarray(g.interior_points())
@@ -54,7 +55,7 @@ class EmuPerfADMM:
                                                g.vtype, self.cent.reshape(-1), self.xc.reshape(-1), self.mu.reshape(-1), self.z.reshape(-1),
                                                self.x_v.reshape(-1), self.z_v.reshape(-1), self.y_v, self.rho, self.ms,
                                                T["vclass"], T["cls_tab"], T["cone_off"], T["cone"].reshape(-1), T["blk_off"], T["blk_he"],
-                                               T["blk_info"], T["tile_voff"], T["tile_voff"].shape[0] - 1, T["caps"]["nb"], T["caps"]["nvt"],
+                                               self.blk_edge, T["blk_info"], T["tile_voff"], T["tile_voff"].shape[0] - 1, T["caps"]["nb"], T["caps"]["nvt"],
                                                T["caps"]["cone"], self.tstate.reshape(-1), self.tn.reshape(-1), self.K, self.alpha, T["kappa"])
 
     def step(self):

@@ -1,30 +1,42 @@
 """BASELINE metric "time to residual 1e-4": perf mode from a cold start until max(pri, dual) < tol, with a trace.
-usage: time_to_residual.py G tol max_iters K [adapt_window_iters]"""
-import sys, os, time, json
+usage: time_to_residual.py --grid G [--tol 1e-4] [--max-iters N] [--inner K] [--window W] [--adapt-every A] [--outer-alpha a] [--rho0 r] [--nu v] [--tau t]"""
+import argparse, sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import utils  # noqa
 import numpy as np
 from gcs_admm_b200.generator import grid_packed_graph
 from gcs_admm_b200 import lib, perf
 
-G, tol, max_iters, K = int(sys.argv[1]), float(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
-window = int(sys.argv[5]) if len(sys.argv) > 5 else max_iters
-g = grid_packed_graph(G)
+ap = argparse.ArgumentParser()
+ap.add_argument("--grid", type=int, default=100)
+ap.add_argument("--tol", type=float, default=1e-4)
+ap.add_argument("--max-iters", type=int, default=400000)
+ap.add_argument("--inner", type=int, default=1)
+ap.add_argument("--window", type=int, default=100, help="rho adapts while it < window (reference: 0.1 * MAX_IT = 100)")
+ap.add_argument("--adapt-every", type=int, default=1)
+ap.add_argument("--outer-alpha", type=float, default=1.0)
+ap.add_argument("--rho0", type=float, default=1.0)
+ap.add_argument("--nu", type=float, default=10.0)
+ap.add_argument("--tau", type=float, default=2.0)
+ap.add_argument("--trace", type=int, default=20, help="trace points")
+ap.add_argument("--budget", type=float, default=1e9, help="seconds")
+a = ap.parse_args()
+g = grid_packed_graph(a.grid)
 T = perf.perf_tables(g)
 # rho adapts while it < frac * max_it (reference rule :703): the window is a parameter of the reference's algorithm
-s = lib.Solver(g, max_it=max_iters + 8, frac=window / (max_iters + 8), abs_stop=1, abs_tol=tol, check_every=64).enable_perf(inner_iters=K, tables=T)
+s = lib.Solver(g, max_it=a.max_iters + 8, frac=a.window / (a.max_iters + 8), abs_stop=1, abs_tol=a.tol, check_every=256, rho0=a.rho0, nu=a.nu,
+               tau_incr=a.tau, tau_decr=a.tau, outer_alpha=a.outer_alpha, adapt_every=a.adapt_every).enable_perf(inner_iters=a.inner, tables=T)
 t0 = time.perf_counter()
-done, chunk, trace = 0, max(64, max_iters // 40), []
-while done < max_iters:
-    st = s.run(min(chunk, max_iters - done))
+done, chunk = 0, max(256, a.max_iters // a.trace)
+while done < a.max_iters and time.perf_counter() - t0 < a.budget:
+    st = s.run(min(chunk, a.max_iters - done))
     done = st["iterations"]
-    trace.append(dict(it=done, s=round(time.perf_counter() - t0, 3), pri=st["pri_res"], dual=st["dual_res"], rho=st["rho"]))
-    print(json.dumps(trace[-1]), flush=True)
+    print(json.dumps(dict(it=done, s=round(time.perf_counter() - t0, 3), pri=st["pri_res"], dual=st["dual_res"], rho=st["rho"])), flush=True)
     if st["converged"] or st["diverged"]:
         break
 x_v, z_v, y_v, z_e = s.solution()
 cost = float(np.sum(np.linalg.norm(z_v[:, :2] - z_v[:, 2:], axis=1)) + 1e-4 * np.sum(z_e[:, 4]))
-print(json.dumps(dict(workload=f"grid{G}x{G}", vertices=g.nV, edges=g.nE, mode=f"perf K={K}", tol=tol, reached=bool(st["converged"]), iterations=done,
+print(json.dumps(dict(workload=f"grid{a.grid}x{a.grid}", vertices=g.nV, edges=g.nE, mode=f"perf K={a.inner}", tol=a.tol, reached=bool(st["converged"]), iterations=done,
                       seconds=time.perf_counter() - t0, pri=st["pri_res"], dual=st["dual_res"], rho=st["rho"], cost=cost,
-                      straight_line=float(np.sqrt(2.0) * (G - 1)), rho_adaptation_window=window)))
+                      straight_line=float(np.sqrt(2.0) * (a.grid - 1)), params=vars(a))))
 s.close()
