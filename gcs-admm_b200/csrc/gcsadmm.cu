@@ -525,7 +525,8 @@ static int create_impl(GcsHandle *h, const GcsGraph *g) {
     UP(edge_he_tail, g->edge_he_tail, g->nE); UP(edge_he_head, g->edge_he_head, g->nE);
     UP(vtype, g->vtype, g->nV); UP(cent, g->cent, 2 * (size_t)g->nV);
     if (g->edge_counted) UP(edge_counted, g->edge_counted, g->nE);
-    UP(xc, (const double *)nullptr, 5 * (Hall + (size_t)g->nH_ghost));      // ghost slots twice: double-buffered in peer mode UP(mu, (const double *)nullptr, 5 * (size_t)g->nH_own); UP(z, (const double *)nullptr, 5 * (size_t)g->nE);
+    UP(xc, (const double *)nullptr, 5 * (Hall + (size_t)g->nH_ghost));      // ghost slots twice: double-buffered in peer mode
+    UP(mu, (const double *)nullptr, 5 * (size_t)g->nH_own); UP(z, (const double *)nullptr, 5 * (size_t)g->nE);
     UP(x_v, (const double *)nullptr, 4 * (size_t)g->nV); UP(z_v, (const double *)nullptr, 4 * (size_t)g->nV); UP(y_v, (const double *)nullptr, g->nV);
     if (h->p.warm_theta > 0.0) UP(ws, (const double *)nullptr, (size_t)g->nV * gcs_ws_stride(h->L));
     UP(partials, (const double *)nullptr, (size_t)h->edge_blocks * NSUMS);
