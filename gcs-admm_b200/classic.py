@@ -26,7 +26,7 @@ from .rounding import rounding
 __all__ = ["solve_classic"]
 
 
-def solve_classic(As, bs, n, *, graph=None, round_solution=True, seed=None, tol=1e-9, verbose=False):
+def solve_classic(As, bs, n, *, graph=None, round_solution=True, seed=None, tol=1e-9, verbose=False, kkt=True):
     """Returns dict(cost, x_v_sol, z_v_sol, y_v_sol, y_e_sol, z_v_e_sol, solve_time, status[, final_cost,
     x_v_rounded, y_v_rounded, path]); ``cost`` is the relaxation optimum the reference prints as
     "Optimal Cost Pre-rounding" (``:208-209``)."""
@@ -112,10 +112,14 @@ def solve_classic(As, bs, n, *, graph=None, round_solution=True, seed=None, tol=
         for k in range(n):
             ineq({Z(v, k): -1.0, Z(v, n + k): 1.0}, 0.0)
         socs.append(n + 1)
-    G = np.zeros((len(rows), nvar))
-    for r, c in enumerate(rows):
-        for k, val in c.items():
-            G[r, k] += val
+    import scipy.sparse as sp
+
+    def assemble(dict_rows):
+        ri = np.fromiter((r for r, c in enumerate(dict_rows) for _ in c), dtype=np.int64)
+        ci = np.fromiter((k for c in dict_rows for k in c), dtype=np.int64)
+        va = np.fromiter((val for c in dict_rows for val in c.values()), dtype=np.float64)
+        return sp.csr_matrix((va, (ri, ci)), shape=(len(dict_rows), nvar))      # duplicate (row, column) entries are summed
+    G = assemble(rows)
     h = np.array(rhs)
 
     erows, f = [], []
@@ -123,9 +127,11 @@ def solve_classic(As, bs, n, *, graph=None, round_solution=True, seed=None, tol=
         v, w = e
         for k in range(n):
             erows.append({ZE(v, e, n + k): 1.0, ZE(w, e, k): -1.0}); f.append(0.0)
+    c6_out_row = {}
     for v in V:
         ds, dt = delta('s', v), delta('t', v)
         c = {Y(v): 1.0}; c.update({YE(e): -1.0 for e in I_in[v]}); erows.append(c); f.append(float(ds))      # C6
+        c6_out_row[v] = len(erows)
         c = {Y(v): 1.0}; c.update({YE(e): -1.0 for e in I_out[v]}); erows.append(c); f.append(float(dt))
         for k in range(d2):                       # C7
             c = {Z(v, k): 1.0}; c.update({ZE(v, e, k): -1.0 for e in I_in[v]})
@@ -136,21 +142,30 @@ def solve_classic(As, bs, n, *, graph=None, round_solution=True, seed=None, tol=
             if dt:
                 c[X(v, k)] = c.get(X(v, k), 0.0) - 1.0
             erows.append(c); f.append(0.0)
-    Em = np.zeros((len(erows), nvar))
-    for r, c in enumerate(erows):
-        for k, val in c.items():
-            Em[r, k] += val
-    # C6 summed over the vertices is 0 = 0 (every edge is one in- and one out-edge): keep a maximal independent set of rows
-    from scipy.linalg import qr
-    _, R, piv = qr(Em.T, mode="economic", pivoting=True)
-    dg = np.abs(np.diag(R))
-    keep = np.sort(piv[:int(np.sum(dg > 1e-10 * dg[0]))])
-    Em, f = Em[keep], [f[k] for k in keep]
+    # C6 summed over the vertices of one connected component is 0 = 0 (every edge is one in- and one out-edge of it): one
+    # redundant row per component — drop the "out" flow row of the component's first vertex.  (Up to a few hundred vertices
+    # this is cross-checked against a pivoted QR of the dense matrix.)
+    from scipy.sparse.csgraph import connected_components
+    adj = sp.csr_matrix((np.ones(nE), ([vi[e[0]] for e in E], [vi[e[1]] for e in E])), shape=(nV, nV)) if nE else sp.csr_matrix((nV, nV))
+    ncomp, comp = connected_components(adj, directed=False)
+    first = {}
+    for v in V:
+        first.setdefault(comp[vi[v]], v)
+    drop = {c6_out_row[v] for v in first.values()}
+    keep = [k for k in range(len(erows)) if k not in drop]
+    Em = assemble(erows)[keep]
+    f = [f[k] for k in keep]
+    if nV <= 300:
+        from scipy.linalg import qr
+        _, R, _ = qr(Em.toarray().T, mode="economic", pivoting=True)
+        dg = np.abs(np.diag(R))
+        if int(np.sum(dg > 1e-10 * dg[0])) != Em.shape[0]:
+            raise RuntimeError("equality rows of the classic program are not independent after the analytic reduction")
     q = np.zeros(nvar)
     q[oye:oye + nE] = 1e-4                        # :99-100
     q[ot:] = 1.0
     t0 = time.time()
-    res = solve_conic_qp(None, q, G, h, l, socs, Em, np.array(f), tol=tol, max_iter=100, augmented=True)
+    res = solve_conic_qp(None, q, G, h, l, socs, Em, np.array(f), tol=tol, max_iter=100, augmented=kkt)
     solve_time = time.time() - t0
     u = res.u
     out = dict(status=res.status, iterations=res.iterations, solve_time=solve_time, V=V0, E=E0,

@@ -41,11 +41,11 @@ extern "C" int gcsemu_vertex_update_perf_all(int nV, int nE, const int *poly_off
                                              const int *vclass, const double *cls_tab, const int *cone_off, const double *cone,
                                              const int *blk_off, const int *blk_he, const int *blk_edge, const int *blk_info, const int *tile_voff, int ntiles,
                                              int cap_blocks, int cap_verts, int cap_cone, double *tstate, double *tn,
-                                             int inner_iters, double alpha, double kappa) {
+                                             int inner_iters, double alpha, double kappa, double theta, const double *edge_delta) {
     GcsGraphView G = {nV, nE, poly_off, polyA, polyb, he_off, he_edge, he_flags, vtype, cent};
     GcsStateView St = {xc, mu, z, x_v, z_v, y_v, 0, 0.0, 0.0};
     GcsPerfLayout L = gcs_perf_layout(cap_blocks, cap_verts, cap_cone);
-    GcsPerfTables T = {vclass, cls_tab, cone_off, cone, blk_off, blk_he, blk_edge, blk_info, tile_voff, ntiles, tstate, tn, inner_iters, alpha, kappa};
+    GcsPerfTables T = {vclass, cls_tab, cone_off, cone, blk_off, blk_he, blk_edge, blk_info, tile_voff, ntiles, tstate, tn, inner_iters, alpha, kappa, theta, edge_delta};
     Ctrl ctrl;
     memset(&ctrl, 0, sizeof ctrl);
     ctrl.rho = rho; ctrl.mu_scale = mu_scale;

@@ -95,7 +95,7 @@ struct GcsHandle {
     GcsPerfLayout PL;
     GcsPerfTables PT;
     long long perf_nblocks;
-    int *p_vclass, *p_cone_off, *p_blk_off, *p_blk_he, *p_blk_edge, *p_blk_info, *p_tile_voff; double *p_cls_tab, *p_cone, *p_tstate, *p_tn;
+    int *p_vclass, *p_cone_off, *p_blk_off, *p_blk_he, *p_blk_edge, *p_blk_info, *p_tile_voff; double *p_cls_tab, *p_cone, *p_tstate, *p_tn, *p_edge_delta;
     // one CUDA graph per chunk of `check_every` iterations (own stream only)
     cudaGraphExec_t graph_exec; int graph_iters;
     // peer mode (multi-GPU over NVLink peer memory, one process per GPU): see the "peer mode" section
@@ -167,43 +167,12 @@ __device__ void control_apply(Ctrl *ctrl, const GcsParams &p, long long n_x, lon
     if (opt) { ctrl->opt = 1; ctrl->stop = 1; }
 }
 
-// ------------------------------------------------------------------------------------------ K2-K5
-// z_e = 1/2 (xc_tail + xc_head)            reference admm_solver_v3.py:543-562 (live scalars only)
-// mu_h <- mu_scale * mu_h + (z_e - xc_h)    :590-594  (mu_scale carries the rho-adaptation rescale :705/:708)
-// partial sums of |z - xc|^2, |dz|^2, |xc|^2, |z|^2, |mu|^2     :597-614
-// One thread per (edge, consensus scalar): z and the tail-side records are walked sequentially (edges are sorted by
-// (tail, head) and a vertex's outgoing half-edges follow that order), the head-side record is a 40-byte gather.
-// oalpha != 1 (perf mode only) over-relaxes the consensus step: xc is replaced by oalpha xc + (1 - oalpha) z_old in the
-// z- and mu-updates (Boyd et al. 3.4.3); the primal residual keeps the true xc.
-// fuse != 0: the last block to finish reduces the block partials in a fixed order and applies the control step.
-__global__ void __launch_bounds__(EDGE_THREADS, 6)
-edge_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *__restrict__ edge_he_head,
-            const unsigned char *__restrict__ edge_counted, const double *__restrict__ xc, double *__restrict__ mu,
-            double *__restrict__ z, Ctrl *ctrl, double *__restrict__ partials, unsigned int *ticket, int fuse,
-            GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap, int nHghost, const PeerView *PVp) {
-    if (ctrl->stop && !ctrl->ignore_stop) return;
-    const double ms = ctrl->mu_scale, oa = p.outer_alpha, ob = 1.0 - p.outer_alpha;
-    // peer mode: the ghost slots of this iteration's parity (PVp lives in device memory: indexed at run time)
-    const int gpar = fuse == 2 ? ((PVp->comm[PVp->rank]->k + 1) & 1) * nHghost : 0;
-    double r2 = 0, dz2 = 0, x2 = 0, z2 = 0, m2 = 0, bad = 0;
-    // 40 registers per thread (6 blocks of 256 per SM), each thread with its index loads and then five independent data loads in flight
-    const unsigned n = 5u * (unsigned)nE, stride = gridDim.x * blockDim.x;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const unsigned e = i / 5u, c = i - 5u * e;
-        const int ht = edge_he_tail[e], hh = edge_he_head[e];
-        const bool ot = ht < nHown, oh = hh < nHown;
-        const unsigned it_ = 5u * (unsigned)(ot ? ht : ht + gpar) + c, ih_ = 5u * (unsigned)(oh ? hh : hh + gpar) + c;
-        const double xt = xc[it_], xh = xc[ih_], zo = z[i];
-        const double mt = ot ? mu[it_] : 0.0, mh = oh ? mu[ih_] : 0.0;       // issued with the xc loads, not after the arithmetic
-        const double w = edge_counted ? (double)edge_counted[e] : 1.0;
-        double at = xt, ah = xh;
-        if (oa != 1.0) { at = oa * xt + ob * zo; ah = oa * xh + ob * zo; }
-        const double zn = 0.5 * (at + ah), dd = zn - zo;
-        z[i] = zn;
-        dz2 += w * dd * dd; z2 += w * zn * zn;
-        if (ot) { const double r = zn - xt, mn = ms * mt + (zn - at); mu[it_] = mn; r2 += r * r; x2 += xt * xt; m2 += mn * mn; }
-        if (oh) { const double r = zn - xh, mn = ms * mh + (zn - ah); mu[ih_] = mn; r2 += r * r; x2 += xh * xh; m2 += mn * mn; }
-    }
+// Block reduction of the six partial sums, then the LAST block to finish (ticket) adds all blocks' partials in a fixed order and
+// applies the control step (fuse = 1), publishes this rank's sums to every peer (fuse = 2) or just leaves them in ctrl->sums (fuse = 0)
+__device__ __forceinline__ void edge_finish(double r2, double dz2, double x2, double z2, double m2, Ctrl *ctrl, double *__restrict__ partials,
+                                            unsigned int *ticket, int fuse, const GcsParams &p, long long n_x, long long n_mu, double *hist,
+                                            int hist_cap, const PeerView *PVp) {
+    double bad = 0;
     if (!isfinite(r2) || !isfinite(dz2) || !isfinite(x2) || !isfinite(z2)) bad = 1.0;
     // block reduction (fixed order: shuffles, then warp partials in shared memory)
     __shared__ double sh[EDGE_THREADS][6];
@@ -262,6 +231,95 @@ edge_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *
         *ticket = 0u;
         if (fuse) control_apply(ctrl, p, n_x, n_mu, hist, hist_cap);
     }
+}
+
+// ------------------------------------------------------------------------------------------ K2-K5
+// z_e = 1/2 (xc_tail + xc_head)            reference admm_solver_v3.py:543-562 (live scalars only)
+// mu_h <- mu_scale * mu_h + (z_e - xc_h)    :590-594  (mu_scale carries the rho-adaptation rescale :705/:708)
+// partial sums of |z - xc|^2, |dz|^2, |xc|^2, |z|^2, |mu|^2     :597-614
+// One thread per (edge, consensus scalar): z and the tail-side records are walked sequentially (edges are sorted by
+// (tail, head) and a vertex's outgoing half-edges follow that order), the head-side record is a 40-byte gather.
+// oalpha != 1 (perf mode only) over-relaxes the consensus step: xc is replaced by oalpha xc + (1 - oalpha) z_old in the
+// z- and mu-updates (Boyd et al. 3.4.3); the primal residual keeps the true xc.
+// fuse != 0: the last block to finish reduces the block partials in a fixed order and applies the control step.
+__global__ void __launch_bounds__(EDGE_THREADS, 6)
+edge_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *__restrict__ edge_he_head,
+            const unsigned char *__restrict__ edge_counted, const double *__restrict__ xc, double *__restrict__ mu,
+            double *__restrict__ z, Ctrl *ctrl, double *__restrict__ partials, unsigned int *ticket, int fuse,
+            GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap, int nHghost, const PeerView *PVp) {
+    if (ctrl->stop && !ctrl->ignore_stop) return;
+    const double ms = ctrl->mu_scale, oa = p.outer_alpha, ob = 1.0 - p.outer_alpha;
+    // peer mode: the ghost slots of this iteration's parity (PVp lives in device memory: indexed at run time)
+    const int gpar = fuse == 2 ? ((PVp->comm[PVp->rank]->k + 1) & 1) * nHghost : 0;
+    double r2 = 0, dz2 = 0, x2 = 0, z2 = 0, m2 = 0;
+    // 40 registers per thread (6 blocks of 256 per SM), each thread with its index loads and then five independent data loads in flight
+    const unsigned n = 5u * (unsigned)nE, stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned e = i / 5u, c = i - 5u * e;
+        const int ht = edge_he_tail[e], hh = edge_he_head[e];
+        const bool ot = ht < nHown, oh = hh < nHown;
+        const unsigned it_ = 5u * (unsigned)(ot ? ht : ht + gpar) + c, ih_ = 5u * (unsigned)(oh ? hh : hh + gpar) + c;
+        const double xt = xc[it_], xh = xc[ih_], zo = z[i];
+        const double mt = ot ? mu[it_] : 0.0, mh = oh ? mu[ih_] : 0.0;       // issued with the xc loads, not after the arithmetic
+        const double w = edge_counted ? (double)edge_counted[e] : 1.0;
+        double at = xt, ah = xh;
+        if (oa != 1.0) { at = oa * xt + ob * zo; ah = oa * xh + ob * zo; }
+        const double zn = 0.5 * (at + ah), dd = zn - zo;
+        z[i] = zn;
+        dz2 += w * dd * dd; z2 += w * zn * zn;
+        if (ot) { const double r = zn - xt, mn = ms * mt + (zn - at); mu[it_] = mn; r2 += r * r; x2 += xt * xt; m2 += mn * mn; }
+        if (oh) { const double r = zn - xh, mn = ms * mh + (zn - ah); mu[ih_] = mn; r2 += r * r; x2 += xh * xh; m2 += mn * mn; }
+    }
+    edge_finish(r2, dz2, x2, z2, m2, ctrl, partials, ticket, fuse, p, n_x, n_mu, hist, hist_cap, PVp);
+}
+
+// local frames (perf-mode option, vertex_perf.cuh GcsPerfTables.edge_delta): the consensus constraint of edge e is
+//   x_head = z,  x_tail = B z,  B (p1, p2, y) = (p1, p2 - y delta, y)
+// so the z-update is the least-squares solve  (I + B'B) z = x_head + B' x_tail  (the duals drop out: B' mu_tail + mu_head = 0 is an
+// invariant of the iteration), closed form per edge; mu_head += z - x_head, mu_tail += B z - x_tail; the dual residual is
+// rho sqrt(|dz|^2 + |B dz|^2).  One thread per edge: the three coupled scalars (p2, y) are needed together.
+__global__ void __launch_bounds__(EDGE_THREADS, 2)
+edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *__restrict__ edge_he_head,
+                   const unsigned char *__restrict__ edge_counted, const double *__restrict__ edge_delta, const double *__restrict__ xc,
+                   double *__restrict__ mu, double *__restrict__ z, Ctrl *ctrl, double *__restrict__ partials, unsigned int *ticket, int fuse,
+                   GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap, int nHghost, const PeerView *PVp) {
+    if (ctrl->stop && !ctrl->ignore_stop) return;
+    const double ms = ctrl->mu_scale;
+    const int gpar = fuse == 2 ? ((PVp->comm[PVp->rank]->k + 1) & 1) * nHghost : 0;
+    double r2 = 0, dz2 = 0, x2 = 0, z2 = 0, m2 = 0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
+        const int ht = edge_he_tail[e], hh = edge_he_head[e];
+        const bool ot = ht < nHown, oh = hh < nHown;
+        const double *pt = xc + 5 * (size_t)(ot ? ht : ht + gpar), *ph = xc + 5 * (size_t)(oh ? hh : hh + gpar);
+        double xt[5], xh[5], zo[5], mt[5], mh[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { xt[c] = pt[c]; xh[c] = ph[c]; zo[c] = z[5 * (size_t)e + c]; }
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { mt[c] = ot ? mu[5 * (size_t)ht + c] : 0.0; mh[c] = oh ? mu[5 * (size_t)hh + c] : 0.0; }
+        const double d0 = edge_delta[2 * (size_t)e], d1 = edge_delta[2 * (size_t)e + 1];
+        const double w = edge_counted ? (double)edge_counted[e] : 1.0;
+        double zn[5], bz[5];
+        zn[0] = 0.5 * (xh[0] + xt[0]); zn[1] = 0.5 * (xh[1] + xt[1]);
+        const double q0 = xh[2] + xt[2], q1 = xh[3] + xt[3], q2 = xh[4] + xt[4] - (d0 * xt[2] + d1 * xt[3]);
+        zn[4] = (q2 + 0.5 * (d0 * q0 + d1 * q1)) / (2.0 + 0.5 * (d0 * d0 + d1 * d1));
+        zn[2] = 0.5 * (q0 + d0 * zn[4]); zn[3] = 0.5 * (q1 + d1 * zn[4]);
+        bz[0] = zn[0]; bz[1] = zn[1]; bz[2] = zn[2] - d0 * zn[4]; bz[3] = zn[3] - d1 * zn[4]; bz[4] = zn[4];
+        double dd[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { dd[c] = zn[c] - zo[c]; z[5 * (size_t)e + c] = zn[c]; }
+        const double db2 = dd[2] - d0 * dd[4], db3 = dd[3] - d1 * dd[4];
+        dz2 += 0.5 * w * (2.0 * (dd[0] * dd[0] + dd[1] * dd[1] + dd[4] * dd[4]) + dd[2] * dd[2] + dd[3] * dd[3] + db2 * db2 + db3 * db3);
+        z2 += 0.5 * w * (2.0 * (zn[0] * zn[0] + zn[1] * zn[1] + zn[4] * zn[4]) + zn[2] * zn[2] + zn[3] * zn[3] + bz[2] * bz[2] + bz[3] * bz[3]);
+        if (ot) {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) { const double r = bz[c] - xt[c], mn = ms * mt[c] + r; mu[5 * (size_t)ht + c] = mn; r2 += r * r; x2 += xt[c] * xt[c]; m2 += mn * mn; }
+        }
+        if (oh) {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) { const double r = zn[c] - xh[c], mn = ms * mh[c] + r; mu[5 * (size_t)hh + c] = mn; r2 += r * r; x2 += xh[c] * xh[c]; m2 += mn * mn; }
+        }
+    }
+    edge_finish(r2, dz2, x2, z2, m2, ctrl, partials, ticket, fuse, p, n_x, n_mu, hist, hist_cap, PVp);
 }
 
 // ------------------------------------------------------------------------------------------ peer mode (kernels)
@@ -431,10 +489,10 @@ static int reset_ctrl(GcsHandle *h) {
 }
 
 static void free_perf(GcsHandle *h) {
-    void *pp[] = {h->p_vclass, h->p_cone_off, h->p_blk_off, h->p_blk_he, h->p_blk_edge, h->p_blk_info, h->p_tile_voff, h->p_cls_tab, h->p_cone, h->p_tstate, h->p_tn};
+    void *pp[] = {h->p_vclass, h->p_cone_off, h->p_blk_off, h->p_blk_he, h->p_blk_edge, h->p_blk_info, h->p_tile_voff, h->p_cls_tab, h->p_cone, h->p_tstate, h->p_tn, h->p_edge_delta};
     for (void *q : pp) if (q) cudaFree(q);
     h->p_vclass = h->p_cone_off = h->p_blk_off = h->p_blk_he = h->p_blk_edge = h->p_blk_info = h->p_tile_voff = nullptr;
-    h->p_cls_tab = h->p_cone = h->p_tstate = h->p_tn = nullptr;
+    h->p_cls_tab = h->p_cone = h->p_tstate = h->p_tn = h->p_edge_delta = nullptr;
     h->perf_on = 0;
 }
 static void drop_graph(GcsHandle *h) {
@@ -624,6 +682,14 @@ static int launch_edge(GcsHandle *h, int fuse) {
         const int blocks = h->nP < 148 * 16 ? h->nP : 148 * 16;
         batched_edge_kernel<<<blocks, BATCH_THREADS, 0, h->stream>>>(h->nP, h->prob_eoff, h->nHown, h->edge_he_tail, h->edge_he_head, h->xc, h->mu, h->z,
                                                                      h->ctrl, h->p, h->prob_nx, h->prob_nmu, h->hist, h->hist_cap);
+        return 0;
+    }
+    if (h->perf_on && h->p_edge_delta) {      // local frames
+        int blocks = (h->nE + EDGE_THREADS - 1) / EDGE_THREADS;
+        if (blocks > h->edge_blocks) blocks = h->edge_blocks;
+        if (blocks < 1) blocks = 1;
+        edge_frames_kernel<<<blocks, EDGE_THREADS, 0, h->stream>>>(h->nE, h->nHown, h->edge_he_tail, h->edge_he_head, h->edge_counted, h->p_edge_delta, h->xc, h->mu,
+                                                                   h->z, h->ctrl, h->partials, h->ticket, fuse, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, h->nHghost, h->PV_dev);
         return 0;
     }
     edge_kernel<<<h->edge_blocks, EDGE_THREADS, 0, h->stream>>>(h->nE, h->nHown, h->edge_he_tail, h->edge_he_head, h->edge_counted, h->xc, h->mu, h->z, h->ctrl,
@@ -984,13 +1050,14 @@ extern "C" int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *c) {
     if (!rc) rc = upload(&h->p_tile_voff, c->tile_voff, (size_t)c->n_tiles + 1);
     if (!rc) rc = upload(&h->p_tstate, (const double *)nullptr, 12 * (size_t)c->n_blocks);
     if (!rc) rc = upload(&h->p_tn, (const double *)nullptr, 2 * (size_t)h->nV);
+    if (!rc && c->edge_delta) rc = upload(&h->p_edge_delta, c->edge_delta, 2 * (size_t)h->nE);
     if (rc) { free_perf(h); return rc; }
     h->perf_nblocks = c->n_blocks;
     h->PL = gcs_perf_layout(c->cap_blocks, c->cap_verts, c->cap_cone);
     h->PT.vclass = h->p_vclass; h->PT.cls_tab = h->p_cls_tab; h->PT.cone_off = h->p_cone_off; h->PT.cone = h->p_cone;
     h->PT.blk_off = h->p_blk_off; h->PT.blk_he = h->p_blk_he; h->PT.blk_edge = h->p_blk_edge; h->PT.blk_info = h->p_blk_info; h->PT.tile_voff = h->p_tile_voff;
     h->PT.ntiles = c->n_tiles; h->PT.tstate = h->p_tstate; h->PT.tn = h->p_tn; h->PT.inner_iters = c->inner_iters;
-    h->PT.alpha = c->alpha; h->PT.kappa = c->kappa;
+    h->PT.alpha = c->alpha; h->PT.kappa = c->kappa; h->PT.theta = c->theta > 0.0 ? c->theta : 1.0; h->PT.edge_delta = h->p_edge_delta;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
     const size_t bytes = (size_t)h->PL.total * sizeof(double);

@@ -64,6 +64,10 @@ struct GcsPerfTables {
     double *tn;                // [nV][2]          the same for the path-length item z_1 - z_2
     int inner_iters;           // K
     double alpha, kappa;
+    double theta;              // penalty of the flow scalars = theta * rho (1: the reference's single rho; see GcsPerfConfig)
+    const double *edge_delta;  // [nE][2] or null.  Non-null = LOCAL FRAMES: every vertex program works in coordinates centred on its
+                               // own region (polytopes / cones shifted by cent[v]); the two copies of an edge e = (u, w) then agree through
+                               // x_head = z_e,  x_tail = B_e z_e  with  B_e (p1, p2, y) = (p1, p2 - y delta_e, y),  delta_e = cent[u] - cent[w]
 };
 
 // shared memory of one tile (offsets in doubles)
@@ -201,6 +205,14 @@ GCS_DEV double gcs_core_output(const double *tab, const double *in, int k) {
     return s0 + s1 + gk[GCS_NCX - 1] * in[GCS_NCX - 1];
 }
 
+// consensus target of scalar c of half-edge h (block descriptor `info`) before the dual is added:  (B z_e)[c]
+GCS_DEV double gcs_target_z(const GcsStateView &St, const GcsPerfTables &T, int e, int c, int info) {
+    double zc = St.z[5 * (size_t)e + c];
+    if (T.edge_delta && ((info >> 8) & 3) == 1 && (c == 2 || c == 3))      // tail side, second point: p2 - y delta_e
+        zc -= T.edge_delta[2 * (size_t)e + c - 2] * St.z[5 * (size_t)e + 4];
+    return zc;
+}
+
 // x-update of one tile of vertices in perf mode.  `bar` is an mbarrier in shared memory (device build only).
 GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const GcsPerfTables &T, const GcsPerfLayout &L,
                            double *S, int tile, Ctrl *ctrl_all, const int *vprob, unsigned long long *bar) {
@@ -255,7 +267,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
         pz[j] = 0.0; pm[j] = 0.0;
         if (q < 5 * nb) {
             const int b = q / 5, c = q - 5 * b, h = bhe[b];
-            if (h >= 0 && vi[GCS_VI_N * (binfo[b] & 255) + GCS_VI_ACTIVE]) { pz[j] = St.z[5 * (size_t)bedge[b] + c]; pm[j] = St.mu[5 * (size_t)h + c]; }
+            if (h >= 0 && vi[GCS_VI_N * (binfo[b] & 255) + GCS_VI_ACTIVE]) { pz[j] = gcs_target_z(St, T, bedge[b], c, binfo[b]); pm[j] = St.mu[5 * (size_t)h + c]; }
         }
     }
 #endif
@@ -314,7 +326,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
 #endif
                 const int b = q / 5, c = q - 5 * b, h = bhe[b], vl = binfo[b] & 255;
                 if (h < 0 || !vi[GCS_VI_N * vl + GCS_VI_ACTIVE]) continue;
-                TS[q] = St.z[5 * (size_t)bedge[b] + c] + vd[2 * vl + 1] * St.mu[5 * (size_t)h + c];
+                TS[q] = gcs_target_z(St, T, bedge[b], c, binfo[b]) + vd[2 * vl + 1] * St.mu[5 * (size_t)h + c];
             }
         }
         GCS_CTA_SYNC();
@@ -337,7 +349,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
                 val = d[2] + d[8];
                 if (!term) val += (1.0 - d[5]) + (1.0 - d[11]);
                 val *= kappa;
-                if (grp < 2) val += TS[q] - GCS_EDGE_PENALTY / vd[2 * vl];
+                if (grp < 2) val += T.theta * TS[q] - GCS_EDGE_PENALTY / vd[2 * vl];
             }
             rS[q] = val;
         }
@@ -377,8 +389,10 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
                 const int vl = q / 9, k = q - 9 * vl;
                 const int *w = vi + GCS_VI_N * vl;
                 if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;
-                const double val = cout[GCS_NCX * vl + k];
+                double val = cout[GCS_NCX * vl + k];
                 const size_t v = (size_t)(v0 + vl);
+                if (T.edge_delta && k < 8)          // local frames: back to global coordinates  x = x' + c_v,  z_v = z_v' + y_v c_v
+                    val += (k < 4 ? 1.0 : cout[GCS_NCX * vl + 8]) * G.cent[2 * v + (k & 1)];
                 if (k < 4) St.x_v[4 * v + k] = val; else if (k < 8) St.z_v[4 * v + k - 4] = val; else St.y_v[v] = val;
             }
         }

@@ -48,7 +48,8 @@ class GcsPerfConfig(C.Structure):
                 ("vclass", C.c_void_p), ("cls_tab", C.c_void_p), ("cone_off", C.c_void_p), ("cone", C.c_void_p),
                 ("n_blocks", C.c_int32), ("blk_off", C.c_void_p), ("blk_he", C.c_void_p), ("blk_info", C.c_void_p),
                 ("n_tiles", C.c_int32), ("tile_voff", C.c_void_p),
-                ("cap_blocks", C.c_int32), ("cap_verts", C.c_int32), ("cap_cone", C.c_int32)]
+                ("cap_blocks", C.c_int32), ("cap_verts", C.c_int32), ("cap_cone", C.c_int32),
+                ("theta", C.c_double), ("edge_delta", C.c_void_p)]
 
 
 class GcsStatus(C.Structure):
@@ -188,10 +189,10 @@ class Solver:
         self._h = h
         self.nHall = self._gs.nH_own + self._gs.nH_ghost
 
-    def enable_perf(self, inner_iters=1, alpha=1.6, kappa=1.0, tables=None):
+    def enable_perf(self, inner_iters=1, alpha=1.6, kappa=1.0, tables=None, frames="global"):
         """Switch the x-update to the inexact `perf` mode (K closed-form splitting iterations per ADMM iteration)."""
         from . import perf
-        T = tables if tables is not None else perf.perf_tables(self.g, kappa)
+        T = tables if tables is not None else perf.perf_tables(self.g, kappa, frames=frames)
         i32, f64 = np.int32, np.float64
         keep = dict(vclass=np.ascontiguousarray(T["vclass"], i32), cls_tab=np.ascontiguousarray(T["cls_tab"], f64),
                     cone_off=np.ascontiguousarray(T["cone_off"], i32), cone=np.ascontiguousarray(T["cone"], f64),
@@ -203,9 +204,14 @@ class Solver:
             setattr(c, k, _ptr(keep[k]))
         c.n_blocks, c.n_tiles = int(keep["blk_he"].shape[0]), int(keep["tile_voff"].shape[0] - 1)
         c.cap_blocks, c.cap_verts, c.cap_cone = int(T["caps"]["nb"]), int(T["caps"]["nvt"]), int(T["caps"]["cone"])
+        c.theta = float(T.get("theta", 1.0))
+        if T.get("edge_delta") is not None:
+            keep["edge_delta"] = np.ascontiguousarray(T["edge_delta"], f64)
+            c.edge_delta = _ptr(keep["edge_delta"])
         _check(load().gcsadmm_enable_perf(self._h, C.byref(c)))
+        self._frames = T.get("edge_delta") is not None
         self.perf = dict(inner_iters=int(inner_iters), alpha=float(alpha), kappa=float(T["kappa"]), classes=len(T["classes"]),
-                         n_blocks=c.n_blocks, n_tiles=c.n_tiles)
+                         n_blocks=c.n_blocks, n_tiles=c.n_tiles, frames="local" if self._frames else "global")
         return self
 
     def perf_state(self):
@@ -280,6 +286,11 @@ class Solver:
         nV, nE = self.g.nV, self.g.nE
         x_v, z_v, y_v, z_e = np.zeros((nV, 4)), np.zeros((nV, 4)), np.zeros(nV), np.zeros((nE, 5))
         _check(load().gcsadmm_get_solution(self._h, _ptr(x_v), _ptr(z_v), _ptr(y_v), _ptr(z_e)))
+        if getattr(self, "_frames", False) and hasattr(self.g, "edge_tail"):
+            # local frames: the edge variables (p1 in the tail's frame, p2 in the head's, y) back to global coordinates
+            c = np.asarray(self.g.interior_points())
+            z_e[:, 0:2] += z_e[:, 4:5] * c[self.g.edge_tail]
+            z_e[:, 2:4] += z_e[:, 4:5] * c[self.g.edge_head]
         return x_v, z_v, y_v, z_e
 
     def state(self):

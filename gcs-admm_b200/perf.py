@@ -102,11 +102,13 @@ def class_inverse(vtype, din, dout, kappa):
     return np.ascontiguousarray(Kinv)
 
 
-def cone_table(g):
+def cone_table(g, shift=None):
     """Per region: polygon vertices (counter-clockwise) with the unit outward normal of the cone face spanned by the
     rays through vertex k and k+1, 1/|r_k|^2 (r_k = (V_k, 1)) and the two in-plane sector normals of that face
     (12 doubles per polygon vertex).  Vectorised over regions with the same vertex count."""
     verts, cnt = g.polygon_vertices_batch() if hasattr(g, "polygon_vertices_batch") else _vertices_batch(g.poly_off.astype(np.int64), g.polyA, g.polyb)
+    if shift is not None:            # local frames: the polygon of region v translated by -shift[v]
+        verts = verts - np.asarray(shift)[:, None, :]
     nV = g.nV
     # duplicates (redundant rows meeting in one vertex) are rare: handle those regions one by one
     per = [None] * nV
@@ -167,7 +169,7 @@ NCX = 19                                      # extended core: x(4) z(4) y_v | b
 CLS_STRIDE = NCX * NCX + NCX + 10 + 2          # G (19 x 19) | g0 (19) | dinv (2 x 5) | pad -> 392 doubles per class
 
 
-def class_tables(vtype, din, dout, kappa):
+def class_tables(vtype, din, dout, kappa, theta=1.0):
     """Structured form of the v-step of one vertex class (``csrc/vertex_perf.cuh``).
 
     The v-step minimises  1/2 u'D u - r'u  over the equalities C6/C7 (reference ``admm_solver_v3.py:450-464``), with
@@ -196,7 +198,7 @@ def class_tables(vtype, din, dout, kappa):
         S[o:o + 2] = 1.0
         if out[j]:
             S[o + 2:o + 4] = 1.0
-        S[o + 4] = 1.0
+        S[o + 4] = theta            # the flow scalar's penalty is theta * rho (theta = 1: the reference's single rho)
     D = np.diag(S) + kappa * M.T @ M
     K1 = N.T @ D @ N
     K1[4, :] = 0.0; K1[:, 4] = 0.0; K1[4, 4] = 1.0          # the epigraph variable t is unused in this mode
@@ -213,7 +215,7 @@ def class_tables(vtype, din, dout, kappa):
     for g in range(2):
         s = np.array([1.0, 1.0, float(g), float(g), 1.0])       # rho-quadratic: first point always, second point of out-edges, flow
         dinv[g, :4] = 1.0 / (s[:4] + nfam * kappa)
-        dinv[g, 4] = 1.0 / (1.0 + 2 * nfam * kappa)
+        dinv[g, 4] = 1.0 / (theta + 2 * nfam * kappa)
     members = [[j for j in range(d) if not out[j]], [j for j in range(d) if out[j]]]
     G = np.zeros((NCX, NCX)); g0 = np.zeros(NCX)
 
@@ -272,10 +274,12 @@ def structured_vstep(T, r):
 TILE_BLOCKS, TILE_VERTS, TILE_CONE, TILE_HE = 64, 32, 160, 128
 
 
-def perf_tables(g, kappa=1.0, cone=None):
+def perf_tables(g, kappa=1.0, cone=None, theta=1.0, frames="global", edge_delta=None):
     """Everything ``gcsadmm_enable_perf`` uploads (``include/gcsadmm.h`` ``GcsPerfConfig``): class tables, cone records,
     the block list (one block per live half-edge plus one per vertex for (z_v, y_v)) and the tiling of the vertices.
-    ``cone = (cone_off, cone)`` reuses records computed elsewhere (multi-GPU: sliced from the global graph)."""
+    ``cone = (cone_off, cone)`` reuses records computed elsewhere (multi-GPU: sliced from the global graph).
+    ``frames="local"``: every vertex program runs in coordinates centred on its own region (cone records of the shifted
+    polygons + ``edge_delta``); same optimisation problem, translation-invariant and far better conditioned on large maps."""
     nV = g.nV
     owner = np.repeat(np.arange(nV, dtype=np.int64), np.diff(np.asarray(g.he_off, dtype=np.int64)))
     flags = np.asarray(g.he_flags)
@@ -292,14 +296,20 @@ def perf_tables(g, kappa=1.0, cone=None):
     for cd in np.unique(code[alive]):
         key = (int(cd // 1000000), int((cd // 1000) % 1000), int(cd % 1000))
         keys[key] = len(keys)
-        T = class_tables(*key, kappa)
+        T = class_tables(*key, kappa, theta)
         tabs.append(np.concatenate([T["G"].reshape(-1), T["g0"], T["dinv"].reshape(-1), np.zeros(2)]))
         vclass[(code == cd) & alive] = keys[key]
     cls_tab = np.ascontiguousarray(np.concatenate(tabs)) if tabs else np.zeros(CLS_STRIDE)
+    # frames = "local": every vertex program in coordinates centred on its own region (gcsadmm.h GcsPerfConfig.edge_delta)
+    cent = np.asarray(g.interior_points()) if frames == "local" else None
     if cone is None:
-        cone_off, cone_rec = cone_table(g)
+        cone_off, cone_rec = cone_table(g, shift=cent)
     else:
         cone_off, cone_rec = cone
+    if frames == "local" and edge_delta is None:
+        if not hasattr(g, "edge_tail"):
+            raise ValueError("local frames need edge_tail / edge_head (single-GPU graphs)")
+        edge_delta = np.ascontiguousarray(cent[np.asarray(g.edge_tail, dtype=np.int64)] - cent[np.asarray(g.edge_head, dtype=np.int64)])
     # blocks: live half-edges of every live vertex in half-edge order, then its (z_v, y_v) block
     nlive = np.where(alive, din + dout, 0).astype(np.int64)
     nblk = np.where(alive, nlive + 1, 0).astype(np.int64)
@@ -327,7 +337,7 @@ def perf_tables(g, kappa=1.0, cone=None):
                 he=int((np.asarray(g.he_off, np.int64)[tv1] - np.asarray(g.he_off, np.int64)[tv0]).max()) if nV else 1)
     return dict(vclass=vclass, cls_tab=cls_tab, cone_off=np.asarray(cone_off, dtype=np.int32), cone=np.ascontiguousarray(cone_rec),
                 blk_off=blk_off.astype(np.int32), blk_he=blk_he, blk_info=blk_info, tile_voff=tile_voff.astype(np.int32),
-                caps=caps, classes=keys, kappa=float(kappa))
+                caps=caps, classes=keys, kappa=float(kappa), theta=float(theta), edge_delta=edge_delta, frames=frames)
 
 
 def _greedy_tiles(nblk, he_cnt, cone_cnt):
@@ -358,4 +368,6 @@ def local_tables(T, lp):
     np.cumsum(cnt, out=loff[1:])
     rec = T["cone"].reshape(-1, 12)
     idx = np.repeat(off[lv] - loff[:-1], cnt) + np.arange(int(loff[-1]))
-    return perf_tables(lp, T["kappa"], cone=(loff.astype(np.int32), np.ascontiguousarray(rec[idx])))
+    frames = T.get("frames", "global")
+    delta = np.ascontiguousarray(T["edge_delta"][np.asarray(lp.global_edges, dtype=np.int64)]) if frames == "local" else None
+    return perf_tables(lp, T["kappa"], cone=(loff.astype(np.int32), np.ascontiguousarray(rec[idx])), theta=T.get("theta", 1.0), frames=frames, edge_delta=delta)

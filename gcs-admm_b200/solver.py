@@ -43,7 +43,7 @@ def perf_abs_tol(g):
 
 
 def solve(As, bs, n, *, device=0, max_it=MAX_IT, round_solution=True, seed=None, verbose=False,
-          graph=None, one_call=True, mode="parity", inner_iters=1, rounding_kw=None, **params):
+          graph=None, one_call=True, mode="parity", inner_iters=1, rounding_kw=None, frames="global", **params):
     """Solve the convex relaxation of the GCS shortest-path problem by full-vertex-split ADMM.
 
     Parameters mirror the reference's literals (``rho0, tau_incr, tau_decr, nu, frac, eps_abs,
@@ -59,6 +59,8 @@ def solve(As, bs, n, *, device=0, max_it=MAX_IT, round_solution=True, seed=None,
     z_v_sol, y_e_sol (also under the short names x_v, y_v, z_v, y_e), x_v_rounded, y_v_rounded, path, iterations,
     converged, diverged, rho_seq, pri_res_seq, dual_res_seq, solve_time, status, mode, V, E.
     ``rounding_kw``: overrides of the rounding literals ``N=5, M=20`` (reference ``GCS_utils.py:92``).
+    ``frames="local"`` (perf mode): vertex programs in coordinates centred on their own regions — the same problem, a
+    translation-invariant and much better conditioned ADMM on large maps (``perf.perf_tables``).
     """
     if int(n) != 2:
         raise ValueError("gcs-admm_b200 implements the 2-D case (n = 2), like all reference data")
@@ -82,7 +84,7 @@ def solve(As, bs, n, *, device=0, max_it=MAX_IT, round_solution=True, seed=None,
     else:
         s = lib.Solver(g, device=device, max_it=max_it, **params)
         if mode == "perf":
-            s.enable_perf(inner_iters=inner_iters)
+            s.enable_perf(inner_iters=inner_iters, frames=frames)
         st = s.run(max_it)
         x_v, z_v, y_v, z_e = s.solution()
         rho, pri, dual = s.history()

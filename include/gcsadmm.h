@@ -171,6 +171,13 @@ typedef struct GcsPerfConfig {
     int32_t n_tiles;             /* a tile = the consecutive vertices one thread block works on */
     const int32_t *tile_voff;    /* [n_tiles+1] */
     int32_t cap_blocks, cap_verts, cap_cone;   /* largest tile: blocks, vertices, cone records (sizes the shared memory) */
+    double theta;                /* penalty of the flow scalars = theta * rho (0 or 1: the reference's single rho) */
+    const double *edge_delta;    /* NULL: global coordinates.  [nE][2] = cent[tail] - cent[head]: LOCAL FRAMES — every vertex program runs in
+                                    coordinates centred on its own region (the cone records must be built from the shifted polygons), the two
+                                    copies of an edge agree through x_head = z_e, x_tail = B_e z_e.  Same optimisation problem, a differently
+                                    conditioned ADMM: the perspective variables y * (p - cent) stay O(region size) instead of O(|p|), which is
+                                    what lets large maps converge.  x_v / z_v come back in global coordinates; xc, mu, z
+                                    (get_state) are in the local frames */
 } GcsPerfConfig;
 int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *cfg);
 /* the warm-start state of the perf mode (t = c + lam of every pair, 12 doubles per block, and 2 doubles per vertex for the

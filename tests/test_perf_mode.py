@@ -27,7 +27,7 @@ def load_emu():
     lib.gcsemu_vertex_update_perf_all.restype = C.c_int
     lib.gcsemu_vertex_update_perf_all.argtypes = [C.c_int, C.c_int, _ip, _dp, _dp, _ip, _ip, _bp, _bp, _dp, _dp, _dp, _dp, _dp, _dp, _dp,
                                                   C.c_double, C.c_double, _ip, _dp, _ip, _dp, _ip, _ip, _ip, _ip, _ip, C.c_int,
-                                                  C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_double]
+                                                  C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p]
     return lib
 
 
@@ -39,9 +39,10 @@ def emu():
 class EmuPerfADMM:
     """Outer ADMM (numpy edge / dual / residual / rho arithmetic of the kernels) around the emulated perf K1."""
 
-    def __init__(self, lib, g, K, kappa=1.0, alpha=1.6, outer_alpha=1.0, adapt=False, nu=10.0, tau=2.0):
+    def __init__(self, lib, g, K, kappa=1.0, alpha=1.6, outer_alpha=1.0, adapt=False, nu=10.0, tau=2.0, theta=1.0, frames="global"):
         self.lib, self.g, self.K, self.alpha, self.oa, self.adapt, self.nu, self.tau = lib, g, K, alpha, outer_alpha, adapt, nu, tau
-        self.T = perf.perf_tables(g, kappa)
+        self.T = perf.perf_tables(g, kappa, theta=theta, frames=frames)
+        self.theta, self.delta = theta, self.T["edge_delta"]
         self.tstate, self.tn = np.zeros((self.T["blk_he"].shape[0], 12)), np.zeros((g.nV, 2))
         self.blk_edge = np.where(self.T["blk_he"] >= 0, g.he_edge[np.maximum(self.T["blk_he"], 0)], -1).astype(np.int32)
         self.xc, self.mu, self.z = np.zeros((g.H, 5)), np.zeros((g.H, 5)), np.zeros((g.nE, 5))
@@ -56,9 +57,43 @@ class EmuPerfADMM:
                                                self.x_v.reshape(-1), self.z_v.reshape(-1), self.y_v, self.rho, self.ms,
                                                T["vclass"], T["cls_tab"], T["cone_off"], T["cone"].reshape(-1), T["blk_off"], T["blk_he"],
                                                self.blk_edge, T["blk_info"], T["tile_voff"], T["tile_voff"].shape[0] - 1, T["caps"]["nb"], T["caps"]["nvt"],
-                                               T["caps"]["cone"], self.tstate.reshape(-1), self.tn.reshape(-1), self.K, self.alpha, T["kappa"])
+                                               T["caps"]["cone"], self.tstate.reshape(-1), self.tn.reshape(-1), self.K, self.alpha, T["kappa"], self.theta,
+                                               None if self.delta is None else self.delta.ctypes.data_as(C.c_void_p))
+
+    def step_frames(self):
+        """local frames: z = argmin |x_head - z|^2 + |x_tail - B z|^2,  B (p1, p2, y) = (p1, p2 - y delta, y)  (gcsadmm.cu edge_frames_kernel)"""
+        g, d = self.g, self.delta
+        self.vertex_update()
+        xt, xh = self.xc[g.edge_he_tail], self.xc[g.edge_he_head]
+        zn = np.empty_like(self.z)
+        zn[:, 0:2] = 0.5 * (xh[:, 0:2] + xt[:, 0:2])
+        q = xh[:, 2:4] + xt[:, 2:4]
+        q2 = xh[:, 4] + xt[:, 4] - np.sum(d * xt[:, 2:4], axis=1)
+        zn[:, 4] = (q2 + 0.5 * np.sum(d * q, axis=1)) / (2.0 + 0.5 * np.sum(d * d, axis=1))
+        zn[:, 2:4] = 0.5 * (q + d * zn[:, 4:5])
+        dz = zn - self.z
+        self.z = zn
+        bz, dbz = zn.copy(), dz.copy()
+        bz[:, 2:4] -= d * zn[:, 4:5]; dbz[:, 2:4] -= d * dz[:, 4:5]
+        r = np.zeros_like(self.xc)
+        r[g.edge_he_head] = zn - xh
+        r[g.edge_he_tail] = bz - xt
+        self.mu = self.ms * self.mu + r
+        self.pri.append(float(np.sqrt(np.sum(r * r)))); self.dual.append(self.rho * float(np.sqrt(np.sum(dz * dz) + np.sum(dbz * dbz))))
+        self._adapt()
+
+    def _adapt(self):
+        pri, dual = self.pri[-1], self.dual[-1]
+        self.ms = 1.0
+        if self.adapt:                       # reference rho rule (:703-709) over the whole run; the rescale of mu is deferred like on the device
+            if pri >= self.nu * dual:
+                self.rho *= self.tau; self.ms = 1.0 / self.tau
+            elif dual >= self.nu * pri:
+                self.rho /= self.tau; self.ms = self.tau
 
     def step(self):
+        if self.delta is not None:
+            return self.step_frames()
         g = self.g
         self.vertex_update()
         xt, xh = self.xc[g.edge_he_tail], self.xc[g.edge_he_head]
@@ -72,14 +107,10 @@ class EmuPerfADMM:
             hat = np.empty_like(self.xc)
             hat[g.edge_he_tail] = at; hat[g.edge_he_head] = ah
         self.mu = self.ms * self.mu + (zn[g.he_edge] - hat)
-        pri, dual = float(np.sqrt(np.sum(r * r))), self.rho * float(np.sqrt(2 * np.sum(dz * dz)))
+        wz = np.array([1.0, 1.0, 1.0, 1.0, self.theta])          # the dual residual carries the penalty of every scalar
+        pri, dual = float(np.sqrt(np.sum(r * r))), self.rho * float(np.sqrt(2 * np.sum((dz * wz) ** 2)))
         self.pri.append(pri); self.dual.append(dual)
-        self.ms = 1.0
-        if self.adapt:                       # reference rho rule (:703-709) over the whole run; the rescale of mu is deferred like on the device
-            if pri >= self.nu * dual:
-                self.rho *= self.tau; self.ms = 1.0 / self.tau
-            elif dual >= self.nu * pri:
-                self.rho /= self.tau; self.ms = self.tau
+        self._adapt()
 
     def cost(self):
         return float(np.sum(np.linalg.norm(self.z_v[:, :2] - self.z_v[:, 2:], axis=1)) + 1e-4 * np.sum(self.z[:, 4]))

@@ -18,11 +18,12 @@ ap.add_argument("--outer-alpha", type=float, default=1.0)
 ap.add_argument("--rho0", type=float, default=1.0)
 ap.add_argument("--nu", type=float, default=10.0)
 ap.add_argument("--tau", type=float, default=2.0)
+ap.add_argument("--frames", type=str, default="local", choices=["local", "global"])
 ap.add_argument("--trace", type=int, default=20, help="trace points")
 ap.add_argument("--budget", type=float, default=1e9, help="seconds")
 a = ap.parse_args()
 g = grid_packed_graph(a.grid)
-T = perf.perf_tables(g)
+T = perf.perf_tables(g, frames=a.frames)
 # rho adapts while it < frac * max_it (reference rule :703): the window is a parameter of the reference's algorithm
 s = lib.Solver(g, max_it=a.max_iters + 8, frac=a.window / (a.max_iters + 8), abs_stop=1, abs_tol=a.tol, check_every=256, rho0=a.rho0, nu=a.nu,
                tau_incr=a.tau, tau_decr=a.tau, outer_alpha=a.outer_alpha, adapt_every=a.adapt_every).enable_perf(inner_iters=a.inner, tables=T)
