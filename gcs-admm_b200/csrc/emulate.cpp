@@ -45,7 +45,24 @@ extern "C" int gcsemu_vertex_update_perf_all(int nV, int nE, const int *poly_off
     GcsGraphView G = {nV, nE, poly_off, polyA, polyb, he_off, he_edge, he_flags, vtype, cent};
     GcsStateView St = {xc, mu, z, x_v, z_v, y_v, 0, 0.0, 0.0};
     GcsPerfLayout L = gcs_perf_layout(cap_blocks, cap_verts, cap_cone);
-    GcsPerfTables T = {vclass, cls_tab, cone_off, cone, blk_off, blk_he, blk_edge, blk_info, tile_voff, ntiles, tstate, tn, inner_iters, alpha, kappa, theta, edge_delta};
+    // the packed descriptors gcsadmm_enable_perf builds on the host (same rules)
+    const int nB = blk_off[nV];
+    int *brec = (int *)calloc(4 * (size_t)(nB ? nB : 1), sizeof(int)), *vrec = (int *)calloc(GCS_VI_N * (size_t)nV, sizeof(int)), *trec = (int *)calloc(8 * (size_t)ntiles, sizeof(int));
+    for (int b = 0; b < nB; ++b) { brec[4 * b] = blk_he[b]; brec[4 * b + 1] = blk_info[b]; brec[4 * b + 2] = blk_edge[b]; }
+    for (int t = 0; t < ntiles; ++t) {
+        const int a = tile_voff[t], b = tile_voff[t + 1];
+        int *r = trec + 8 * t;
+        r[0] = a; r[1] = b - a; r[2] = blk_off[a]; r[3] = blk_off[b] - blk_off[a]; r[4] = cone_off[a]; r[5] = cone_off[b] - cone_off[a];
+        r[6] = he_off[a]; r[7] = he_off[b] - he_off[a];
+        for (int hh = he_off[a]; hh < he_off[b]; ++hh) if (he_flags[hh] & GCS_HE_ZERO) r[7] |= 1 << 30;
+        for (int v = a; v < b; ++v) {
+            int *w = vrec + GCS_VI_N * v;
+            w[GCS_VI_CONE] = cone_off[v] - cone_off[a]; w[GCS_VI_NV] = cone_off[v + 1] - cone_off[v]; w[GCS_VI_CLS] = vclass[v];
+            w[GCS_VI_TERM] = vtype[v] != GCS_VT_GENERIC; w[GCS_VI_BLK] = blk_off[v] - blk_off[a]; w[GCS_VI_NB] = blk_off[v + 1] - blk_off[v];
+            w[GCS_VI_ACTIVE] = 0; w[GCS_VI_HE] = he_off[v] - he_off[a];
+        }
+    }
+    GcsPerfTables T = {vclass, cls_tab, cone_off, cone, blk_off, brec, vrec, trec, ntiles, tstate, tn, inner_iters, alpha, kappa, theta, edge_delta};
     Ctrl ctrl;
     memset(&ctrl, 0, sizeof ctrl);
     ctrl.rho = rho; ctrl.mu_scale = mu_scale;
@@ -61,6 +78,7 @@ extern "C" int gcsemu_vertex_update_perf_all(int nV, int nE, const int *poly_off
         }
         free(S);
     }
+    free(brec); free(vrec); free(trec);
     for (int v = 0; v < nV; ++v)      // what perf_init_dead_kernel writes once on the device
         if (vtype[v] == GCS_VT_DEAD) { for (int k = 0; k < 4; ++k) { z_v[4 * v + k] = 0.0; x_v[4 * v + k] = cent[2 * v + (k & 1)]; } y_v[v] = 0.0; }
     return ntiles;

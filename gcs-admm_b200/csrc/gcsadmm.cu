@@ -73,7 +73,7 @@ struct GcsHandle {
     long long n_x, n_mu;
     int dcap, mcap;
     GcsScratchLayout L;
-    int k1_smem, k1_blocks, k1_warps, edge_blocks;
+    int k1_smem, k1_blocks, k1_warps, edge_blocks, edge_per_edge;
     // device
     int *poly_off, *he_off, *he_edge, *edge_he_tail, *edge_he_head;
     double *polyA, *polyb, *cent;
@@ -91,11 +91,11 @@ struct GcsHandle {
     cudaEvent_t ev[4];
     void *flush_buf; size_t flush_bytes;
     // perf mode (inexact x-update by K closed-form splitting iterations)
-    int perf_on, perf_smem;
+    int perf_on, perf_smem, perf_threads;
     GcsPerfLayout PL;
     GcsPerfTables PT;
     long long perf_nblocks;
-    int *p_vclass, *p_cone_off, *p_blk_off, *p_blk_he, *p_blk_edge, *p_blk_info, *p_tile_voff; double *p_cls_tab, *p_cone, *p_tstate, *p_tn, *p_edge_delta;
+    int *p_vclass, *p_cone_off, *p_blk_off, *p_blk_rec, *p_vrec, *p_tile_rec; double *p_cls_tab, *p_cone, *p_tstate, *p_tn, *p_edge_delta;
     // one CUDA graph per chunk of `check_every` iterations (own stream only)
     cudaGraphExec_t graph_exec; int graph_iters;
     // peer mode (multi-GPU over NVLink peer memory, one process per GPU): see the "peer mode" section
@@ -296,7 +296,7 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
         for (int c = 0; c < 5; ++c) { xt[c] = pt[c]; xh[c] = ph[c]; zo[c] = z[5 * (size_t)e + c]; }
 #pragma unroll
         for (int c = 0; c < 5; ++c) { mt[c] = ot ? mu[5 * (size_t)ht + c] : 0.0; mh[c] = oh ? mu[5 * (size_t)hh + c] : 0.0; }
-        const double d0 = edge_delta[2 * (size_t)e], d1 = edge_delta[2 * (size_t)e + 1];
+        const double d0 = edge_delta ? edge_delta[2 * (size_t)e] : 0.0, d1 = edge_delta ? edge_delta[2 * (size_t)e + 1] : 0.0;
         const double w = edge_counted ? (double)edge_counted[e] : 1.0;
         double zn[5], bz[5];
         zn[0] = 0.5 * (xh[0] + xt[0]); zn[1] = 0.5 * (xh[1] + xt[1]);
@@ -489,9 +489,9 @@ static int reset_ctrl(GcsHandle *h) {
 }
 
 static void free_perf(GcsHandle *h) {
-    void *pp[] = {h->p_vclass, h->p_cone_off, h->p_blk_off, h->p_blk_he, h->p_blk_edge, h->p_blk_info, h->p_tile_voff, h->p_cls_tab, h->p_cone, h->p_tstate, h->p_tn, h->p_edge_delta};
+    void *pp[] = {h->p_vclass, h->p_cone_off, h->p_blk_off, h->p_blk_rec, h->p_vrec, h->p_tile_rec, h->p_cls_tab, h->p_cone, h->p_tstate, h->p_tn, h->p_edge_delta};
     for (void *q : pp) if (q) cudaFree(q);
-    h->p_vclass = h->p_cone_off = h->p_blk_off = h->p_blk_he = h->p_blk_edge = h->p_blk_info = h->p_tile_voff = nullptr;
+    h->p_vclass = h->p_cone_off = h->p_blk_off = h->p_blk_rec = h->p_vrec = h->p_tile_rec = nullptr;
     h->p_cls_tab = h->p_cone = h->p_tstate = h->p_tn = h->p_edge_delta = nullptr;
     h->perf_on = 0;
 }
@@ -570,7 +570,10 @@ static int create_impl(GcsHandle *h, const GcsGraph *g) {
     h->k1_blocks = (g->nV + h->k1_warps - 1) / h->k1_warps;
     {   // edge kernel: 5 threads per edge, a whole number of waves of resident blocks (8 blocks of 256 threads per SM)
         const long long need = (5ll * g->nE + EDGE_THREADS - 1) / EDGE_THREADS;
-        const long long cap = (long long)prop.multiProcessorCount * 6 * 4;   // 4 waves of the 6 resident blocks per SM
+        const char *bps = getenv("GCS_EDGE_BLOCKS_PER_SM");                  // tuning knob (default: 4 waves of the 6 resident blocks per SM)
+        const long long cap = (long long)prop.multiProcessorCount * (bps && atoi(bps) > 0 ? atoi(bps) : 24);
+        const char *ek = getenv("GCS_EDGE_KERNEL");
+        h->edge_per_edge = ek && !strcmp(ek, "per_edge");
         h->edge_blocks = (int)(need < 1 ? 1 : (need > cap ? cap : need));
     }
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -670,7 +673,7 @@ static GcsStateView state_view(const GcsHandle *h) {
 }
 static int launch_k1(GcsHandle *h) {
     if (h->perf_on) {
-        vertex_perf_kernel<<<h->PT.ntiles, GCS_PERF_THREADS, h->perf_smem, h->stream>>>(graph_view(h), state_view(h), h->PT, h->ctrl, h->vprob, h->PL);
+        vertex_perf_kernel<<<h->PT.ntiles, h->perf_threads, h->perf_smem, h->stream>>>(graph_view(h), state_view(h), h->PT, h->ctrl, h->vprob, h->PL);
         return 0;
     }
     vertex_kernel<<<h->k1_blocks, h->k1_warps * 32, h->k1_smem, h->stream>>>(graph_view(h), state_view(h), h->ctrl, h->vprob, h->L, h->p.inner_tol, h->p.inner_max_iter);
@@ -684,11 +687,11 @@ static int launch_edge(GcsHandle *h, int fuse) {
                                                                      h->ctrl, h->p, h->prob_nx, h->prob_nmu, h->hist, h->hist_cap);
         return 0;
     }
-    if (h->perf_on && h->p_edge_delta) {      // local frames
+    if ((h->perf_on && h->p_edge_delta) || (h->edge_per_edge && h->p.outer_alpha == 1.0)) {      // local frames (or the one-thread-per-edge variant by request)
         int blocks = (h->nE + EDGE_THREADS - 1) / EDGE_THREADS;
         if (blocks > h->edge_blocks) blocks = h->edge_blocks;
         if (blocks < 1) blocks = 1;
-        edge_frames_kernel<<<blocks, EDGE_THREADS, 0, h->stream>>>(h->nE, h->nHown, h->edge_he_tail, h->edge_he_head, h->edge_counted, h->p_edge_delta, h->xc, h->mu,
+        edge_frames_kernel<<<blocks, EDGE_THREADS, 0, h->stream>>>(h->nE, h->nHown, h->edge_he_tail, h->edge_he_head, h->edge_counted, h->perf_on ? h->p_edge_delta : nullptr, h->xc, h->mu,
                                                                    h->z, h->ctrl, h->partials, h->ticket, fuse, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, h->nHghost, h->PV_dev);
         return 0;
     }
@@ -1037,17 +1040,45 @@ extern "C" int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *c) {
     if (!rc) rc = upload(&h->p_cone_off, c->cone_off, (size_t)h->nV + 1);
     if (!rc) rc = upload(&h->p_cone, c->cone, GCS_CONE_REC * ncone);
     if (!rc) rc = upload(&h->p_blk_off, c->blk_off, (size_t)h->nV + 1);
-    if (!rc) rc = upload(&h->p_blk_he, c->blk_he, (size_t)c->n_blocks);
-    if (!rc) rc = upload(&h->p_blk_info, c->blk_info, (size_t)c->n_blocks);
-    if (!rc) {        // edge of every block's half-edge, so that the kernel's gather has one dependent load less
-        int *be = (int *)malloc(sizeof(int) * (size_t)(c->n_blocks > 0 ? c->n_blocks : 1)), *he = (int *)malloc(sizeof(int) * (size_t)(h->nHown > 0 ? h->nHown : 1));
-        if (!be || !he) { free(be); free(he); free_perf(h); return set_err(GCS_E_NOMEM, "out of host memory%s", ""); }
-        cudaMemcpy(he, h->he_edge, sizeof(int) * (size_t)h->nHown, cudaMemcpyDeviceToHost);
-        for (int b = 0; b < c->n_blocks; ++b) be[b] = c->blk_he[b] >= 0 ? he[c->blk_he[b]] : -1;
-        rc = upload(&h->p_blk_edge, be, (size_t)c->n_blocks);
-        free(be); free(he);
+    if (!rc) {
+        // packed descriptors the kernel stages with bulk copies: 4 ints per block, GCS_VI_N ints per vertex, 8 ints per tile
+        const size_t nB = (size_t)c->n_blocks, nVt = (size_t)h->nV, nT = (size_t)c->n_tiles;
+        int *brec = (int *)calloc(4 * (nB ? nB : 1), sizeof(int)), *vrec = (int *)calloc(GCS_VI_N * nVt, sizeof(int)), *trec = (int *)calloc(8 * nT, sizeof(int));
+        int *he_edge = (int *)malloc(sizeof(int) * (size_t)(h->nHown > 0 ? h->nHown : 1)), *he_off = (int *)malloc(sizeof(int) * (nVt + 1));
+        unsigned char *vtype = (unsigned char *)malloc(nVt), *he_flags = (unsigned char *)malloc((size_t)(h->nHown > 0 ? h->nHown : 1));
+        int *vprob = (int *)calloc(nVt, sizeof(int));
+        if (!brec || !vrec || !trec || !he_edge || !he_off || !vtype || !he_flags || !vprob) rc = set_err(GCS_E_NOMEM, "out of host memory%s", "");
+        if (!rc) {
+            cudaMemcpy(he_edge, h->he_edge, sizeof(int) * (size_t)h->nHown, cudaMemcpyDeviceToHost);
+            cudaMemcpy(he_off, h->he_off, sizeof(int) * (nVt + 1), cudaMemcpyDeviceToHost);
+            cudaMemcpy(vtype, h->vtype, nVt, cudaMemcpyDeviceToHost);
+            cudaMemcpy(he_flags, h->he_flags, (size_t)h->nHown, cudaMemcpyDeviceToHost);
+            if (h->vprob) cudaMemcpy(vprob, h->vprob, sizeof(int) * nVt, cudaMemcpyDeviceToHost);
+            for (size_t b = 0; b < nB; ++b) {
+                brec[4 * b] = c->blk_he[b]; brec[4 * b + 1] = c->blk_info[b]; brec[4 * b + 2] = c->blk_he[b] >= 0 ? he_edge[c->blk_he[b]] : -1;
+            }
+            for (int t = 0; t < c->n_tiles; ++t) {
+                const int a = c->tile_voff[t], b = c->tile_voff[t + 1];
+                int *r = trec + 8 * (size_t)t;
+                r[0] = a; r[1] = b - a; r[2] = c->blk_off[a]; r[3] = c->blk_off[b] - c->blk_off[a];
+                r[4] = c->cone_off[a]; r[5] = c->cone_off[b] - c->cone_off[a]; r[6] = he_off[a]; r[7] = he_off[b] - he_off[a];
+                bool zero = false;
+                for (int hh = he_off[a]; hh < he_off[b]; ++hh) zero = zero || (he_flags[hh] & GCS_HE_FLAG_ZERO);
+                if (zero) r[7] |= 1 << 30;
+                for (int v = a; v < b; ++v) {
+                    int *w = vrec + GCS_VI_N * (size_t)v;
+                    w[GCS_VI_CONE] = c->cone_off[v] - c->cone_off[a]; w[GCS_VI_NV] = c->cone_off[v + 1] - c->cone_off[v];
+                    w[GCS_VI_CLS] = c->vclass[v]; w[GCS_VI_TERM] = vtype[v] != GCS_VT_GENERIC;
+                    w[GCS_VI_BLK] = c->blk_off[v] - c->blk_off[a]; w[GCS_VI_NB] = c->blk_off[v + 1] - c->blk_off[v];
+                    w[GCS_VI_ACTIVE] = vprob[v]; w[GCS_VI_HE] = he_off[v] - he_off[a];
+                }
+            }
+            rc = upload(&h->p_blk_rec, brec, 4 * nB);
+            if (!rc) rc = upload(&h->p_vrec, vrec, GCS_VI_N * nVt);
+            if (!rc) rc = upload(&h->p_tile_rec, trec, 8 * nT);
+        }
+        free(brec); free(vrec); free(trec); free(he_edge); free(he_off); free(vtype); free(he_flags); free(vprob);
     }
-    if (!rc) rc = upload(&h->p_tile_voff, c->tile_voff, (size_t)c->n_tiles + 1);
     if (!rc) rc = upload(&h->p_tstate, (const double *)nullptr, 12 * (size_t)c->n_blocks);
     if (!rc) rc = upload(&h->p_tn, (const double *)nullptr, 2 * (size_t)h->nV);
     if (!rc && c->edge_delta) rc = upload(&h->p_edge_delta, c->edge_delta, 2 * (size_t)h->nE);
@@ -1055,7 +1086,7 @@ extern "C" int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *c) {
     h->perf_nblocks = c->n_blocks;
     h->PL = gcs_perf_layout(c->cap_blocks, c->cap_verts, c->cap_cone);
     h->PT.vclass = h->p_vclass; h->PT.cls_tab = h->p_cls_tab; h->PT.cone_off = h->p_cone_off; h->PT.cone = h->p_cone;
-    h->PT.blk_off = h->p_blk_off; h->PT.blk_he = h->p_blk_he; h->PT.blk_edge = h->p_blk_edge; h->PT.blk_info = h->p_blk_info; h->PT.tile_voff = h->p_tile_voff;
+    h->PT.blk_off = h->p_blk_off; h->PT.blk_rec = h->p_blk_rec; h->PT.vrec = h->p_vrec; h->PT.tile_rec = h->p_tile_rec;
     h->PT.ntiles = c->n_tiles; h->PT.tstate = h->p_tstate; h->PT.tn = h->p_tn; h->PT.inner_iters = c->inner_iters;
     h->PT.alpha = c->alpha; h->PT.kappa = c->kappa; h->PT.theta = c->theta > 0.0 ? c->theta : 1.0; h->PT.edge_delta = h->p_edge_delta;
     cudaDeviceProp prop;
@@ -1063,6 +1094,7 @@ extern "C" int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *c) {
     const size_t bytes = (size_t)h->PL.total * sizeof(double);
     if (bytes > prop.sharedMemPerBlockOptin) { free_perf(h); return set_err(GCS_E_INVALID, "perf-mode tile too large for shared memory (a vertex of very high degree)%s", ""); }
     h->perf_smem = (int)bytes;
+    h->perf_threads = c->threads >= 32 && c->threads <= GCS_PERF_THREADS ? (c->threads / 32) * 32 : GCS_PERF_THREADS;
     CK(cudaFuncSetAttribute(vertex_perf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->perf_smem));
     CK(cudaFuncSetAttribute(vertex_perf_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     perf_init_dead_kernel<<<(h->nV + 255) / 256, 256, 0, h->stream>>>(graph_view(h), state_view(h));

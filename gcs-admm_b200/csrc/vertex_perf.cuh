@@ -55,10 +55,11 @@ struct GcsPerfTables {
     const int *cone_off;       // [nV+1] polygon vertices of vertex v: cone_off[v]..cone_off[v+1]
     const double *cone;        // GCS_CONE_REC doubles per polygon vertex (see gcs_cone_project)
     const int *blk_off;        // [nV+1] blocks of vertex v: its live half-edges in half-edge order, then (z_v, y_v)
-    const int *blk_he;         // [B] half-edge of the block, -1 for the (z_v, y_v) block
-    const int *blk_edge;       // [B] edge of that half-edge (-1 for the (z_v, y_v) block)
-    const int *blk_info;       // [B] bits 0-7: vertex index inside its tile | bits 8-9: group (0 in, 1 out, 2 z-block) | bit 10: 's' / 't'
-    const int *tile_voff;      // [ntiles+1]
+    const int *blk_rec;        // [B][4]: half-edge of the block (-1 for the (z_v, y_v) block) | descriptor: bits 0-7 vertex index inside its
+                               //         tile, bits 8-9 group (0 in, 1 out, 2 z-block), bit 10 's' / 't' | edge of the half-edge | 0
+    const int *vrec;           // [nV][GCS_VI_N]: the per-vertex descriptor the kernel keeps in shared memory (offsets relative to the tile)
+    const int *tile_rec;       // [ntiles][8]: first vertex, #vertices, first block, #blocks, first cone record, #records, first half-edge,
+                               //              #half-edges | bit 30 of #half-edges: the tile has forced-zero half-edges
     int ntiles;
     double *tstate;            // [B][4 pairs][3]  t = c + lam of every (point, flow) pair
     double *tn;                // [nV][2]          the same for the path-length item z_1 - z_2
@@ -79,7 +80,7 @@ struct GcsPerfLayout { int nb_cap, nvt_cap, cone_cap, tS, eS, cone, tnS, enS, T,
 #define GCS_VI_TERM 3
 #define GCS_VI_BLK 4      // first block, relative to the tile's
 #define GCS_VI_NB 5       // blocks (0: dead vertex)
-#define GCS_VI_ACTIVE 6   // its problem is still iterating
+#define GCS_VI_ACTIVE 6   // its problem is still iterating (the table holds the vertex's problem index here)
 #define GCS_VI_HE 7       // first half-edge, relative to the tile's
 #if defined(__CUDACC__)
 __host__ __device__
@@ -101,8 +102,9 @@ static inline GcsPerfLayout gcs_perf_layout(int nb_cap, int nvt_cap, int cone_ca
     L.cin = o; o += GCS_NCX * nvt_cap;
     L.cout = o; o += GCS_NCX * nvt_cap;
     L.vd = o; o += 2 * nvt_cap;
-    L.vi = o; o += (GCS_VI_N * nvt_cap + 1) / 2;
-    L.bi = o; o += nb_cap + (nb_cap + 1) / 2; // 3 ints per block: half-edge, descriptor, edge
+    o += o & 1;                               // bulk-copied int records: 16-byte aligned
+    L.vi = o; o += (GCS_VI_N * nvt_cap) / 2;
+    L.bi = o; o += 2 * nb_cap;                // 4 ints per block: half-edge, descriptor, edge, pad
     L.total = o + (o & 1);
     return L;
 }
@@ -184,7 +186,7 @@ __device__ __forceinline__ void gcs_fence_async_smem() { asm volatile("fence.pro
 #define GCS_PF 3   // consensus targets a thread keeps in registers between issuing their loads and using them (device build)
 
 // input k of the extended core of vertex vl:  r_x (4) | r_z, r_yv (5) | sum of r over the in-blocks (5) | over the out-blocks (5)
-GCS_DEV double gcs_core_input(const double *tS, const double *rS, const int *binfo, const int *w, int k, double kappa) {
+GCS_DEV double gcs_core_input(const double *tS, const double *rS, const int *brec, const int *w, int k, double kappa) {
     const int bl = w[GCS_VI_BLK], zb = bl + w[GCS_VI_NB] - 1;
     double s = 0.0;
     if (k < 4) {
@@ -192,7 +194,7 @@ GCS_DEV double gcs_core_input(const double *tS, const double *rS, const int *bin
     } else if (k < 9) s = rS[5 * zb + k - 4];
     else {
         const int g = k >= 14, tau = k - 9 - 5 * g;
-        for (int b = bl; b < zb; ++b) if (((binfo[b] >> 8) & 3) == g) s += rS[5 * b + tau];
+        for (int b = bl; b < zb; ++b) if (((brec[4 * b + 1] >> 8) & 3) == g) s += rS[5 * b + tau];
     }
     return s;
 }
@@ -216,35 +218,39 @@ GCS_DEV double gcs_target_z(const GcsStateView &St, const GcsPerfTables &T, int 
 // x-update of one tile of vertices in perf mode.  `bar` is an mbarrier in shared memory (device build only).
 GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const GcsPerfTables &T, const GcsPerfLayout &L,
                            double *S, int tile, Ctrl *ctrl_all, const int *vprob, unsigned long long *bar) {
-    const int v0 = T.tile_voff[tile], nvt = T.tile_voff[tile + 1] - v0;
-    const int b0 = T.blk_off[v0], nb = T.blk_off[v0 + nvt] - b0;
-    const int c0 = T.cone_off[v0], ncone = T.cone_off[v0 + nvt] - c0;
-    const int h0 = G.he_off[v0], nhe = G.he_off[v0 + nvt] - h0;
+    const int *tr = T.tile_rec + 8 * (size_t)tile;
+    const int v0 = tr[0], nvt = tr[1], b0 = tr[2], nb = tr[3], c0 = tr[4], ncone = tr[5], h0 = tr[6], nhe = tr[7] & 0x3fffffff;
+    const bool has_zero = (tr[7] >> 30) & 1;
     double *tS = S + L.tS, *eS = S + L.eS, *coneS = S + L.cone, *tnS = S + L.tnS, *enS = S + L.enS, *TS = S + L.T, *rS = S + L.r;
     double *cin = S + L.cin, *cout = S + L.cout, *vd = S + L.vd;
-    int *vi = (int *)(S + L.vi), *bhe = (int *)(S + L.bi), *binfo = bhe + L.nb_cap, *bedge = binfo + L.nb_cap;
-    // ---- P0: stage the tile: state / cone records by bulk copies, per-vertex and per-block descriptors by plain loads
+    int *vi = (int *)(S + L.vi), *brec = (int *)(S + L.bi);
+#define bhe(b) brec[4 * (b)]
+#define binfo(b) brec[4 * (b) + 1]
+#define bedge(b) brec[4 * (b) + 2]
+    // ---- P0: stage the tile with bulk copies: state, cone records, per-vertex and per-block descriptors (all contiguous per tile)
 #if defined(GCS_EMULATE)
     memcpy(tS, T.tstate + 12 * (size_t)b0, sizeof(double) * 12 * nb);
     memcpy(tnS, T.tn + 2 * (size_t)v0, sizeof(double) * 2 * nvt);
     memcpy(coneS, T.cone + GCS_CONE_REC * (size_t)c0, sizeof(double) * GCS_CONE_REC * ncone);
+    memcpy(vi, T.vrec + GCS_VI_N * (size_t)v0, sizeof(int) * GCS_VI_N * nvt);
+    memcpy(brec, T.blk_rec + 4 * (size_t)b0, sizeof(int) * 4 * nb);
 #else
     if (threadIdx.x == 0) {
         gcs_mbar_init(bar, 1);
-        gcs_mbar_expect_tx(bar, (unsigned)(sizeof(double) * (12 * nb + 2 * nvt + GCS_CONE_REC * ncone)));
+        gcs_mbar_expect_tx(bar, (unsigned)(sizeof(double) * (12 * nb + 2 * nvt + GCS_CONE_REC * ncone) + sizeof(int) * (GCS_VI_N * nvt + 4 * nb)));
+        gcs_bulk_g2s(vi, T.vrec + GCS_VI_N * (size_t)v0, (unsigned)(sizeof(int) * GCS_VI_N * nvt), bar);
+        if (nb) gcs_bulk_g2s(brec, T.blk_rec + 4 * (size_t)b0, (unsigned)(sizeof(int) * 4 * nb), bar);
         if (nb) gcs_bulk_g2s(tS, T.tstate + 12 * (size_t)b0, (unsigned)(sizeof(double) * 12 * nb), bar);
         gcs_bulk_g2s(tnS, T.tn + 2 * (size_t)v0, (unsigned)(sizeof(double) * 2 * nvt), bar);
         if (ncone) gcs_bulk_g2s(coneS, T.cone + GCS_CONE_REC * (size_t)c0, (unsigned)(sizeof(double) * GCS_CONE_REC * ncone), bar);
     }
+    __syncthreads();               // the barrier object is initialised before anybody polls it
+    gcs_mbar_wait(bar, 0);
 #endif
-    GCS_CTA_LOOP(i, nvt) {
-        const int v = v0 + i;
-        Ctrl *c = ctrl_all + (vprob ? vprob[v] : 0);
+    GCS_CTA_LOOP(i, nvt) {         // rho, mu_scale and the stop flag of the vertex's problem
         int *w = vi + GCS_VI_N * i;
-        w[GCS_VI_CONE] = T.cone_off[v] - c0; w[GCS_VI_NV] = T.cone_off[v + 1] - T.cone_off[v];
-        w[GCS_VI_CLS] = T.vclass[v]; w[GCS_VI_TERM] = G.vtype[v] != GCS_VT_GENERIC;
-        w[GCS_VI_BLK] = T.blk_off[v] - b0; w[GCS_VI_NB] = T.blk_off[v + 1] - T.blk_off[v];
-        w[GCS_VI_ACTIVE] = !(c->stop && !c->ignore_stop); w[GCS_VI_HE] = G.he_off[v] - h0;
+        Ctrl *c = ctrl_all + (vprob ? w[GCS_VI_ACTIVE] : 0);
+        w[GCS_VI_ACTIVE] = !(c->stop && !c->ignore_stop);
         vd[2 * i] = c->rho; vd[2 * i + 1] = c->mu_scale;
         if (vprob && w[GCS_VI_ACTIVE] && w[GCS_VI_NB]) {
 #if defined(GCS_EMULATE)
@@ -254,8 +260,6 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
 #endif
         }
     }
-    GCS_CTA_LOOP(b, nb) { bhe[b] = T.blk_he[b0 + b]; binfo[b] = T.blk_info[b0 + b]; bedge[b] = T.blk_edge[b0 + b]; }
-    GCS_CTA_SYNC();
     // ---- P1: consensus targets  T = z_e + mu_h  of the live half-edges.  Device build: the gathers are only ISSUED here — the
     // values stay in registers while the thread does its cone projections and are combined after them, so the DRAM / L2
     // latency of the gather hides behind the c-step instead of stalling the block; forced-zero half-edges are answered directly
@@ -266,12 +270,13 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
         const int q = threadIdx.x + j * blockDim.x;
         pz[j] = 0.0; pm[j] = 0.0;
         if (q < 5 * nb) {
-            const int b = q / 5, c = q - 5 * b, h = bhe[b];
-            if (h >= 0 && vi[GCS_VI_N * (binfo[b] & 255) + GCS_VI_ACTIVE]) { pz[j] = gcs_target_z(St, T, bedge[b], c, binfo[b]); pm[j] = St.mu[5 * (size_t)h + c]; }
+            const int b = q / 5, c = q - 5 * b, h = bhe(b);
+            if (h >= 0) { pz[j] = gcs_target_z(St, T, bedge(b), c, binfo(b)); pm[j] = St.mu[5 * (size_t)h + c]; }
         }
     }
 #endif
-    GCS_CTA_LOOP(q, 5 * nhe) {
+    GCS_CTA_SYNC();                // vd / ACTIVE of every vertex of the tile are in shared memory
+    if (has_zero) GCS_CTA_LOOP(q, 5 * nhe) {
         const int hl = q / 5, c = q - 5 * hl, h = h0 + hl, f = G.he_flags[h];
         if (!(f & GCS_HE_ZERO)) continue;
         int vl = 0;
@@ -282,15 +287,12 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
         if (c < 2 && !(f & GCS_HE_OUT)) x = St.z[5 * (size_t)G.he_edge[h] + c] + vd[2 * vl + 1] * St.mu[5 * (size_t)h + c];
         St.xc[5 * (size_t)h + c] = x;
     }
-#if !defined(GCS_EMULATE)
-    gcs_mbar_wait(bar, 0);
-#endif
     const double alpha = T.alpha, kappa = T.kappa;
     for (int it = 0; it < T.inner_iters; ++it) {
         const bool last = it + 1 == T.inner_iters;
         // ---- P2: c-step.  d = c - lam (what the v-step sees) replaces t in place; e = (1 - alpha) c + lam waits for the t-step
         GCS_CTA_LOOP(p, 4 * nb) {
-            const int b = p >> 2, info = binfo[b], vl = info & 255;
+            const int b = p >> 2, info = binfo(b), vl = info & 255;
             const int *w = vi + GCS_VI_N * vl;
             if (!w[GCS_VI_ACTIVE] || ((info >> 10) & (p & 1))) continue;       // 's' / 't' have no C2 / C4 pairs
             const double ms = it ? 1.0 : vd[2 * vl + 1];                      // sigma = kappa rho: lam rescales with mu (:705 / :708)
@@ -318,21 +320,21 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
 #pragma unroll
             for (int j = 0; j < GCS_PF; ++j) {
                 const int q = threadIdx.x + j * blockDim.x;
-                if (q < 5 * nb) TS[q] = pz[j] + vd[2 * (binfo[q / 5] & 255) + 1] * pm[j];
+                if (q < 5 * nb) TS[q] = pz[j] + vd[2 * (binfo(q / 5) & 255) + 1] * pm[j];
             }
             for (int q = threadIdx.x + GCS_PF * blockDim.x; q < 5 * nb; q += blockDim.x) {
 #else
             for (int q = 0; q < 5 * nb; ++q) {
 #endif
-                const int b = q / 5, c = q - 5 * b, h = bhe[b], vl = binfo[b] & 255;
+                const int b = q / 5, c = q - 5 * b, h = bhe(b), vl = binfo(b) & 255;
                 if (h < 0 || !vi[GCS_VI_N * vl + GCS_VI_ACTIVE]) continue;
-                TS[q] = gcs_target_z(St, T, bedge[b], c, binfo[b]) + vd[2 * vl + 1] * St.mu[5 * (size_t)h + c];
+                TS[q] = gcs_target_z(St, T, bedge(b), c, binfo(b)) + vd[2 * vl + 1] * St.mu[5 * (size_t)h + c];
             }
         }
         GCS_CTA_SYNC();
         // ---- P3: right-hand side of the v-step, in units of rho:  r = S'T - (eps / rho) e_y + kappa M'(d - m0)
         GCS_CTA_LOOP(q, 5 * nb) {
-            const int b = q / 5, tau = q - 5 * b, info = binfo[b], vl = info & 255, grp = (info >> 8) & 3;
+            const int b = q / 5, tau = q - 5 * b, info = binfo(b), vl = info & 255, grp = (info >> 8) & 3;
             if (!vi[GCS_VI_N * vl + GCS_VI_ACTIVE]) continue;
             const bool term = (info >> 10) & 1;
             const double *d = tS + 12 * b;                                    // pair (i, fam) at 3 (2 i + fam)
@@ -361,7 +363,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
         for (int vl = 0; vl < nvt; ++vl) {
             const int *w = vi + GCS_VI_N * vl;
             if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;
-            for (int k = 0; k < GCS_NCX; ++k) cin[GCS_NCX * vl + k] = gcs_core_input(tS, rS, binfo, w, k, kappa);
+            for (int k = 0; k < GCS_NCX; ++k) cin[GCS_NCX * vl + k] = gcs_core_input(tS, rS, brec, w, k, kappa);
             for (int k = 0; k < GCS_NCX; ++k) cout[GCS_NCX * vl + k] = gcs_core_output(T.cls_tab + (size_t)GCS_CLS_STRIDE * w[GCS_VI_CLS], cin + GCS_NCX * vl, k);
         }
 #else
@@ -369,7 +371,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
             const int *w = vi + GCS_VI_N * vl;
             const int k = threadIdx.x & 31;
             const bool on = w[GCS_VI_ACTIVE] && w[GCS_VI_NB] && k < GCS_NCX;
-            if (on) cin[GCS_NCX * vl + k] = gcs_core_input(tS, rS, binfo, w, k, kappa);
+            if (on) cin[GCS_NCX * vl + k] = gcs_core_input(tS, rS, brec, w, k, kappa);
             __syncwarp();
             if (on) cout[GCS_NCX * vl + k] = gcs_core_output(T.cls_tab + (size_t)GCS_CLS_STRIDE * w[GCS_VI_CLS], cin + GCS_NCX * vl, k);
         }
@@ -377,7 +379,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
         GCS_CTA_SYNC();
         // ---- P6: block variables  u = dinv r + beta  (in place of r); vertex outputs on the last pass
         GCS_CTA_LOOP(q, 5 * nb) {
-            const int b = q / 5, tau = q - 5 * b, info = binfo[b], vl = info & 255, grp = (info >> 8) & 3;
+            const int b = q / 5, tau = q - 5 * b, info = binfo(b), vl = info & 255, grp = (info >> 8) & 3;
             const int *w = vi + GCS_VI_N * vl;
             if (!w[GCS_VI_ACTIVE]) continue;
             const double *co = cout + GCS_NCX * vl;
@@ -399,7 +401,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
         GCS_CTA_SYNC();
         // ---- P7: t-step  t = alpha (M u + m0) + e;  on the last pass the consensus copies xc in edge-canonical order (:492-522)
         GCS_CTA_LOOP(p, 4 * nb) {
-            const int b = p >> 2, i = (p >> 1) & 1, fam = p & 1, info = binfo[b], vl = info & 255;
+            const int b = p >> 2, i = (p >> 1) & 1, fam = p & 1, info = binfo(b), vl = info & 255;
             if (!vi[GCS_VI_N * vl + GCS_VI_ACTIVE] || ((info >> 10) & fam)) continue;
             const double *ub = rS + 5 * b, *x = cout + GCS_NCX * vl + 2 * i, *e = eS + 3 * p;
             double p0 = ub[2 * i], p1 = ub[2 * i + 1], p2 = ub[4];
@@ -415,7 +417,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
         }
         if (last) {
             GCS_CTA_LOOP(q, 5 * nb) {
-                const int b = q / 5, c = q - 5 * b, h = bhe[b], info = binfo[b], vl = info & 255;
+                const int b = q / 5, c = q - 5 * b, h = bhe(b), info = binfo(b), vl = info & 255;
                 if (h < 0 || !vi[GCS_VI_N * vl + GCS_VI_ACTIVE]) continue;
                 double x;
                 if ((info >> 8) & 1) x = rS[q];                                 // out-edge: own first point | other's first point == own second point (C5)
@@ -440,4 +442,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
         if (!vprob) atomicAdd(&ctrl_all->inner_iters, (unsigned long long)T.inner_iters * (unsigned long long)nvt);
     }
 #endif
+#undef bhe
+#undef binfo
+#undef bedge
 }

@@ -48,7 +48,7 @@ class GcsPerfConfig(C.Structure):
                 ("vclass", C.c_void_p), ("cls_tab", C.c_void_p), ("cone_off", C.c_void_p), ("cone", C.c_void_p),
                 ("n_blocks", C.c_int32), ("blk_off", C.c_void_p), ("blk_he", C.c_void_p), ("blk_info", C.c_void_p),
                 ("n_tiles", C.c_int32), ("tile_voff", C.c_void_p),
-                ("cap_blocks", C.c_int32), ("cap_verts", C.c_int32), ("cap_cone", C.c_int32),
+                ("cap_blocks", C.c_int32), ("cap_verts", C.c_int32), ("cap_cone", C.c_int32), ("threads", C.c_int32),
                 ("theta", C.c_double), ("edge_delta", C.c_void_p)]
 
 
@@ -205,6 +205,7 @@ class Solver:
         c.n_blocks, c.n_tiles = int(keep["blk_he"].shape[0]), int(keep["tile_voff"].shape[0] - 1)
         c.cap_blocks, c.cap_verts, c.cap_cone = int(T["caps"]["nb"]), int(T["caps"]["nvt"]), int(T["caps"]["cone"])
         c.theta = float(T.get("theta", 1.0))
+        c.threads = int(T.get("threads", 0))
         if T.get("edge_delta") is not None:
             keep["edge_delta"] = np.ascontiguousarray(T["edge_delta"], f64)
             c.edge_delta = _ptr(keep["edge_delta"])

@@ -270,8 +270,12 @@ def structured_vstep(T, r):
     return u
 
 
-# limits of one tile (= one thread block of the perf kernel): consecutive vertices are packed greedily up to these
-TILE_BLOCKS, TILE_VERTS, TILE_CONE, TILE_HE = 64, 32, 160, 128
+# limits of one tile (= one thread block of the perf kernel): consecutive vertices are packed greedily up to these.
+# TILE_BLOCKS blocks = 4 * TILE_BLOCKS (point, flow) pairs = one pair per thread of a block of TILE_THREADS threads.
+import os as _os
+TILE_BLOCKS = int(_os.environ.get("GCS_TILE_BLOCKS", "64"))
+TILE_THREADS = int(_os.environ.get("GCS_TILE_THREADS", str(min(256, 4 * TILE_BLOCKS))))
+TILE_VERTS, TILE_CONE, TILE_HE = 32, 160, 128
 
 
 def perf_tables(g, kappa=1.0, cone=None, theta=1.0, frames="global", edge_delta=None):
@@ -337,7 +341,7 @@ def perf_tables(g, kappa=1.0, cone=None, theta=1.0, frames="global", edge_delta=
                 he=int((np.asarray(g.he_off, np.int64)[tv1] - np.asarray(g.he_off, np.int64)[tv0]).max()) if nV else 1)
     return dict(vclass=vclass, cls_tab=cls_tab, cone_off=np.asarray(cone_off, dtype=np.int32), cone=np.ascontiguousarray(cone_rec),
                 blk_off=blk_off.astype(np.int32), blk_he=blk_he, blk_info=blk_info, tile_voff=tile_voff.astype(np.int32),
-                caps=caps, classes=keys, kappa=float(kappa), theta=float(theta), edge_delta=edge_delta, frames=frames)
+                caps=caps, classes=keys, kappa=float(kappa), theta=float(theta), edge_delta=edge_delta, frames=frames, threads=TILE_THREADS)
 
 
 def _greedy_tiles(nblk, he_cnt, cone_cnt):

@@ -171,6 +171,7 @@ typedef struct GcsPerfConfig {
     int32_t n_tiles;             /* a tile = the consecutive vertices one thread block works on */
     const int32_t *tile_voff;    /* [n_tiles+1] */
     int32_t cap_blocks, cap_verts, cap_cone;   /* largest tile: blocks, vertices, cone records (sizes the shared memory) */
+    int32_t threads;             /* threads per tile's thread block (0 = 256; a multiple of 32 up to 256 — pairs of the tile's blocks) */
     double theta;                /* penalty of the flow scalars = theta * rho (0 or 1: the reference's single rho) */
     const double *edge_delta;    /* NULL: global coordinates.  [nE][2] = cent[tail] - cent[head]: LOCAL FRAMES — every vertex program runs in
                                     coordinates centred on its own region (the cone records must be built from the shifted polygons), the two
