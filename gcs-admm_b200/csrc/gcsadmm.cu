@@ -570,10 +570,11 @@ static int create_impl(GcsHandle *h, const GcsGraph *g) {
     h->k1_blocks = (g->nV + h->k1_warps - 1) / h->k1_warps;
     {   // edge kernel: 5 threads per edge, a whole number of waves of resident blocks (8 blocks of 256 threads per SM)
         const long long need = (5ll * g->nE + EDGE_THREADS - 1) / EDGE_THREADS;
-        const char *bps = getenv("GCS_EDGE_BLOCKS_PER_SM");                  // tuning knob (default: 4 waves of the 6 resident blocks per SM)
-        const long long cap = (long long)prop.multiProcessorCount * (bps && atoi(bps) > 0 ? atoi(bps) : 24);
-        const char *ek = getenv("GCS_EDGE_KERNEL");
-        h->edge_per_edge = ek && !strcmp(ek, "per_edge");
+        // measured on the 100k-vertex grid (profiles/r02_edge_variants.txt): one thread per edge with 4 blocks per SM 55 us,
+        // one thread per (edge, scalar) 68 us (6 blocks per SM) .. 84 us (24); the env variables are tuning knobs
+        const char *bps = getenv("GCS_EDGE_BLOCKS_PER_SM"), *ek = getenv("GCS_EDGE_KERNEL");
+        h->edge_per_edge = !(ek && !strcmp(ek, "per_scalar"));
+        const long long cap = (long long)prop.multiProcessorCount * (bps && atoi(bps) > 0 ? atoi(bps) : (h->edge_per_edge ? 4 : 6));
         h->edge_blocks = (int)(need < 1 ? 1 : (need > cap ? cap : need));
     }
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));

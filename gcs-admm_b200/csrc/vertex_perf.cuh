@@ -207,6 +207,34 @@ GCS_DEV double gcs_core_output(const double *tab, const double *in, int k) {
     return s0 + s1 + gk[GCS_NCX - 1] * in[GCS_NCX - 1];
 }
 
+// right-hand side r[q] of block-variable q = 5 b + tau of vertex vl (see P3 in gcs_perf_tile); d = c - lam of the block's pairs
+GCS_DEV double gcs_rhs(const GcsPerfTables &T, const double *tS, const double *TS, const double *tnS, const int *brec, int q, int vl, double rho, double kappa) {
+    const int b = q / 5, tau = q - 5 * b, info = brec[4 * b + 1], grp = (info >> 8) & 3;
+    const bool term = (info >> 10) & 1;
+    const double *d = tS + 12 * b;                                    // pair (i, fam) at 3 (2 i + fam)
+    double val;
+    if (tau < 4) {
+        const int i = tau >> 1, c = tau & 1;
+        val = d[6 * i + c];
+        if (!term) val -= d[6 * i + 3 + c];
+        val *= kappa;
+        if (grp == 1) val += TS[q];                                    // out-edge: both points carry the rho-quadratic
+        else if (grp == 0) { if (tau < 2) val += TS[q + 2]; }          // in-edge: own first point (edge-canonical slots 2, 3)
+        else val += (i ? -kappa : kappa) * tnS[2 * vl + c];            // (z_v, y_v) block: the path-length item
+    } else {
+        val = d[2] + d[8];
+        if (!term) val += (1.0 - d[5]) + (1.0 - d[11]);
+        val *= kappa;
+        if (grp < 2) val += T.theta * TS[q] - GCS_EDGE_PENALTY / rho;
+    }
+    return val;
+}
+// block variable tau of block b after the v-step:  u = dinv r + beta  (edge blocks),  (z_v, y_v) itself for the vertex's own block
+GCS_DEV double gcs_block_u(const double *rS, const double *co, const double *tab, int info, int b, int tau) {
+    const int grp = (info >> 8) & 3;
+    return grp == 2 ? co[4 + tau] : tab[GCS_CLS_DINV + 5 * grp + tau] * rS[5 * b + tau] + co[9 + 5 * grp + tau];
+}
+
 // consensus target of scalar c of half-edge h (block descriptor `info`) before the dual is added:  (B z_e)[c]
 GCS_DEV double gcs_target_z(const GcsStateView &St, const GcsPerfTables &T, int e, int c, int info) {
     double zc = St.z[5 * (size_t)e + c];
@@ -332,37 +360,15 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
             }
         }
         GCS_CTA_SYNC();
-        // ---- P3: right-hand side of the v-step, in units of rho:  r = S'T - (eps / rho) e_y + kappa M'(d - m0)
-        GCS_CTA_LOOP(q, 5 * nb) {
-            const int b = q / 5, tau = q - 5 * b, info = binfo(b), vl = info & 255, grp = (info >> 8) & 3;
-            if (!vi[GCS_VI_N * vl + GCS_VI_ACTIVE]) continue;
-            const bool term = (info >> 10) & 1;
-            const double *d = tS + 12 * b;                                    // pair (i, fam) at 3 (2 i + fam)
-            double val;
-            if (tau < 4) {
-                const int i = tau >> 1, c = tau & 1;
-                val = d[6 * i + c];
-                if (!term) val -= d[6 * i + 3 + c];
-                val *= kappa;
-                if (grp == 1) val += TS[q];                                    // out-edge: both points carry the rho-quadratic
-                else if (grp == 0) { if (tau < 2) val += TS[q + 2]; }          // in-edge: own first point (edge-canonical slots 2, 3)
-                else val += (i ? -kappa : kappa) * tnS[2 * vl + c];            // (z_v, y_v) block: the path-length item
-            } else {
-                val = d[2] + d[8];
-                if (!term) val += (1.0 - d[5]) + (1.0 - d[11]);
-                val *= kappa;
-                if (grp < 2) val += T.theta * TS[q] - GCS_EDGE_PENALTY / vd[2 * vl];
-            }
-            rS[q] = val;
-        }
-        GCS_CTA_SYNC();
-        // ---- P4 + P5: extended core of every vertex: its 19 inputs (r_x, r_z, r_yv, sums of r over the in- and the out-blocks),
-        // then (x, z_v, y_v, beta_in, beta_out) = G (inputs) + g0.  Device build: one warp per vertex, lane k owns input and
-        // output k, so the two steps are separated by a warp barrier only
+        // ---- P3 + P4 + P5, one warp per vertex (device build), so that only warp barriers separate them:
+        //   P3  right-hand side of the v-step in units of rho,  r = S'T - (eps / rho) e_y + kappa M'(d - m0),  for the vertex's blocks
+        //   P4  the 19 inputs of its extended core (r_x, r_z, r_yv, sums of r over the in- and the out-blocks)
+        //   P5  (x, z_v, y_v, beta_in, beta_out) = G (inputs) + g0
 #if defined(GCS_EMULATE)
         for (int vl = 0; vl < nvt; ++vl) {
             const int *w = vi + GCS_VI_N * vl;
             if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;
+            for (int q = 5 * w[GCS_VI_BLK]; q < 5 * (w[GCS_VI_BLK] + w[GCS_VI_NB]); ++q) rS[q] = gcs_rhs(T, tS, TS, tnS, brec, q, vl, vd[2 * vl], kappa);
             for (int k = 0; k < GCS_NCX; ++k) cin[GCS_NCX * vl + k] = gcs_core_input(tS, rS, brec, w, k, kappa);
             for (int k = 0; k < GCS_NCX; ++k) cout[GCS_NCX * vl + k] = gcs_core_output(T.cls_tab + (size_t)GCS_CLS_STRIDE * w[GCS_VI_CLS], cin + GCS_NCX * vl, k);
         }
@@ -370,21 +376,32 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
         for (int vl = threadIdx.x >> 5; vl < nvt; vl += blockDim.x >> 5) {
             const int *w = vi + GCS_VI_N * vl;
             const int k = threadIdx.x & 31;
-            const bool on = w[GCS_VI_ACTIVE] && w[GCS_VI_NB] && k < GCS_NCX;
-            if (on) cin[GCS_NCX * vl + k] = gcs_core_input(tS, rS, brec, w, k, kappa);
+            if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;                    // warp-uniform
+            for (int q = 5 * w[GCS_VI_BLK] + k; q < 5 * (w[GCS_VI_BLK] + w[GCS_VI_NB]); q += 32) rS[q] = gcs_rhs(T, tS, TS, tnS, brec, q, vl, vd[2 * vl], kappa);
             __syncwarp();
-            if (on) cout[GCS_NCX * vl + k] = gcs_core_output(T.cls_tab + (size_t)GCS_CLS_STRIDE * w[GCS_VI_CLS], cin + GCS_NCX * vl, k);
+            if (k < GCS_NCX) cin[GCS_NCX * vl + k] = gcs_core_input(tS, rS, brec, w, k, kappa);
+            __syncwarp();
+            if (k < GCS_NCX) cout[GCS_NCX * vl + k] = gcs_core_output(T.cls_tab + (size_t)GCS_CLS_STRIDE * w[GCS_VI_CLS], cin + GCS_NCX * vl, k);
         }
 #endif
         GCS_CTA_SYNC();
-        // ---- P6: block variables  u = dinv r + beta  (in place of r); vertex outputs on the last pass
-        GCS_CTA_LOOP(q, 5 * nb) {
-            const int b = q / 5, tau = q - 5 * b, info = binfo(b), vl = info & 255, grp = (info >> 8) & 3;
+        // ---- P7: block variables  u = dinv r + beta  (evaluated where they are used), t-step  t = alpha (M u + m0) + e;  on the
+        // last pass the vertex outputs and the consensus copies xc in edge-canonical order (:492-522)
+        GCS_CTA_LOOP(p, 4 * nb) {
+            const int b = p >> 2, i = (p >> 1) & 1, fam = p & 1, info = binfo(b), vl = info & 255;
             const int *w = vi + GCS_VI_N * vl;
-            if (!w[GCS_VI_ACTIVE]) continue;
-            const double *co = cout + GCS_NCX * vl;
-            if (grp == 2) rS[q] = co[4 + tau];
-            else rS[q] = T.cls_tab[(size_t)GCS_CLS_STRIDE * w[GCS_VI_CLS] + GCS_CLS_DINV + 5 * grp + tau] * rS[q] + co[9 + 5 * grp + tau];
+            if (!w[GCS_VI_ACTIVE] || ((info >> 10) & fam)) continue;
+            const double *co = cout + GCS_NCX * vl, *tab = T.cls_tab + (size_t)GCS_CLS_STRIDE * w[GCS_VI_CLS], *e = eS + 3 * p;
+            double p0 = gcs_block_u(rS, co, tab, info, b, 2 * i), p1 = gcs_block_u(rS, co, tab, info, b, 2 * i + 1), p2 = gcs_block_u(rS, co, tab, info, b, 4);
+            if (fam) { p0 = co[2 * i] - p0; p1 = co[2 * i + 1] - p1; p2 = 1.0 - p2; }
+            double *t = tS + 3 * p;
+            t[0] = alpha * p0 + e[0]; t[1] = alpha * p1 + e[1]; t[2] = alpha * p2 + e[2];
+        }
+        GCS_CTA_LOOP(i, nvt) {
+            const int *w = vi + GCS_VI_N * i;
+            if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;
+            const double *zz = cout + GCS_NCX * i + 4;
+            tnS[2 * i] = alpha * (zz[0] - zz[2]) + enS[2 * i]; tnS[2 * i + 1] = alpha * (zz[1] - zz[3]) + enS[2 * i + 1];
         }
         if (last) {
             GCS_CTA_LOOP(q, 9 * nvt) {
@@ -397,31 +414,14 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
                     val += (k < 4 ? 1.0 : cout[GCS_NCX * vl + 8]) * G.cent[2 * v + (k & 1)];
                 if (k < 4) St.x_v[4 * v + k] = val; else if (k < 8) St.z_v[4 * v + k - 4] = val; else St.y_v[v] = val;
             }
-        }
-        GCS_CTA_SYNC();
-        // ---- P7: t-step  t = alpha (M u + m0) + e;  on the last pass the consensus copies xc in edge-canonical order (:492-522)
-        GCS_CTA_LOOP(p, 4 * nb) {
-            const int b = p >> 2, i = (p >> 1) & 1, fam = p & 1, info = binfo(b), vl = info & 255;
-            if (!vi[GCS_VI_N * vl + GCS_VI_ACTIVE] || ((info >> 10) & fam)) continue;
-            const double *ub = rS + 5 * b, *x = cout + GCS_NCX * vl + 2 * i, *e = eS + 3 * p;
-            double p0 = ub[2 * i], p1 = ub[2 * i + 1], p2 = ub[4];
-            if (fam) { p0 = x[0] - p0; p1 = x[1] - p1; p2 = 1.0 - p2; }
-            double *t = tS + 3 * p;
-            t[0] = alpha * p0 + e[0]; t[1] = alpha * p1 + e[1]; t[2] = alpha * p2 + e[2];
-        }
-        GCS_CTA_LOOP(i, nvt) {
-            const int *w = vi + GCS_VI_N * i;
-            if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;
-            const double *zz = cout + GCS_NCX * i + 4;
-            tnS[2 * i] = alpha * (zz[0] - zz[2]) + enS[2 * i]; tnS[2 * i + 1] = alpha * (zz[1] - zz[3]) + enS[2 * i + 1];
-        }
-        if (last) {
             GCS_CTA_LOOP(q, 5 * nb) {
                 const int b = q / 5, c = q - 5 * b, h = bhe(b), info = binfo(b), vl = info & 255;
-                if (h < 0 || !vi[GCS_VI_N * vl + GCS_VI_ACTIVE]) continue;
+                const int *w = vi + GCS_VI_N * vl;
+                if (h < 0 || !w[GCS_VI_ACTIVE]) continue;
+                const double *co = cout + GCS_NCX * vl, *tab = T.cls_tab + (size_t)GCS_CLS_STRIDE * w[GCS_VI_CLS];
                 double x;
-                if ((info >> 8) & 1) x = rS[q];                                 // out-edge: own first point | other's first point == own second point (C5)
-                else x = c < 2 ? TS[q] : (c < 4 ? rS[q - 2] : rS[q]);           // in-edge: other's first point is free -> its target | own first point
+                if ((info >> 8) & 1) x = gcs_block_u(rS, co, tab, info, b, c);      // out-edge: own first point | other's first point == own second point (C5)
+                else x = c < 2 ? TS[q] : gcs_block_u(rS, co, tab, info, b, c < 4 ? c - 2 : 4);   // in-edge: other's first point is free -> its target | own first point
                 St.xc[5 * (size_t)h + c] = x;
             }
         }
