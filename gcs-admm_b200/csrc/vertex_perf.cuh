@@ -246,6 +246,13 @@ GCS_DEV double gcs_target_z(const GcsStateView &St, const GcsPerfTables &T, int 
 // x-update of one tile of vertices in perf mode.  `bar` is an mbarrier in shared memory (device build only).
 GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const GcsPerfTables &T, const GcsPerfLayout &L,
                            double *S, int tile, Ctrl *ctrl_all, const int *vprob, unsigned long long *bar) {
+    // single problem: rho / mu_scale are uniform — loaded once into registers here, so their latency overlaps the bulk copies
+    // (batched problems: per vertex, from its problem's control block, after the descriptors have arrived)
+    const double rho_u = ctrl_all->rho, ms_u = ctrl_all->mu_scale;
+#define RHO(vl) (vprob ? vd[2 * (vl)] : rho_u)
+#define MSC(vl) (vprob ? vd[2 * (vl) + 1] : ms_u)
+#define ACT(vl) (!vprob || vi[GCS_VI_N * (vl) + GCS_VI_ACTIVE])
+#define ACT_W (!vprob || w[GCS_VI_ACTIVE])
     const int *tr = T.tile_rec + 8 * (size_t)tile;
     const int v0 = tr[0], nvt = tr[1], b0 = tr[2], nb = tr[3], c0 = tr[4], ncone = tr[5], h0 = tr[6], nhe = tr[7] & 0x3fffffff;
     const bool has_zero = (tr[7] >> 30) & 1;
@@ -275,17 +282,19 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
     __syncthreads();               // the barrier object is initialised before anybody polls it
     gcs_mbar_wait(bar, 0);
 #endif
-    GCS_CTA_LOOP(i, nvt) {         // rho, mu_scale and the stop flag of the vertex's problem
-        int *w = vi + GCS_VI_N * i;
-        Ctrl *c = ctrl_all + (vprob ? w[GCS_VI_ACTIVE] : 0);
-        w[GCS_VI_ACTIVE] = !(c->stop && !c->ignore_stop);
-        vd[2 * i] = c->rho; vd[2 * i + 1] = c->mu_scale;
-        if (vprob && w[GCS_VI_ACTIVE] && w[GCS_VI_NB]) {
+    if (vprob) {
+        GCS_CTA_LOOP(i, nvt) {     // rho, mu_scale and the stop flag of the vertex's problem
+            int *w = vi + GCS_VI_N * i;
+            Ctrl *c = ctrl_all + w[GCS_VI_ACTIVE];
+            w[GCS_VI_ACTIVE] = !(c->stop && !c->ignore_stop);
+            vd[2 * i] = c->rho; vd[2 * i + 1] = c->mu_scale;
+            if (w[GCS_VI_ACTIVE] && w[GCS_VI_NB]) {
 #if defined(GCS_EMULATE)
-            c->inner_iters += (unsigned long long)T.inner_iters;
+                c->inner_iters += (unsigned long long)T.inner_iters;
 #else
-            atomicAdd(&c->inner_iters, (unsigned long long)T.inner_iters);
+                atomicAdd(&c->inner_iters, (unsigned long long)T.inner_iters);
 #endif
+            }
         }
     }
     // ---- P1: consensus targets  T = z_e + mu_h  of the live half-edges.  Device build: the gathers are only ISSUED here — the
@@ -303,16 +312,16 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
         }
     }
 #endif
-    GCS_CTA_SYNC();                // vd / ACTIVE of every vertex of the tile are in shared memory
+    if (vprob) GCS_CTA_SYNC();     // vd / ACTIVE of every vertex of the tile are in shared memory
     if (has_zero) GCS_CTA_LOOP(q, 5 * nhe) {
         const int hl = q / 5, c = q - 5 * hl, h = h0 + hl, f = G.he_flags[h];
         if (!(f & GCS_HE_ZERO)) continue;
         int vl = 0;
         while (vl + 1 < nvt && vi[GCS_VI_N * (vl + 1) + GCS_VI_HE] <= hl) ++vl;
-        if (!vi[GCS_VI_N * vl + GCS_VI_ACTIVE]) continue;
+        if (!ACT(vl)) continue;
         // own copy and flow are 0; an incoming edge's "other copy" first point is unconstrained and sits on its target
         double x = 0.0;
-        if (c < 2 && !(f & GCS_HE_OUT)) x = St.z[5 * (size_t)G.he_edge[h] + c] + vd[2 * vl + 1] * St.mu[5 * (size_t)h + c];
+        if (c < 2 && !(f & GCS_HE_OUT)) x = St.z[5 * (size_t)G.he_edge[h] + c] + MSC(vl) * St.mu[5 * (size_t)h + c];
         St.xc[5 * (size_t)h + c] = x;
     }
     const double alpha = T.alpha, kappa = T.kappa;
@@ -322,8 +331,8 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
         GCS_CTA_LOOP(p, 4 * nb) {
             const int b = p >> 2, info = binfo(b), vl = info & 255;
             const int *w = vi + GCS_VI_N * vl;
-            if (!w[GCS_VI_ACTIVE] || ((info >> 10) & (p & 1))) continue;       // 's' / 't' have no C2 / C4 pairs
-            const double ms = it ? 1.0 : vd[2 * vl + 1];                      // sigma = kappa rho: lam rescales with mu (:705 / :708)
+            if (!ACT_W || ((info >> 10) & (p & 1))) continue;       // 's' / 't' have no C2 / C4 pairs
+            const double ms = it ? 1.0 : MSC(vl);                      // sigma = kappa rho: lam rescales with mu (:705 / :708)
             double *t = tS + 3 * p, *e = eS + 3 * p;
             const double t0 = t[0], t1 = t[1], t2 = t[2];
             double q0, q1, q2;
@@ -334,9 +343,9 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
         }
         GCS_CTA_LOOP(i, nvt) {                                                // path-length item: block soft-threshold, threshold 1 / sigma
             const int *w = vi + GCS_VI_N * i;
-            if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;
-            const double ms = it ? 1.0 : vd[2 * i + 1];
-            const double sigma = kappa * vd[2 * i] * ms;                      // the threshold of the pass that produced t (rho before its rescale)
+            if (!ACT_W || !w[GCS_VI_NB]) continue;
+            const double ms = it ? 1.0 : MSC(i);
+            const double sigma = kappa * RHO(i) * ms;                      // the threshold of the pass that produced t (rho before its rescale)
             const double a0 = tnS[2 * i], a1 = tnS[2 * i + 1], nrm = hypot(a0, a1);
             const double sc = nrm > 0.0 ? fmax(0.0, 1.0 - 1.0 / (sigma * nrm)) : 0.0;
             const double q0 = sc * a0, q1 = sc * a1, l0 = ms * (a0 - q0), l1 = ms * (a1 - q1);
@@ -348,15 +357,15 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
 #pragma unroll
             for (int j = 0; j < GCS_PF; ++j) {
                 const int q = threadIdx.x + j * blockDim.x;
-                if (q < 5 * nb) TS[q] = pz[j] + vd[2 * (binfo(q / 5) & 255) + 1] * pm[j];
+                if (q < 5 * nb) TS[q] = pz[j] + MSC(binfo(q / 5) & 255) * pm[j];
             }
             for (int q = threadIdx.x + GCS_PF * blockDim.x; q < 5 * nb; q += blockDim.x) {
 #else
             for (int q = 0; q < 5 * nb; ++q) {
 #endif
                 const int b = q / 5, c = q - 5 * b, h = bhe(b), vl = binfo(b) & 255;
-                if (h < 0 || !vi[GCS_VI_N * vl + GCS_VI_ACTIVE]) continue;
-                TS[q] = gcs_target_z(St, T, bedge(b), c, binfo(b)) + vd[2 * vl + 1] * St.mu[5 * (size_t)h + c];
+                if (h < 0 || !ACT(vl)) continue;
+                TS[q] = gcs_target_z(St, T, bedge(b), c, binfo(b)) + MSC(vl) * St.mu[5 * (size_t)h + c];
             }
         }
         GCS_CTA_SYNC();
@@ -367,8 +376,8 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
 #if defined(GCS_EMULATE)
         for (int vl = 0; vl < nvt; ++vl) {
             const int *w = vi + GCS_VI_N * vl;
-            if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;
-            for (int q = 5 * w[GCS_VI_BLK]; q < 5 * (w[GCS_VI_BLK] + w[GCS_VI_NB]); ++q) rS[q] = gcs_rhs(T, tS, TS, tnS, brec, q, vl, vd[2 * vl], kappa);
+            if (!ACT_W || !w[GCS_VI_NB]) continue;
+            for (int q = 5 * w[GCS_VI_BLK]; q < 5 * (w[GCS_VI_BLK] + w[GCS_VI_NB]); ++q) rS[q] = gcs_rhs(T, tS, TS, tnS, brec, q, vl, RHO(vl), kappa);
             for (int k = 0; k < GCS_NCX; ++k) cin[GCS_NCX * vl + k] = gcs_core_input(tS, rS, brec, w, k, kappa);
             for (int k = 0; k < GCS_NCX; ++k) cout[GCS_NCX * vl + k] = gcs_core_output(T.cls_tab + (size_t)GCS_CLS_STRIDE * w[GCS_VI_CLS], cin + GCS_NCX * vl, k);
         }
@@ -376,8 +385,8 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
         for (int vl = threadIdx.x >> 5; vl < nvt; vl += blockDim.x >> 5) {
             const int *w = vi + GCS_VI_N * vl;
             const int k = threadIdx.x & 31;
-            if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;                    // warp-uniform
-            for (int q = 5 * w[GCS_VI_BLK] + k; q < 5 * (w[GCS_VI_BLK] + w[GCS_VI_NB]); q += 32) rS[q] = gcs_rhs(T, tS, TS, tnS, brec, q, vl, vd[2 * vl], kappa);
+            if (!ACT_W || !w[GCS_VI_NB]) continue;                    // warp-uniform
+            for (int q = 5 * w[GCS_VI_BLK] + k; q < 5 * (w[GCS_VI_BLK] + w[GCS_VI_NB]); q += 32) rS[q] = gcs_rhs(T, tS, TS, tnS, brec, q, vl, RHO(vl), kappa);
             __syncwarp();
             if (k < GCS_NCX) cin[GCS_NCX * vl + k] = gcs_core_input(tS, rS, brec, w, k, kappa);
             __syncwarp();
@@ -390,7 +399,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
         GCS_CTA_LOOP(p, 4 * nb) {
             const int b = p >> 2, i = (p >> 1) & 1, fam = p & 1, info = binfo(b), vl = info & 255;
             const int *w = vi + GCS_VI_N * vl;
-            if (!w[GCS_VI_ACTIVE] || ((info >> 10) & fam)) continue;
+            if (!ACT_W || ((info >> 10) & fam)) continue;
             const double *co = cout + GCS_NCX * vl, *tab = T.cls_tab + (size_t)GCS_CLS_STRIDE * w[GCS_VI_CLS], *e = eS + 3 * p;
             double p0 = gcs_block_u(rS, co, tab, info, b, 2 * i), p1 = gcs_block_u(rS, co, tab, info, b, 2 * i + 1), p2 = gcs_block_u(rS, co, tab, info, b, 4);
             if (fam) { p0 = co[2 * i] - p0; p1 = co[2 * i + 1] - p1; p2 = 1.0 - p2; }
@@ -399,7 +408,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
         }
         GCS_CTA_LOOP(i, nvt) {
             const int *w = vi + GCS_VI_N * i;
-            if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;
+            if (!ACT_W || !w[GCS_VI_NB]) continue;
             const double *zz = cout + GCS_NCX * i + 4;
             tnS[2 * i] = alpha * (zz[0] - zz[2]) + enS[2 * i]; tnS[2 * i + 1] = alpha * (zz[1] - zz[3]) + enS[2 * i + 1];
         }
@@ -407,7 +416,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
             GCS_CTA_LOOP(q, 9 * nvt) {
                 const int vl = q / 9, k = q - 9 * vl;
                 const int *w = vi + GCS_VI_N * vl;
-                if (!w[GCS_VI_ACTIVE] || !w[GCS_VI_NB]) continue;
+                if (!ACT_W || !w[GCS_VI_NB]) continue;
                 double val = cout[GCS_NCX * vl + k];
                 const size_t v = (size_t)(v0 + vl);
                 if (T.edge_delta && k < 8)          // local frames: back to global coordinates  x = x' + c_v,  z_v = z_v' + y_v c_v
@@ -417,7 +426,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
             GCS_CTA_LOOP(q, 5 * nb) {
                 const int b = q / 5, c = q - 5 * b, h = bhe(b), info = binfo(b), vl = info & 255;
                 const int *w = vi + GCS_VI_N * vl;
-                if (h < 0 || !w[GCS_VI_ACTIVE]) continue;
+                if (h < 0 || !ACT_W) continue;
                 const double *co = cout + GCS_NCX * vl, *tab = T.cls_tab + (size_t)GCS_CLS_STRIDE * w[GCS_VI_CLS];
                 double x;
                 if ((info >> 8) & 1) x = gcs_block_u(rS, co, tab, info, b, c);      // out-edge: own first point | other's first point == own second point (C5)
@@ -445,4 +454,8 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
 #undef bhe
 #undef binfo
 #undef bedge
+#undef RHO
+#undef MSC
+#undef ACT
+#undef ACT_W
 }
