@@ -284,7 +284,7 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
                    double *__restrict__ mu, double *__restrict__ z, Ctrl *ctrl, double *__restrict__ partials, unsigned int *ticket, int fuse,
                    GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap, int nHghost, const PeerView *PVp) {
     if (ctrl->stop && !ctrl->ignore_stop) return;
-    const double ms = ctrl->mu_scale;
+    const double ms = ctrl->mu_scale, oa = p.outer_alpha, ob = 1.0 - p.outer_alpha;
     const int gpar = fuse == 2 ? ((PVp->comm[PVp->rank]->k + 1) & 1) * nHghost : 0;
     double r2 = 0, dz2 = 0, x2 = 0, z2 = 0, m2 = 0;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
@@ -298,9 +298,18 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
         for (int c = 0; c < 5; ++c) { mt[c] = ot ? mu[5 * (size_t)ht + c] : 0.0; mh[c] = oh ? mu[5 * (size_t)hh + c] : 0.0; }
         const double d0 = edge_delta ? edge_delta[2 * (size_t)e] : 0.0, d1 = edge_delta ? edge_delta[2 * (size_t)e + 1] : 0.0;
         const double w = edge_counted ? (double)edge_counted[e] : 1.0;
-        double zn[5], bz[5];
-        zn[0] = 0.5 * (xh[0] + xt[0]); zn[1] = 0.5 * (xh[1] + xt[1]);
-        const double q0 = xh[2] + xt[2], q1 = xh[3] + xt[3], q2 = xh[4] + xt[4] - (d0 * xt[2] + d1 * xt[3]);
+        double zn[5], bz[5], at[5], ah[5];
+        // oalpha != 1: over-relaxed consensus step (Boyd et al. 3.4.3) — x is replaced by oalpha x + (1 - oalpha) (B) z_old in the z- and
+        // mu-updates; the primal residual keeps the true x.  B' mu_tail + mu_head = 0 stays invariant.
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { at[c] = xt[c]; ah[c] = xh[c]; }
+        if (oa != 1.0) {
+            const double bo[5] = {zo[0], zo[1], zo[2] - d0 * zo[4], zo[3] - d1 * zo[4], zo[4]};
+#pragma unroll
+            for (int c = 0; c < 5; ++c) { at[c] = oa * xt[c] + ob * bo[c]; ah[c] = oa * xh[c] + ob * zo[c]; }
+        }
+        zn[0] = 0.5 * (ah[0] + at[0]); zn[1] = 0.5 * (ah[1] + at[1]);
+        const double q0 = ah[2] + at[2], q1 = ah[3] + at[3], q2 = ah[4] + at[4] - (d0 * at[2] + d1 * at[3]);
         zn[4] = (q2 + 0.5 * (d0 * q0 + d1 * q1)) / (2.0 + 0.5 * (d0 * d0 + d1 * d1));
         zn[2] = 0.5 * (q0 + d0 * zn[4]); zn[3] = 0.5 * (q1 + d1 * zn[4]);
         bz[0] = zn[0]; bz[1] = zn[1]; bz[2] = zn[2] - d0 * zn[4]; bz[3] = zn[3] - d1 * zn[4]; bz[4] = zn[4];
@@ -312,11 +321,11 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
         z2 += 0.5 * w * (2.0 * (zn[0] * zn[0] + zn[1] * zn[1] + zn[4] * zn[4]) + zn[2] * zn[2] + zn[3] * zn[3] + bz[2] * bz[2] + bz[3] * bz[3]);
         if (ot) {
 #pragma unroll
-            for (int c = 0; c < 5; ++c) { const double r = bz[c] - xt[c], mn = ms * mt[c] + r; mu[5 * (size_t)ht + c] = mn; r2 += r * r; x2 += xt[c] * xt[c]; m2 += mn * mn; }
+            for (int c = 0; c < 5; ++c) { const double r = bz[c] - xt[c], mn = ms * mt[c] + (bz[c] - at[c]); mu[5 * (size_t)ht + c] = mn; r2 += r * r; x2 += xt[c] * xt[c]; m2 += mn * mn; }
         }
         if (oh) {
 #pragma unroll
-            for (int c = 0; c < 5; ++c) { const double r = zn[c] - xh[c], mn = ms * mh[c] + r; mu[5 * (size_t)hh + c] = mn; r2 += r * r; x2 += xh[c] * xh[c]; m2 += mn * mn; }
+            for (int c = 0; c < 5; ++c) { const double r = zn[c] - xh[c], mn = ms * mh[c] + (zn[c] - ah[c]); mu[5 * (size_t)hh + c] = mn; r2 += r * r; x2 += xh[c] * xh[c]; m2 += mn * mn; }
         }
     }
     edge_finish(r2, dz2, x2, z2, m2, ctrl, partials, ticket, fuse, p, n_x, n_mu, hist, hist_cap, PVp);
@@ -688,7 +697,7 @@ static int launch_edge(GcsHandle *h, int fuse) {
                                                                      h->ctrl, h->p, h->prob_nx, h->prob_nmu, h->hist, h->hist_cap);
         return 0;
     }
-    if ((h->perf_on && h->p_edge_delta) || (h->edge_per_edge && h->p.outer_alpha == 1.0)) {      // local frames (or the one-thread-per-edge variant by request)
+    if ((h->perf_on && h->p_edge_delta) || h->edge_per_edge) {      // local frames (or the one-thread-per-edge variant by request)
         int blocks = (h->nE + EDGE_THREADS - 1) / EDGE_THREADS;
         if (blocks > h->edge_blocks) blocks = h->edge_blocks;
         if (blocks < 1) blocks = 1;
@@ -705,14 +714,15 @@ static int launch_ctrl(GcsHandle *h) {
     control_kernel<<<1, 32, 0, h->stream>>>(h->ctrl, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap);
     return 0;
 }
-static void launch_iteration(GcsHandle *h) {
-    launch_k1(h);
+// everything of an iteration after K1
+static void launch_rest(GcsHandle *h) {
     if (!h->peer_on) { launch_edge(h, 1); return; }          // single GPU: 2 launches per ADMM iteration
     peer_push_kernel<<<1, 1024, 0, h->stream>>>(h->xc, h->send_he, h->send_rank, h->send_slot, h->nsend, h->ctrl, h->PV_dev);
     peer_wait_kernel<<<1, 32, 0, h->stream>>>(h->ctrl, h->PV_dev);
     launch_edge(h, 2);
     peer_control_kernel<<<1, 32, 0, h->stream>>>(h->ctrl, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, h->PV_dev);
 }
+static void launch_iteration(GcsHandle *h) { launch_k1(h); launch_rest(h); }
 // `iters` iterations as one CUDA graph launch (captured once per chunk length; the kernels read rho / stop from the control block)
 static int launch_chunk(GcsHandle *h, int iters) {
     // only whole chunks of check_every iterations are replayed (a remainder would force a re-instantiation every time)
@@ -909,6 +919,44 @@ extern "C" int gcsadmm_time_steps(GcsHandle *h, int k, float *ms_total, float *m
     CK(cudaEventElapsedTime(ms_total, h->ev[0], h->ev[3]));
     if (ms_k1) *ms_k1 = k1;
     if (ms_edge) *ms_edge = ed;
+    rc = set_ignore_stop(h, 0); if (rc) return rc;
+    CK(cudaGetLastError());
+    return fetch_ctrl(h);
+}
+
+// k iterations enqueued back to back, each preceded by an L2 eviction (memset of flush_bytes on the same stream, outside the
+// event pair) and bracketed by its own CUDA events: the host never waits between iterations, so launch latency and the skew
+// between ranks of a multi-GPU run are not part of what is measured.  ms_iter[k], ms_k1[k] (optional): per-iteration times.
+extern "C" int gcsadmm_time_window(GcsHandle *h, int k, long long flush_bytes, float *ms_iter, float *ms_k1) {
+    if (!h || !ms_iter || k < 1) return set_err(GCS_E_INVALID, "bad argument%s", "");
+    CK(cudaSetDevice(h->device));
+    if (flush_bytes > 0 && (!h->flush_buf || h->flush_bytes < (size_t)flush_bytes)) {
+        if (h->flush_buf) cudaFree(h->flush_buf);
+        h->flush_buf = nullptr;
+        CK(cudaMalloc(&h->flush_buf, (size_t)flush_bytes));
+        h->flush_bytes = (size_t)flush_bytes;
+    }
+    int rc = set_ignore_stop(h, 1); if (rc) return rc;
+    cudaEvent_t *ev = (cudaEvent_t *)calloc(3 * (size_t)k, sizeof(cudaEvent_t));
+    if (!ev) return set_err(GCS_E_NOMEM, "out of host memory%s", "");
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 3 * k && e == cudaSuccess; ++i) e = cudaEventCreate(&ev[i]);
+    for (int i = 0; i < k && e == cudaSuccess; ++i) {
+        if (flush_bytes > 0) cudaMemsetAsync(h->flush_buf, 0, (size_t)flush_bytes, h->stream);
+        cudaEventRecord(ev[3 * i], h->stream);
+        launch_k1(h);
+        if (ms_k1) cudaEventRecord(ev[3 * i + 1], h->stream);
+        launch_rest(h);
+        e = cudaEventRecord(ev[3 * i + 2], h->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < k && e == cudaSuccess; ++i) {
+        e = cudaEventElapsedTime(&ms_iter[i], ev[3 * i], ev[3 * i + 2]);
+        if (ms_k1 && e == cudaSuccess) e = cudaEventElapsedTime(&ms_k1[i], ev[3 * i], ev[3 * i + 1]);
+    }
+    for (int i = 0; i < 3 * k; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+    free(ev);
+    if (e != cudaSuccess) return set_err(GCS_E_CUDA, "time_window: %s", cudaGetErrorString(e));
     rc = set_ignore_stop(h, 0); if (rc) return rc;
     CK(cudaGetLastError());
     return fetch_ctrl(h);

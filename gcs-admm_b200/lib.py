@@ -19,7 +19,7 @@ EXPORTS = [
     "gcsadmm_create", "gcsadmm_destroy", "gcsadmm_set_stream", "gcsadmm_run", "gcsadmm_step",
     "gcsadmm_get_status", "gcsadmm_vertex_update", "gcsadmm_edge_update", "gcsadmm_control",
     "gcsadmm_sums_device_ptr", "gcsadmm_xc_device_ptr", "gcsadmm_get_history", "gcsadmm_get_solution",
-    "gcsadmm_get_state", "gcsadmm_set_state", "gcsadmm_time_steps", "gcsadmm_solve_host",
+    "gcsadmm_get_state", "gcsadmm_set_state", "gcsadmm_time_steps", "gcsadmm_time_window", "gcsadmm_solve_host",
     "gcsadmm_scratch_bytes", "gcsadmm_flush_l2", "gcsadmm_get_problem_status", "gcsadmm_get_problem_history", "gcsadmm_enable_perf",
     "gcsadmm_get_perf_state", "gcsadmm_set_perf_state", "gcsadmm_peer_export", "gcsadmm_peer_connect", "gcsadmm_peer_error",
 ]
@@ -96,6 +96,7 @@ def load():
     L.gcsadmm_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.gcsadmm_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int]
     L.gcsadmm_time_steps.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.gcsadmm_time_window.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]
     L.gcsadmm_solve_host.argtypes = [C.POINTER(GcsGraph), C.POINTER(GcsParams), C.c_int, C.c_int, C.POINTER(GcsStatus),
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.gcsadmm_enable_perf.argtypes = [C.c_void_p, C.POINTER(GcsPerfConfig)]
@@ -326,6 +327,14 @@ class Solver:
         _check(load().gcsadmm_time_steps(self._h, int(k), C.byref(tot), C.byref(k1) if split else None,
                                          C.byref(ed) if split else None))
         return tot.value, k1.value, ed.value
+
+
+    def time_window(self, k, flush_bytes=256 << 20, split=False):
+        """k iterations enqueued back to back, L2 evicted in-stream before each (outside the event pairs) -> (ms per iteration [k], K1 ms [k] | None)"""
+        it = np.zeros(int(k), dtype=np.float32)
+        k1 = np.zeros(int(k), dtype=np.float32) if split else None
+        _check(load().gcsadmm_time_window(self._h, int(k), int(flush_bytes), _ptr(it), _ptr(k1)))
+        return it, k1
 
 
 def solve_host(g, device=0, max_iters=None, **params):

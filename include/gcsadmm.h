@@ -142,6 +142,10 @@ int gcsadmm_set_state(GcsHandle *h, const double *xc, const double *mu, const do
 /* timing: k passes bracketed by CUDA events on the handle's stream; ms_k1 / ms_edge may be NULL */
 int gcsadmm_time_steps(GcsHandle *h, int k, float *ms_total, float *ms_k1, float *ms_edge);
 
+/* timing window (bench protocol): k iterations enqueued back to back, each preceded by an in-stream L2 eviction of flush_bytes
+   (0: none) outside its own event pair; no host round trip between iterations.  ms_iter[k]; ms_k1[k] may be NULL */
+int gcsadmm_time_window(GcsHandle *h, int k, long long flush_bytes, float *ms_iter, float *ms_k1);
+
 /* evicts L2 between timed iterations (bench hygiene): overwrites a scratch buffer of `bytes` (0: 256 MiB) */
 int gcsadmm_flush_l2(GcsHandle *h, long long bytes);
 

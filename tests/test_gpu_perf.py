@@ -78,16 +78,17 @@ def test_parity_mode_rounds_gpu_flows_to_the_stored_result(name):
         assert res["path"] == gpath
 
 
-@pytest.mark.parametrize("name,K,adapt,frames", [("benchmark4", 3, False, "global"), ("benchmark3", 1, True, "global"), ("test_autogen2", 2, True, "global"),
-                                                 ("benchmark4", 1, True, "local"), ("benchmark2", 2, False, "local")])
-def test_perf_kernel_equals_cpu_emulation(name, K, adapt, frames):
+@pytest.mark.parametrize("name,K,adapt,frames,oa", [("benchmark4", 3, False, "global", 1.0), ("benchmark3", 1, True, "global", 1.0), ("test_autogen2", 2, True, "global", 1.0),
+                                                    ("benchmark4", 1, True, "local", 1.0), ("benchmark2", 2, False, "local", 1.0),
+                                                    ("benchmark4", 1, True, "local", 1.7), ("benchmark3", 1, False, "global", 1.5)])
+def test_perf_kernel_equals_cpu_emulation(name, K, adapt, frames, oa):
     """the CUDA kernel against the same source compiled for the host, iterate by iterate — with the rho adaptation on
     (adapt=True: the lam / mu rescale paths are exercised) and off"""
     import test_perf_mode as T
     from gcs_admm_b200.lib import Solver
     g = pack_graph(*load_golden(name)[:2])
-    a = T.EmuPerfADMM(T.load_emu(), g, K=K, adapt=adapt, frames=frames)
-    s = Solver(g, frac=1.0 if adapt else 0.0, max_it=1000, use_graph=0).enable_perf(inner_iters=K, frames=frames)
+    a = T.EmuPerfADMM(T.load_emu(), g, K=K, adapt=adapt, frames=frames, outer_alpha=oa)
+    s = Solver(g, frac=1.0 if adapt else 0.0, max_it=1000, use_graph=0, outer_alpha=oa).enable_perf(inner_iters=K, frames=frames)
     for it in range(60):
         a.step()
         s.step(1)

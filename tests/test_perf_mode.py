@@ -65,6 +65,13 @@ class EmuPerfADMM:
         g, d = self.g, self.delta
         self.vertex_update()
         xt, xh = self.xc[g.edge_he_tail], self.xc[g.edge_he_head]
+        at, ah = xt, xh
+        if self.oa != 1.0:                   # over-relaxed consensus step: x -> oa x + (1 - oa) (B) z_old in the z- and mu-updates
+            bo = self.z.copy()
+            bo[:, 2:4] -= d * self.z[:, 4:5]
+            at, ah = self.oa * xt + (1 - self.oa) * bo, self.oa * xh + (1 - self.oa) * self.z
+        xt_true, xh_true = xt, xh
+        xt, xh = at, ah
         zn = np.empty_like(self.z)
         zn[:, 0:2] = 0.5 * (xh[:, 0:2] + xt[:, 0:2])
         q = xh[:, 2:4] + xt[:, 2:4]
@@ -75,10 +82,12 @@ class EmuPerfADMM:
         self.z = zn
         bz, dbz = zn.copy(), dz.copy()
         bz[:, 2:4] -= d * zn[:, 4:5]; dbz[:, 2:4] -= d * dz[:, 4:5]
-        r = np.zeros_like(self.xc)
-        r[g.edge_he_head] = zn - xh
-        r[g.edge_he_tail] = bz - xt
-        self.mu = self.ms * self.mu + r
+        r, rh = np.zeros_like(self.xc), np.zeros_like(self.xc)
+        r[g.edge_he_head] = zn - xh_true
+        r[g.edge_he_tail] = bz - xt_true
+        rh[g.edge_he_head] = zn - xh
+        rh[g.edge_he_tail] = bz - xt
+        self.mu = self.ms * self.mu + rh
         self.pri.append(float(np.sqrt(np.sum(r * r)))); self.dual.append(self.rho * float(np.sqrt(np.sum(dz * dz) + np.sum(dbz * dbz))))
         self._adapt()
 

@@ -1,5 +1,5 @@
 """BASELINE metric "time to residual 1e-4": perf mode from a cold start until max(pri, dual) < tol, with a trace.
-usage: time_to_residual.py --grid G [--tol 1e-4] [--max-iters N] [--inner K] [--window W] [--adapt-every A] [--outer-alpha a] [--rho0 r] [--nu v] [--tau t]"""
+usage: time_to_residual.py --grid G [--tol 1e-4] [--max-iters N] [--inner K] [--window W] [--adapt-every A] [--outer-alpha a] [--rho0 r] [--nu v] [--tau t] [--theta th] [--warm dijkstra]"""
 import argparse, sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import utils  # noqa
@@ -19,15 +19,22 @@ ap.add_argument("--rho0", type=float, default=1.0)
 ap.add_argument("--nu", type=float, default=10.0)
 ap.add_argument("--tau", type=float, default=2.0)
 ap.add_argument("--frames", type=str, default="local", choices=["local", "global"])
+ap.add_argument("--theta", type=float, default=1.0, help="penalty of the flow scalars = theta * rho")
+ap.add_argument("--warm", type=str, default="none", choices=["none", "dijkstra", "euclid"], help="dual start from a cost-to-go field (gcs_admm_b200.warmstart)")
 ap.add_argument("--trace", type=int, default=20, help="trace points")
 ap.add_argument("--budget", type=float, default=1e9, help="seconds")
 a = ap.parse_args()
 g = grid_packed_graph(a.grid)
-T = perf.perf_tables(g, frames=a.frames)
+T = perf.perf_tables(g, frames=a.frames, theta=a.theta)
 # rho adapts while it < frac * max_it (reference rule :703): the window is a parameter of the reference's algorithm
 s = lib.Solver(g, max_it=a.max_iters + 8, frac=a.window / (a.max_iters + 8), abs_stop=1, abs_tol=a.tol, check_every=256, rho0=a.rho0, nu=a.nu,
                tau_incr=a.tau, tau_decr=a.tau, outer_alpha=a.outer_alpha, adapt_every=a.adapt_every).enable_perf(inner_iters=a.inner, tables=T)
 t0 = time.perf_counter()
+if a.warm != "none":
+    from gcs_admm_b200 import warmstart
+    mu0 = warmstart.dual_start(g, T["edge_delta"], a.rho0, field=a.warm)
+    s.set_state(np.zeros((g.H, 5)), mu0, np.zeros((g.nE, 5)), a.rho0, 0)
+    print(json.dumps(dict(warm=a.warm, host_seconds=round(time.perf_counter() - t0, 3))), flush=True)
 done, chunk = 0, max(256, a.max_iters // a.trace)
 while done < a.max_iters and time.perf_counter() - t0 < a.budget:
     st = s.run(min(chunk, a.max_iters - done))
