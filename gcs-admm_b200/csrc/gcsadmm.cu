@@ -91,7 +91,7 @@ struct GcsHandle {
     cudaEvent_t ev[4];
     void *flush_buf; size_t flush_bytes;
     // perf mode (inexact x-update by K closed-form splitting iterations)
-    int perf_on, perf_smem, perf_threads;
+    int perf_on, perf_smem, perf_threads, perf_grid;
     GcsPerfLayout PL;
     GcsPerfTables PT;
     long long perf_nblocks;
@@ -126,13 +126,38 @@ vertex_kernel(GcsGraphView G, GcsStateView St, Ctrl *ctrl_all, const int *__rest
 }
 
 // ------------------------------------------------------------------------------------------ K1 (perf mode)
-// one thread block per tile of consecutive vertices (<= 256 (point, flow) pairs); ~25 KB of shared memory per block
+// PERSISTENT thread blocks (4 per SM), each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ... of consecutive vertices
+// (<= 256 (point, flow) pairs per tile).  Two stage buffers: while a block computes tile i from one, the bulk copies (TMA unit,
+// mbarrier-signalled) of tile i + gridDim.x fill the other, and the bulk stores of tile i - gridDim.x drain — the DRAM latency of
+// the per-tile state, cone records and descriptors never sits on the critical path.  ~43 KB of shared memory per block.
 __global__ void __launch_bounds__(GCS_PERF_THREADS, 4)
 vertex_perf_kernel(GcsGraphView G, GcsStateView St, GcsPerfTables T, Ctrl *ctrl_all, const int *__restrict__ vprob, GcsPerfLayout L) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ __align__(8) unsigned long long bar;
+    __shared__ __align__(8) unsigned long long bar[2];
     if (!vprob && ctrl_all->stop && !ctrl_all->ignore_stop) return;
-    gcs_perf_tile(G, St, T, L, smem, blockIdx.x, ctrl_all, vprob, &bar);
+    int tile = blockIdx.x;
+    if (tile >= T.ntiles) return;
+    double *const stage0 = smem + L.work;
+#define STAGE(b) (stage0 + (b) * L.stage)
+    if (threadIdx.x == 0) {
+        gcs_mbar_init(&bar[0], 1);
+        gcs_mbar_init(&bar[1], 1);
+        gcs_perf_stage(T, L, STAGE(0), tile, &bar[0]);
+    }
+    __syncthreads();                   // the barrier objects are initialised before anybody polls them
+    unsigned phase = 0;                // bit b: parity of the next completion of bar[b]
+    for (int buf = 0; tile < T.ntiles; tile += gridDim.x, buf ^= 1) {
+        const int next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < T.ntiles) {
+            gcs_bulk_wait_read();      // the stores of the tile that used the other buffer have finished reading it
+            gcs_perf_stage(T, L, STAGE(buf ^ 1), next, &bar[buf ^ 1]);
+        }
+        gcs_mbar_wait(&bar[buf], (phase >> buf) & 1u);
+        phase ^= 1u << buf;
+        gcs_perf_tile(G, St, T, L, smem, STAGE(buf), tile, ctrl_all, vprob);
+    }
+    if (threadIdx.x == 0) gcs_bulk_wait_read();   // shared memory stays valid until the last stores have read it
+#undef STAGE
 }
 // x_v / z_v / y_v of vertices no flow can pass are constants: written once when the mode is enabled
 __global__ void perf_init_dead_kernel(GcsGraphView G, GcsStateView St) {
@@ -683,7 +708,7 @@ static GcsStateView state_view(const GcsHandle *h) {
 }
 static int launch_k1(GcsHandle *h) {
     if (h->perf_on) {
-        vertex_perf_kernel<<<h->PT.ntiles, h->perf_threads, h->perf_smem, h->stream>>>(graph_view(h), state_view(h), h->PT, h->ctrl, h->vprob, h->PL);
+        vertex_perf_kernel<<<h->perf_grid, h->perf_threads, h->perf_smem, h->stream>>>(graph_view(h), state_view(h), h->PT, h->ctrl, h->vprob, h->PL);
         return 0;
     }
     vertex_kernel<<<h->k1_blocks, h->k1_warps * 32, h->k1_smem, h->stream>>>(graph_view(h), state_view(h), h->ctrl, h->vprob, h->L, h->p.inner_tol, h->p.inner_max_iter);
@@ -1140,10 +1165,18 @@ extern "C" int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *c) {
     h->PT.alpha = c->alpha; h->PT.kappa = c->kappa; h->PT.theta = c->theta > 0.0 ? c->theta : 1.0; h->PT.edge_delta = h->p_edge_delta;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
-    const size_t bytes = (size_t)h->PL.total * sizeof(double);
+    const size_t bytes = (size_t)(h->PL.work + 2 * h->PL.stage) * sizeof(double);      // work arrays + two stage buffers
     if (bytes > prop.sharedMemPerBlockOptin) { free_perf(h); return set_err(GCS_E_INVALID, "perf-mode tile too large for shared memory (a vertex of very high degree)%s", ""); }
     h->perf_smem = (int)bytes;
     h->perf_threads = c->threads >= 32 && c->threads <= GCS_PERF_THREADS ? (c->threads / 32) * 32 : GCS_PERF_THREADS;
+    {   // persistent grid: as many blocks as are resident at once (GCS_PERF_BLOCKS_PER_SM: tuning knob), never more than tiles
+        const char *bps = getenv("GCS_PERF_BLOCKS_PER_SM");
+        int per_sm = bps && atoi(bps) > 0 ? atoi(bps) : 4;
+        const int by_smem = (int)(prop.sharedMemPerMultiprocessor / (bytes + 1024));
+        if (per_sm > by_smem) per_sm = by_smem > 0 ? by_smem : 1;
+        const long long cap = (long long)prop.multiProcessorCount * per_sm;
+        h->perf_grid = (int)(c->n_tiles < cap ? c->n_tiles : cap);
+    }
     CK(cudaFuncSetAttribute(vertex_perf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->perf_smem));
     CK(cudaFuncSetAttribute(vertex_perf_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     perf_init_dead_kernel<<<(h->nV + 255) / 256, 256, 0, h->stream>>>(graph_view(h), state_view(h));

@@ -71,8 +71,10 @@ struct GcsPerfTables {
                                // x_head = z_e,  x_tail = B_e z_e  with  B_e (p1, p2, y) = (p1, p2 - y delta_e, y),  delta_e = cent[u] - cent[w]
 };
 
-// shared memory of one tile (offsets in doubles)
-struct GcsPerfLayout { int nb_cap, nvt_cap, cone_cap, tS, eS, cone, tnS, enS, T, r, cin, cout, vd, vi, bi, total; };
+// shared memory of one tile (offsets in doubles).  Two regions: the STAGED arrays that arrive by bulk copies (state t, cone
+// records, path-length state, per-vertex and per-block descriptors; offsets relative to the stage base — the kernel keeps two
+// stage buffers and fills one while it works on the other) and the WORK arrays (offsets relative to the work base).
+struct GcsPerfLayout { int nb_cap, nvt_cap, cone_cap, tS, cone, tnS, vi, bi, tr, stage, eS, enS, T, r, cin, cout, vd, work, total; };
 #define GCS_VI_N 8        // ints per vertex of the tile
 #define GCS_VI_CONE 0     // first cone record, relative to the tile's
 #define GCS_VI_NV 1       // polygon vertices
@@ -92,9 +94,14 @@ static inline GcsPerfLayout gcs_perf_layout(int nb_cap, int nvt_cap, int cone_ca
     if (cone_cap < 1) cone_cap = 1;
     L.nb_cap = nb_cap; L.nvt_cap = nvt_cap; L.cone_cap = cone_cap;
     int o = 0;
-    L.tS = o; o += 12 * nb_cap;              // bulk-copied arrays first: 16-byte aligned offsets
+    L.tS = o; o += 12 * nb_cap;              // every staged array starts at a 16-byte aligned offset and is a multiple of 16 bytes long
     L.cone = o; o += GCS_CONE_REC * cone_cap;
     L.tnS = o; o += 2 * nvt_cap;
+    L.vi = o; o += (GCS_VI_N * nvt_cap) / 2;
+    L.bi = o; o += 2 * nb_cap;                // 4 ints per block: half-edge, descriptor, edge, pad
+    L.tr = o; o += 4;                         // the tile's own record (8 ints)
+    L.stage = o;
+    o = 0;
     L.eS = o; o += 12 * nb_cap;
     L.enS = o; o += 2 * nvt_cap;
     L.T = o; o += 5 * nb_cap;
@@ -102,10 +109,8 @@ static inline GcsPerfLayout gcs_perf_layout(int nb_cap, int nvt_cap, int cone_ca
     L.cin = o; o += GCS_NCX * nvt_cap;
     L.cout = o; o += GCS_NCX * nvt_cap;
     L.vd = o; o += 2 * nvt_cap;
-    o += o & 1;                               // bulk-copied int records: 16-byte aligned
-    L.vi = o; o += (GCS_VI_N * nvt_cap) / 2;
-    L.bi = o; o += 2 * nb_cap;                // 4 ints per block: half-edge, descriptor, edge, pad
-    L.total = o + (o & 1);
+    L.work = o + (o & 1);
+    L.total = L.work + L.stage;               // single-buffered (host emulation); the kernel uses work + 2 stage
     return L;
 }
 
@@ -176,10 +181,8 @@ __device__ __forceinline__ void gcs_mbar_wait(unsigned long long *bar, unsigned 
 __device__ __forceinline__ void gcs_bulk_s2g(void *dst, const void *src, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(gcs_smem_u32(src)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void gcs_bulk_commit_wait() {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
+__device__ __forceinline__ void gcs_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void gcs_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void gcs_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
@@ -243,44 +246,54 @@ GCS_DEV double gcs_target_z(const GcsStateView &St, const GcsPerfTables &T, int 
     return zc;
 }
 
-// x-update of one tile of vertices in perf mode.  `bar` is an mbarrier in shared memory (device build only).
+#if !defined(GCS_EMULATE) && defined(__CUDACC__)
+// P0 (one thread): the bulk copies that stage tile `tile` into the stage buffer B; completion is signalled on `bar`
+__device__ __forceinline__ void gcs_perf_stage(const GcsPerfTables &T, const GcsPerfLayout &L, double *B, int tile, unsigned long long *bar) {
+    const int *tr = T.tile_rec + 8 * (size_t)tile;
+    const int v0 = tr[0], nvt = tr[1], b0 = tr[2], nb = tr[3], c0 = tr[4], ncone = tr[5];
+    gcs_mbar_expect_tx(bar, (unsigned)(sizeof(double) * (12 * nb + 2 * nvt + GCS_CONE_REC * ncone) + sizeof(int) * (GCS_VI_N * nvt + 4 * nb + 8)));
+    gcs_bulk_g2s(B + L.tr, tr, (unsigned)(sizeof(int) * 8), bar);
+    gcs_bulk_g2s(B + L.vi, T.vrec + GCS_VI_N * (size_t)v0, (unsigned)(sizeof(int) * GCS_VI_N * nvt), bar);
+    if (nb) gcs_bulk_g2s(B + L.bi, T.blk_rec + 4 * (size_t)b0, (unsigned)(sizeof(int) * 4 * nb), bar);
+    if (nb) gcs_bulk_g2s(B + L.tS, T.tstate + 12 * (size_t)b0, (unsigned)(sizeof(double) * 12 * nb), bar);
+    gcs_bulk_g2s(B + L.tnS, T.tn + 2 * (size_t)v0, (unsigned)(sizeof(double) * 2 * nvt), bar);
+    if (ncone) gcs_bulk_g2s(B + L.cone, T.cone + GCS_CONE_REC * (size_t)c0, (unsigned)(sizeof(double) * GCS_CONE_REC * ncone), bar);
+}
+#endif
+
+// x-update of one tile of vertices in perf mode.  S: work arrays, B: the tile's staged arrays (device build: already filled by
+// gcs_perf_stage and waited for; the new state leaves B by bulk stores that the CALLER waits for before B is refilled).
 GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const GcsPerfTables &T, const GcsPerfLayout &L,
-                           double *S, int tile, Ctrl *ctrl_all, const int *vprob, unsigned long long *bar) {
-    // single problem: rho / mu_scale are uniform — loaded once into registers here, so their latency overlaps the bulk copies
-    // (batched problems: per vertex, from its problem's control block, after the descriptors have arrived)
+                           double *S, double *B, int tile, Ctrl *ctrl_all, const int *vprob) {
+    // single problem: rho / mu_scale are uniform — loaded once into registers here
+    // (batched problems: per vertex, from its problem's control block)
     const double rho_u = ctrl_all->rho, ms_u = ctrl_all->mu_scale;
 #define RHO(vl) (vprob ? vd[2 * (vl)] : rho_u)
 #define MSC(vl) (vprob ? vd[2 * (vl) + 1] : ms_u)
 #define ACT(vl) (!vprob || vi[GCS_VI_N * (vl) + GCS_VI_ACTIVE])
 #define ACT_W (!vprob || w[GCS_VI_ACTIVE])
+#if defined(GCS_EMULATE)
     const int *tr = T.tile_rec + 8 * (size_t)tile;
-    const int v0 = tr[0], nvt = tr[1], b0 = tr[2], nb = tr[3], c0 = tr[4], ncone = tr[5], h0 = tr[6], nhe = tr[7] & 0x3fffffff;
+#else
+    const int *tr = (const int *)(B + L.tr);       // staged with the rest of the tile
+#endif
+    const int v0 = tr[0], nvt = tr[1], b0 = tr[2], nb = tr[3], h0 = tr[6], nhe = tr[7] & 0x3fffffff;
     const bool has_zero = (tr[7] >> 30) & 1;
-    double *tS = S + L.tS, *eS = S + L.eS, *coneS = S + L.cone, *tnS = S + L.tnS, *enS = S + L.enS, *TS = S + L.T, *rS = S + L.r;
+    double *tS = B + L.tS, *eS = S + L.eS, *coneS = B + L.cone, *tnS = B + L.tnS, *enS = S + L.enS, *TS = S + L.T, *rS = S + L.r;
     double *cin = S + L.cin, *cout = S + L.cout, *vd = S + L.vd;
-    int *vi = (int *)(S + L.vi), *brec = (int *)(S + L.bi);
+    int *vi = (int *)(B + L.vi), *brec = (int *)(B + L.bi);
 #define bhe(b) brec[4 * (b)]
 #define binfo(b) brec[4 * (b) + 1]
 #define bedge(b) brec[4 * (b) + 2]
-    // ---- P0: stage the tile with bulk copies: state, cone records, per-vertex and per-block descriptors (all contiguous per tile)
 #if defined(GCS_EMULATE)
-    memcpy(tS, T.tstate + 12 * (size_t)b0, sizeof(double) * 12 * nb);
-    memcpy(tnS, T.tn + 2 * (size_t)v0, sizeof(double) * 2 * nvt);
-    memcpy(coneS, T.cone + GCS_CONE_REC * (size_t)c0, sizeof(double) * GCS_CONE_REC * ncone);
-    memcpy(vi, T.vrec + GCS_VI_N * (size_t)v0, sizeof(int) * GCS_VI_N * nvt);
-    memcpy(brec, T.blk_rec + 4 * (size_t)b0, sizeof(int) * 4 * nb);
-#else
-    if (threadIdx.x == 0) {
-        gcs_mbar_init(bar, 1);
-        gcs_mbar_expect_tx(bar, (unsigned)(sizeof(double) * (12 * nb + 2 * nvt + GCS_CONE_REC * ncone) + sizeof(int) * (GCS_VI_N * nvt + 4 * nb)));
-        gcs_bulk_g2s(vi, T.vrec + GCS_VI_N * (size_t)v0, (unsigned)(sizeof(int) * GCS_VI_N * nvt), bar);
-        if (nb) gcs_bulk_g2s(brec, T.blk_rec + 4 * (size_t)b0, (unsigned)(sizeof(int) * 4 * nb), bar);
-        if (nb) gcs_bulk_g2s(tS, T.tstate + 12 * (size_t)b0, (unsigned)(sizeof(double) * 12 * nb), bar);
-        gcs_bulk_g2s(tnS, T.tn + 2 * (size_t)v0, (unsigned)(sizeof(double) * 2 * nvt), bar);
-        if (ncone) gcs_bulk_g2s(coneS, T.cone + GCS_CONE_REC * (size_t)c0, (unsigned)(sizeof(double) * GCS_CONE_REC * ncone), bar);
+    {   // ---- P0 on the host: the tile's contiguous state, cone records and descriptors
+        const int c0 = tr[4], ncone = tr[5];
+        memcpy(tS, T.tstate + 12 * (size_t)b0, sizeof(double) * 12 * nb);
+        memcpy(tnS, T.tn + 2 * (size_t)v0, sizeof(double) * 2 * nvt);
+        memcpy(coneS, T.cone + GCS_CONE_REC * (size_t)c0, sizeof(double) * GCS_CONE_REC * ncone);
+        memcpy(vi, T.vrec + GCS_VI_N * (size_t)v0, sizeof(int) * GCS_VI_N * nvt);
+        memcpy(brec, T.blk_rec + 4 * (size_t)b0, sizeof(int) * 4 * nb);
     }
-    __syncthreads();               // the barrier object is initialised before anybody polls it
-    gcs_mbar_wait(bar, 0);
 #endif
     if (vprob) {
         GCS_CTA_LOOP(i, nvt) {     // rho, mu_scale and the stop flag of the vertex's problem
@@ -434,9 +447,9 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
                 St.xc[5 * (size_t)h + c] = x;
             }
         }
-        GCS_CTA_SYNC();
+        if (!last) GCS_CTA_SYNC();     // (after the last pass P8's barrier follows)
     }
-    // ---- P8: the new state goes back with bulk stores
+    // ---- P8: the new state goes back with bulk stores (the caller waits for them before it refills B)
 #if defined(GCS_EMULATE)
     memcpy(T.tstate + 12 * (size_t)b0, tS, sizeof(double) * 12 * nb);
     memcpy(T.tn + 2 * (size_t)v0, tnS, sizeof(double) * 2 * nvt);
@@ -447,7 +460,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
     if (threadIdx.x == 0) {
         if (nb) gcs_bulk_s2g(T.tstate + 12 * (size_t)b0, tS, (unsigned)(sizeof(double) * 12 * nb));
         gcs_bulk_s2g(T.tn + 2 * (size_t)v0, tnS, (unsigned)(sizeof(double) * 2 * nvt));
-        gcs_bulk_commit_wait();
+        gcs_bulk_commit();
         if (!vprob) atomicAdd(&ctrl_all->inner_iters, (unsigned long long)T.inner_iters * (unsigned long long)nvt);
     }
 #endif
