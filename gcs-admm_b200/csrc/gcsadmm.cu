@@ -39,12 +39,13 @@ static int set_err(int code, const char *fmt, const char *a = "", const char *b 
 
 // ------------------------------------------------------------------------------------------ peer mode (types)
 // Vertex-partitioned graph, one process per GPU of one NVSwitch box.  Per ADMM iteration k a rank
-//   K1 -> peer_push_kernel: stores the 5 consensus scalars of every cut half-edge straight into the neighbour's ghost
-//         slot (peer pointer over NVLink), system fence, then raises halo_flag[me] = k in the neighbour's block
-//   peer_wait_kernel: spins until every neighbour's flag has reached k
-//   edge_kernel (fuse = 2): its last block stores this rank's 6 partial sums into EVERY rank's block and raises sums_flag[me] = k
+//   K1, then the halo push: the 5 consensus scalars of every cut half-edge are stored straight into the neighbour's ghost slot
+//         (peer pointer over NVLink), system fence, then halo_flag[me] = k is raised in the neighbour's block.  Perf mode: the
+//         LAST block of K1 to finish does it (ticket); exact mode: peer_push_kernel
+//   edge kernel (fuse = 2): every block first spins until each neighbour's flag has reached k; the last block to finish stores
+//         this rank's 6 partial sums into EVERY rank's block and raises sums_flag[me] = k
 //   peer_control_kernel: waits for all ranks' sums, adds them in rank order (identical on every rank) and applies the control step
-// No NCCL call and no host round trip inside the iteration; the five launches are replayed from one CUDA graph.
+// No NCCL call and no host round trip inside the iteration; the three (exact mode: four) launches are replayed from one CUDA graph.
 // Ghost slots and the sums inbox are double-buffered by the parity of k, so a fast neighbour's iteration k + 1 never
 // overwrites what iteration k still reads (it cannot reach k + 2 before this rank has raised its k + 1 flags).
 #define GCS_MAX_PEERS 8
@@ -64,6 +65,9 @@ struct PeerView {
     int nHown[GCS_MAX_PEERS], nHghost[GCS_MAX_PEERS];
 };
 
+// what a kernel needs to push this rank's cut half-edges to its neighbours (PV == nullptr: nothing to push)
+struct PeerPush { const int *send_he, *send_rank, *send_slot; int nsend; const PeerView *PV; unsigned int *ticket; };
+
 struct GcsHandle {
     int device;
     cudaStream_t stream, own_stream;
@@ -81,6 +85,7 @@ struct GcsHandle {
     int *vprob, *prob_eoff; long long *prob_nx, *prob_nmu;   // batched mode (nP > 1)
     int *he_prob_host;  // host: problem of each half-edge (batched mode)
     unsigned int *ticket;   // edge_kernel: blocks finished in the current launch (the last one reduces + controls)
+    unsigned int *push_ticket;   // perf K1 in peer mode: blocks finished (the last one pushes the halo)
     double *xc, *mu, *z, *x_v, *z_v, *y_v;
     double *ws;         // [nV][gcs_ws_stride] interior-point warm-start records (null when warm_theta == 0)
     double *partials;   // [edge_blocks][NSUMS]
@@ -125,13 +130,41 @@ vertex_kernel(GcsGraphView G, GcsStateView St, Ctrl *ctrl_all, const int *__rest
     }
 }
 
+// ------------------------------------------------------------------------------------------ peer mode (device functions)
+__device__ __forceinline__ unsigned long long gcs_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
+// one thread block: cut half-edges -> the neighbours' ghost slots of this iteration's parity, then the flags (NVLink peer stores)
+__device__ __forceinline__ void peer_push(const double *xc, const int *__restrict__ send_he, const int *__restrict__ send_rank,
+                                          const int *__restrict__ send_slot, int nsend, const PeerView &PV) {
+    const int k = PV.comm[PV.rank]->k + 1, par = k & 1;
+    for (int i = threadIdx.x; i < 5 * nsend; i += blockDim.x) {
+        const int j = i / 5, c = i - 5 * j, q = send_rank[j];
+        PV.xc[q][5 * ((size_t)PV.nHown[q] + (size_t)par * PV.nHghost[q] + send_slot[j]) + c] = __ldcg(xc + 5 * (size_t)send_he[j] + c);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < PV.world && ((PV.neighbours >> threadIdx.x) & 1u)) *(volatile int *)&PV.comm[threadIdx.x]->halo_flag[PV.rank] = k;
+}
+// start of the edge kernels in peer mode: wait until every neighbour's halo of this iteration has arrived
+__device__ __forceinline__ void peer_wait_halo(const PeerView &PV) {
+    PeerComm *me = PV.comm[PV.rank];
+    const int k = me->k + 1, p = threadIdx.x;
+    if (p < PV.world && ((PV.neighbours >> p) & 1u)) {
+        const unsigned long long t0 = gcs_globaltimer();
+        while (*(volatile int *)&me->halo_flag[p] < k)
+            if (gcs_globaltimer() - t0 > GCS_PEER_TIMEOUT_NS) { me->error = 1; break; }
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------ K1 (perf mode)
 // PERSISTENT thread blocks (4 per SM), each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ... of consecutive vertices
 // (<= 256 (point, flow) pairs per tile).  Two stage buffers: while a block computes tile i from one, the bulk copies (TMA unit,
 // mbarrier-signalled) of tile i + gridDim.x fill the other, and the bulk stores of tile i - gridDim.x drain — the DRAM latency of
 // the per-tile state, cone records and descriptors never sits on the critical path.  ~43 KB of shared memory per block.
 __global__ void __launch_bounds__(GCS_PERF_THREADS, 4)
-vertex_perf_kernel(GcsGraphView G, GcsStateView St, GcsPerfTables T, Ctrl *ctrl_all, const int *__restrict__ vprob, GcsPerfLayout L) {
+vertex_perf_kernel(GcsGraphView G, GcsStateView St, GcsPerfTables T, Ctrl *ctrl_all, const int *__restrict__ vprob, GcsPerfLayout L, PeerPush P) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) unsigned long long bar[2];
     if (!vprob && ctrl_all->stop && !ctrl_all->ignore_stop) return;
@@ -158,6 +191,18 @@ vertex_perf_kernel(GcsGraphView G, GcsStateView St, GcsPerfTables T, Ctrl *ctrl_
     }
     if (threadIdx.x == 0) gcs_bulk_wait_read();   // shared memory stays valid until the last stores have read it
 #undef STAGE
+    if (P.PV) {      // peer mode: the LAST block to finish pushes the cut half-edges to the neighbours (no separate launch)
+        __shared__ int is_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            peer_push(St.xc, P.send_he, P.send_rank, P.send_slot, P.nsend, *P.PV);
+            if (threadIdx.x == 0) *P.ticket = 0u;
+        }
+    }
 }
 // x_v / z_v / y_v of vertices no flow can pass are constants: written once when the mode is enabled
 __global__ void perf_init_dead_kernel(GcsGraphView G, GcsStateView St) {
@@ -273,6 +318,7 @@ edge_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *
             double *__restrict__ z, Ctrl *ctrl, double *__restrict__ partials, unsigned int *ticket, int fuse,
             GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap, int nHghost, const PeerView *PVp) {
     if (ctrl->stop && !ctrl->ignore_stop) return;
+    if (fuse == 2) peer_wait_halo(*PVp);
     const double ms = ctrl->mu_scale, oa = p.outer_alpha, ob = 1.0 - p.outer_alpha;
     // peer mode: the ghost slots of this iteration's parity (PVp lives in device memory: indexed at run time)
     const int gpar = fuse == 2 ? ((PVp->comm[PVp->rank]->k + 1) & 1) * nHghost : 0;
@@ -309,6 +355,7 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
                    double *__restrict__ mu, double *__restrict__ z, Ctrl *ctrl, double *__restrict__ partials, unsigned int *ticket, int fuse,
                    GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap, int nHghost, const PeerView *PVp) {
     if (ctrl->stop && !ctrl->ignore_stop) return;
+    if (fuse == 2) peer_wait_halo(*PVp);
     const double ms = ctrl->mu_scale, oa = p.outer_alpha, ob = 1.0 - p.outer_alpha;
     const int gpar = fuse == 2 ? ((PVp->comm[PVp->rank]->k + 1) & 1) * nHghost : 0;
     double r2 = 0, dz2 = 0, x2 = 0, z2 = 0, m2 = 0;
@@ -357,35 +404,12 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
 }
 
 // ------------------------------------------------------------------------------------------ peer mode (kernels)
-__device__ __forceinline__ unsigned long long gcs_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-
-// one block: cut half-edges -> the neighbours' ghost slots of this iteration's parity, then the flags
+// exact mode: the push is a launch of its own after K1 (the perf kernel's last block does it itself)
 __global__ void __launch_bounds__(1024)
 peer_push_kernel(const double *__restrict__ xc, const int *__restrict__ send_he, const int *__restrict__ send_rank,
                  const int *__restrict__ send_slot, int nsend, Ctrl *ctrl, const PeerView *PVp) {
     if (ctrl->stop && !ctrl->ignore_stop) return;
-    const PeerView &PV = *PVp;
-    const int k = PV.comm[PV.rank]->k + 1, par = k & 1;
-    for (int i = threadIdx.x; i < 5 * nsend; i += blockDim.x) {
-        const int j = i / 5, c = i - 5 * j, q = send_rank[j];
-        PV.xc[q][5 * ((size_t)PV.nHown[q] + (size_t)par * PV.nHghost[q] + send_slot[j]) + c] = xc[5 * (size_t)send_he[j] + c];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < PV.world && ((PV.neighbours >> threadIdx.x) & 1u)) *(volatile int *)&PV.comm[threadIdx.x]->halo_flag[PV.rank] = k;
-}
-// one warp: lane p waits for neighbour p's halo of this iteration
-__global__ void peer_wait_kernel(Ctrl *ctrl, const PeerView *PVp) {
-    if (ctrl->stop && !ctrl->ignore_stop) return;
-    const PeerView &PV = *PVp;
-    PeerComm *me = PV.comm[PV.rank];
-    const int k = me->k + 1, p = threadIdx.x;
-    if (p < PV.world && ((PV.neighbours >> p) & 1u)) {
-        const unsigned long long t0 = gcs_globaltimer();
-        while (*(volatile int *)&me->halo_flag[p] < k)
-            if (gcs_globaltimer() - t0 > GCS_PEER_TIMEOUT_NS) { me->error = 1; break; }
-    }
-    __threadfence_system();
+    peer_push(xc, send_he, send_rank, send_slot, nsend, *PVp);
 }
 // one warp: waits for every rank's sums, adds them in rank order, control step, advances the peer iteration counter
 __global__ void peer_control_kernel(Ctrl *ctrl, GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap, const PeerView *PVp) {
@@ -548,6 +572,7 @@ extern "C" int gcsadmm_destroy(GcsHandle *h) {
     for (void *m : h->ipc_opened) if (m) cudaIpcCloseMemHandle(m);
     { void *pp[] = {h->comm, h->send_he, h->send_rank, h->send_slot, h->PV_dev}; for (void *q : pp) if (q) cudaFree(q); }
     if (h->ticket) cudaFree(h->ticket);
+    if (h->push_ticket) cudaFree(h->push_ticket);
     free_perf(h);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -627,6 +652,7 @@ static int create_impl(GcsHandle *h, const GcsGraph *g) {
     if (h->p.warm_theta > 0.0) UP(ws, (const double *)nullptr, (size_t)g->nV * gcs_ws_stride(h->L));
     UP(partials, (const double *)nullptr, (size_t)h->edge_blocks * NSUMS);
     UP(ticket, (const unsigned int *)nullptr, 1);
+    UP(push_ticket, (const unsigned int *)nullptr, 1);
     h->hist_cap = h->p.max_it + 2;
     UP(hist, (const double *)nullptr, 3 * (size_t)h->hist_cap * h->nP);
 #undef UP
@@ -708,7 +734,8 @@ static GcsStateView state_view(const GcsHandle *h) {
 }
 static int launch_k1(GcsHandle *h) {
     if (h->perf_on) {
-        vertex_perf_kernel<<<h->perf_grid, h->perf_threads, h->perf_smem, h->stream>>>(graph_view(h), state_view(h), h->PT, h->ctrl, h->vprob, h->PL);
+        PeerPush P = {h->send_he, h->send_rank, h->send_slot, h->nsend, h->peer_on ? h->PV_dev : nullptr, h->push_ticket};
+        vertex_perf_kernel<<<h->perf_grid, h->perf_threads, h->perf_smem, h->stream>>>(graph_view(h), state_view(h), h->PT, h->ctrl, h->vprob, h->PL, P);
         return 0;
     }
     vertex_kernel<<<h->k1_blocks, h->k1_warps * 32, h->k1_smem, h->stream>>>(graph_view(h), state_view(h), h->ctrl, h->vprob, h->L, h->p.inner_tol, h->p.inner_max_iter);
@@ -742,8 +769,8 @@ static int launch_ctrl(GcsHandle *h) {
 // everything of an iteration after K1
 static void launch_rest(GcsHandle *h) {
     if (!h->peer_on) { launch_edge(h, 1); return; }          // single GPU: 2 launches per ADMM iteration
-    peer_push_kernel<<<1, 1024, 0, h->stream>>>(h->xc, h->send_he, h->send_rank, h->send_slot, h->nsend, h->ctrl, h->PV_dev);
-    peer_wait_kernel<<<1, 32, 0, h->stream>>>(h->ctrl, h->PV_dev);
+    // perf mode: 3 launches per iteration (K1 + push by its last block | halo wait + edges + sums publish | sums wait + control)
+    if (!h->perf_on) peer_push_kernel<<<1, 1024, 0, h->stream>>>(h->xc, h->send_he, h->send_rank, h->send_slot, h->nsend, h->ctrl, h->PV_dev);
     launch_edge(h, 2);
     peer_control_kernel<<<1, 32, 0, h->stream>>>(h->ctrl, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, h->PV_dev);
 }

@@ -147,15 +147,15 @@ def main(args):
         line = {"metric": bench.METRIC, "value": 1e3 / per, "unit": bench.UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": per, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"grid{G}x{G} 2-D GCS: {g.nV} vertices, {g.nE} directed edges, strips over {world} GPUs",
-                           "mode": bench.MODE_TEXT[headline] + (f", K={args.inner}" if headline == "perf" else ""), "l2": "flushed (256 MiB) before every timed iteration", "burn_in_iterations": burn,
+                           "mode": bench.MODE_TEXT[headline] + (f", K={args.inner}" if headline == "perf" else ""), "l2": "flushed (256 MiB memset in-stream before every timed iteration, outside its event pair; the window is enqueued ahead)", "burn_in_iterations": burn,
                            "halo_half_edges_rank0": int(lp.nH_ghost),
                            "exchange": ("peer memory: cut half-edges and residual sums stored straight into the neighbours' buffers over NVLink, flag-ordered; "
-                                        "no collective call inside the iteration; one CUDA graph per 8 iterations") if use_peer else
+                                        "no collective call inside the iteration; 3 launches per iteration (K1 + halo push by its last block | halo wait + edges + sums | sums wait + control)") if use_peer else
                                        "all_to_all_single(halo) + all_reduce(8 doubles) per iteration, NCCL" + (", one CUDA graph per iteration" if args.dist_graph else "")},
                 "clocks": clocks,
                 "e2e": {"value": n_e2e / e2e, "unit": bench.UNIT, "h2d_bytes_per_step": gs_bytes / n_e2e,
                         "d2h_bytes_per_step": out_bytes / n_e2e, "note": "per rank, from a cold start: local graph upload + (burn_in + K) iterations + solution download; max over ranks"},
-                "gpu_launches": (5 if use_peer else 3) * args.steps,
+                "gpu_launches": ((3 if headline == "perf" else 4) if use_peer else 3) * args.steps,
                 "roofline": {"bound": "hbm", "achieved": (k1b + k2b) / world / (per * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": (k1b + k2b) / world / (per * 1e-3) / 1e9 / peak, "traffic": None,
                              "note": "whole iteration, algorithmic bytes per GPU / max-over-ranks time"}}
