@@ -77,7 +77,7 @@ struct GcsHandle {
     long long n_x, n_mu;
     int dcap, mcap;
     GcsScratchLayout L;
-    int k1_smem, k1_blocks, k1_warps, edge_blocks, edge_per_edge;
+    int k1_smem, k1_blocks, k1_warps, edge_blocks, edge_per_edge, edge_minb;
     // device
     int *poly_off, *he_off, *he_edge, *edge_he_tail, *edge_he_head;
     double *polyA, *polyb, *cent;
@@ -100,7 +100,7 @@ struct GcsHandle {
     GcsPerfLayout PL;
     GcsPerfTables PT;
     long long perf_nblocks;
-    int *p_vclass, *p_cone_off, *p_blk_off, *p_blk_rec, *p_vrec, *p_tile_rec; double *p_cls_tab, *p_cone, *p_tstate, *p_tn, *p_edge_delta;
+    int *p_vclass, *p_cone_off, *p_blk_off, *p_blk_rec, *p_vrec, *p_tile_rec; double *p_cls_tab, *p_cone, *p_tstate, *p_tn, *p_edge_delta, *p_tile_res;
     // one CUDA graph per chunk of `check_every` iterations (own stream only)
     cudaGraphExec_t graph_exec; int graph_iters;
     // peer mode (multi-GPU over NVLink peer memory, one process per GPU): see the "peer mode" section
@@ -229,11 +229,14 @@ __device__ void control_apply(Ctrl *ctrl, const GcsParams &p, long long n_x, lon
     const double nAx = sqrt(s[2]), nBz = sqrt(2.0 * s[3]), nmu = scale * sqrt(s[4]);
     const double eps_pri = sqrt((double)n_x) * p.eps_abs + p.eps_rel * fmax(nAx, nBz);   // :605-610
     const double eps_dual = sqrt((double)n_mu) * p.eps_abs + p.eps_rel * nmu;            // :613-614
-    ctrl->it = it; ctrl->pri = pri; ctrl->dual = dual; ctrl->eps_pri = eps_pri; ctrl->eps_dual = eps_dual;
+    const double inner = sqrt(s[6]);                     // perf mode: residual of the vertex programs' own cone constraints (0 otherwise)
+    ctrl->it = it; ctrl->pri = pri; ctrl->dual = dual; ctrl->eps_pri = eps_pri; ctrl->eps_dual = eps_dual; ctrl->inner = inner;
     ctrl->rho = rho_new; ctrl->mu_scale = scale;
     if (it < hist_cap) { hist[it] = rho_new; hist[hist_cap + it] = pri; hist[2 * hist_cap + it] = dual; }
     if (s[5] != 0.0 || !isfinite(pri) || !isfinite(dual)) { ctrl->diverged = 1; ctrl->stop = 1; return; }  // :662-664
-    const bool opt = p.abs_stop ? (fmax(pri, dual) < p.abs_tol) : (pri < eps_pri && dual < eps_dual);        // :712
+    // abs_stop (the "residual < tol" metric): the inexact x-update's own residual counts too — an iterate whose consensus
+    // residuals are small while its vertex programs still violate their cone constraints is not a solution
+    const bool opt = p.abs_stop ? (fmax(fmax(pri, dual), inner) < p.abs_tol) : (pri < eps_pri && dual < eps_dual);        // :712
     if (opt) { ctrl->opt = 1; ctrl->stop = 1; }
 }
 
@@ -241,11 +244,11 @@ __device__ void control_apply(Ctrl *ctrl, const GcsParams &p, long long n_x, lon
 // applies the control step (fuse = 1), publishes this rank's sums to every peer (fuse = 2) or just leaves them in ctrl->sums (fuse = 0)
 __device__ __forceinline__ void edge_finish(double r2, double dz2, double x2, double z2, double m2, Ctrl *ctrl, double *__restrict__ partials,
                                             unsigned int *ticket, int fuse, const GcsParams &p, long long n_x, long long n_mu, double *hist,
-                                            int hist_cap, const PeerView *PVp) {
+                                            int hist_cap, const PeerView *PVp, const double *__restrict__ tile_res, int ntiles) {
     double bad = 0;
     if (!isfinite(r2) || !isfinite(dz2) || !isfinite(x2) || !isfinite(z2)) bad = 1.0;
     // block reduction (fixed order: shuffles, then warp partials in shared memory)
-    __shared__ double sh[EDGE_THREADS][6];
+    __shared__ double sh[EDGE_THREADS][7];
     __shared__ int is_last;
     double vals[6] = {r2, dz2, x2, z2, m2, bad};
 #pragma unroll
@@ -272,24 +275,26 @@ __device__ __forceinline__ void edge_finish(double r2, double dz2, double x2, do
     if (!is_last) return;
     __threadfence();
     // last block: every block's partials are visible; sum them in an order that does not depend on which block is last
-    double acc[6] = {0, 0, 0, 0, 0, 0};
+    // (seventh sum, perf mode: the tiles' squared inner residuals written by K1 of this iteration)
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
 #pragma unroll
         for (int q = 0; q < 6; ++q) acc[q] += __ldcg(partials + (size_t)b * NSUMS + q);
+    if (tile_res) for (int b = threadIdx.x; b < ntiles; b += blockDim.x) acc[6] += __ldcg(tile_res + b);
 #pragma unroll
-    for (int q = 0; q < 6; ++q) sh[threadIdx.x][q] = acc[q];
+    for (int q = 0; q < 7; ++q) sh[threadIdx.x][q] = acc[q];
     __syncthreads();
     for (int st = EDGE_THREADS / 2; st > 0; st >>= 1) {
         if (threadIdx.x < st)
 #pragma unroll
-            for (int q = 0; q < 6; ++q) sh[threadIdx.x][q] += sh[threadIdx.x + st][q];
+            for (int q = 0; q < 7; ++q) sh[threadIdx.x][q] += sh[threadIdx.x + st][q];
         __syncthreads();
     }
-    if (threadIdx.x < 6) ctrl->sums[threadIdx.x] = sh[0][threadIdx.x];
+    if (threadIdx.x < 7) ctrl->sums[threadIdx.x] = sh[0][threadIdx.x];
     __syncthreads();
     if (fuse == 2) {       // peer mode: this rank's sums into every rank's inbox, then the flag
         const int me = PVp->rank, world = PVp->world, k = PVp->comm[me]->k + 1, par = k & 1;
-        if (threadIdx.x < 6)
+        if (threadIdx.x < 7)
             for (int q = 0; q < world; ++q) PVp->comm[q]->sums_in[par][me][threadIdx.x] = sh[0][threadIdx.x];
         __threadfence_system();
         __syncthreads();
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 6)
 edge_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *__restrict__ edge_he_head,
             const unsigned char *__restrict__ edge_counted, const double *__restrict__ xc, double *__restrict__ mu,
             double *__restrict__ z, Ctrl *ctrl, double *__restrict__ partials, unsigned int *ticket, int fuse,
-            GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap, int nHghost, const PeerView *PVp) {
+            GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap, int nHghost, const PeerView *PVp, const double *__restrict__ tile_res, int ntiles) {
     if (ctrl->stop && !ctrl->ignore_stop) return;
     if (fuse == 2) peer_wait_halo(*PVp);
     const double ms = ctrl->mu_scale, oa = p.outer_alpha, ob = 1.0 - p.outer_alpha;
@@ -341,7 +346,7 @@ edge_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *
         if (ot) { const double r = zn - xt, mn = ms * mt + (zn - at); mu[it_] = mn; r2 += r * r; x2 += xt * xt; m2 += mn * mn; }
         if (oh) { const double r = zn - xh, mn = ms * mh + (zn - ah); mu[ih_] = mn; r2 += r * r; x2 += xh * xh; m2 += mn * mn; }
     }
-    edge_finish(r2, dz2, x2, z2, m2, ctrl, partials, ticket, fuse, p, n_x, n_mu, hist, hist_cap, PVp);
+    edge_finish(r2, dz2, x2, z2, m2, ctrl, partials, ticket, fuse, p, n_x, n_mu, hist, hist_cap, PVp, tile_res, ntiles);
 }
 
 // local frames (perf-mode option, vertex_perf.cuh GcsPerfTables.edge_delta): the consensus constraint of edge e is
@@ -349,11 +354,12 @@ edge_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *
 // so the z-update is the least-squares solve  (I + B'B) z = x_head + B' x_tail  (the duals drop out: B' mu_tail + mu_head = 0 is an
 // invariant of the iteration), closed form per edge; mu_head += z - x_head, mu_tail += B z - x_tail; the dual residual is
 // rho sqrt(|dz|^2 + |B dz|^2).  One thread per edge: the three coupled scalars (p2, y) are needed together.
-__global__ void __launch_bounds__(EDGE_THREADS, 2)
+template <int MINB, bool OA>
+__global__ void __launch_bounds__(EDGE_THREADS, MINB)
 edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *__restrict__ edge_he_head,
                    const unsigned char *__restrict__ edge_counted, const double *__restrict__ edge_delta, const double *__restrict__ xc,
                    double *__restrict__ mu, double *__restrict__ z, Ctrl *ctrl, double *__restrict__ partials, unsigned int *ticket, int fuse,
-                   GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap, int nHghost, const PeerView *PVp) {
+                   GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap, int nHghost, const PeerView *PVp, const double *__restrict__ tile_res, int ntiles) {
     if (ctrl->stop && !ctrl->ignore_stop) return;
     if (fuse == 2) peer_wait_halo(*PVp);
     const double ms = ctrl->mu_scale, oa = p.outer_alpha, ob = 1.0 - p.outer_alpha;
@@ -366,8 +372,12 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
         double xt[5], xh[5], zo[5], mt[5], mh[5];
 #pragma unroll
         for (int c = 0; c < 5; ++c) { xt[c] = pt[c]; xh[c] = ph[c]; zo[c] = z[5 * (size_t)e + c]; }
+        // MINB == 2 (128 registers): the duals are loaded together with the copies (maximum memory-level parallelism per thread);
+        // MINB > 2 (<= 80 / 64 registers, more resident warps): they are loaded after z has been written, one side at a time
+        if (MINB == 2) {
 #pragma unroll
-        for (int c = 0; c < 5; ++c) { mt[c] = ot ? mu[5 * (size_t)ht + c] : 0.0; mh[c] = oh ? mu[5 * (size_t)hh + c] : 0.0; }
+            for (int c = 0; c < 5; ++c) { mt[c] = ot ? mu[5 * (size_t)ht + c] : 0.0; mh[c] = oh ? mu[5 * (size_t)hh + c] : 0.0; }
+        }
         const double d0 = edge_delta ? edge_delta[2 * (size_t)e] : 0.0, d1 = edge_delta ? edge_delta[2 * (size_t)e + 1] : 0.0;
         const double w = edge_counted ? (double)edge_counted[e] : 1.0;
         double zn[5], bz[5], at[5], ah[5];
@@ -375,7 +385,7 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
         // mu-updates; the primal residual keeps the true x.  B' mu_tail + mu_head = 0 stays invariant.
 #pragma unroll
         for (int c = 0; c < 5; ++c) { at[c] = xt[c]; ah[c] = xh[c]; }
-        if (oa != 1.0) {
+        if (OA) {          // (compile-time: without over-relaxation at / ah are xt / xh and cost no registers)
             const double bo[5] = {zo[0], zo[1], zo[2] - d0 * zo[4], zo[3] - d1 * zo[4], zo[4]};
 #pragma unroll
             for (int c = 0; c < 5; ++c) { at[c] = oa * xt[c] + ob * bo[c]; ah[c] = oa * xh[c] + ob * zo[c]; }
@@ -391,16 +401,25 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
         const double db2 = dd[2] - d0 * dd[4], db3 = dd[3] - d1 * dd[4];
         dz2 += 0.5 * w * (2.0 * (dd[0] * dd[0] + dd[1] * dd[1] + dd[4] * dd[4]) + dd[2] * dd[2] + dd[3] * dd[3] + db2 * db2 + db3 * db3);
         z2 += 0.5 * w * (2.0 * (zn[0] * zn[0] + zn[1] * zn[1] + zn[4] * zn[4]) + zn[2] * zn[2] + zn[3] * zn[3] + bz[2] * bz[2] + bz[3] * bz[3]);
+        if (MINB > 2) asm volatile("" ::: "memory");     // keeps the compiler from hoisting the dual loads above this point
         if (ot) {
+            if (MINB > 2) {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) mt[c] = mu[5 * (size_t)ht + c];
+            }
 #pragma unroll
             for (int c = 0; c < 5; ++c) { const double r = bz[c] - xt[c], mn = ms * mt[c] + (bz[c] - at[c]); mu[5 * (size_t)ht + c] = mn; r2 += r * r; x2 += xt[c] * xt[c]; m2 += mn * mn; }
         }
         if (oh) {
+            if (MINB > 2) {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) mh[c] = mu[5 * (size_t)hh + c];
+            }
 #pragma unroll
             for (int c = 0; c < 5; ++c) { const double r = zn[c] - xh[c], mn = ms * mh[c] + (zn[c] - ah[c]); mu[5 * (size_t)hh + c] = mn; r2 += r * r; x2 += xh[c] * xh[c]; m2 += mn * mn; }
         }
     }
-    edge_finish(r2, dz2, x2, z2, m2, ctrl, partials, ticket, fuse, p, n_x, n_mu, hist, hist_cap, PVp);
+    edge_finish(r2, dz2, x2, z2, m2, ctrl, partials, ticket, fuse, p, n_x, n_mu, hist, hist_cap, PVp, tile_res, ntiles);
 }
 
 // ------------------------------------------------------------------------------------------ peer mode (kernels)
@@ -425,7 +444,7 @@ __global__ void peer_control_kernel(Ctrl *ctrl, GcsParams p, long long n_x, long
     __threadfence_system();
     __syncwarp();
     if (threadIdx.x == 0) {
-        for (int j = 0; j < 6; ++j) {
+        for (int j = 0; j < 7; ++j) {
             double s = 0.0;
             for (int r = 0; r < PV.world; ++r) s += *(volatile double *)&me->sums_in[par][r][j];
             ctrl->sums[j] = s;
@@ -547,10 +566,10 @@ static int reset_ctrl(GcsHandle *h) {
 }
 
 static void free_perf(GcsHandle *h) {
-    void *pp[] = {h->p_vclass, h->p_cone_off, h->p_blk_off, h->p_blk_rec, h->p_vrec, h->p_tile_rec, h->p_cls_tab, h->p_cone, h->p_tstate, h->p_tn, h->p_edge_delta};
+    void *pp[] = {h->p_vclass, h->p_cone_off, h->p_blk_off, h->p_blk_rec, h->p_vrec, h->p_tile_rec, h->p_cls_tab, h->p_cone, h->p_tstate, h->p_tn, h->p_edge_delta, h->p_tile_res};
     for (void *q : pp) if (q) cudaFree(q);
     h->p_vclass = h->p_cone_off = h->p_blk_off = h->p_blk_rec = h->p_vrec = h->p_tile_rec = nullptr;
-    h->p_cls_tab = h->p_cone = h->p_tstate = h->p_tn = h->p_edge_delta = nullptr;
+    h->p_cls_tab = h->p_cone = h->p_tstate = h->p_tn = h->p_edge_delta = h->p_tile_res = nullptr;
     h->perf_on = 0;
 }
 static void drop_graph(GcsHandle *h) {
@@ -633,6 +652,8 @@ static int create_impl(GcsHandle *h, const GcsGraph *g) {
         // one thread per (edge, scalar) 68 us (6 blocks per SM) .. 84 us (24); the env variables are tuning knobs
         const char *bps = getenv("GCS_EDGE_BLOCKS_PER_SM"), *ek = getenv("GCS_EDGE_KERNEL");
         h->edge_per_edge = !(ek && !strcmp(ek, "per_scalar"));
+        const char *mb = getenv("GCS_EDGE_MINB");        // register budget of the per-edge kernel: 2, 3 or 4 resident blocks per SM
+        h->edge_minb = mb && atoi(mb) >= 2 && atoi(mb) <= 4 ? atoi(mb) : 2;
         const long long cap = (long long)prop.multiProcessorCount * (bps && atoi(bps) > 0 ? atoi(bps) : (h->edge_per_edge ? 4 : 6));
         h->edge_blocks = (int)(need < 1 ? 1 : (need > cap ? cap : need));
     }
@@ -753,12 +774,16 @@ static int launch_edge(GcsHandle *h, int fuse) {
         int blocks = (h->nE + EDGE_THREADS - 1) / EDGE_THREADS;
         if (blocks > h->edge_blocks) blocks = h->edge_blocks;
         if (blocks < 1) blocks = 1;
-        edge_frames_kernel<<<blocks, EDGE_THREADS, 0, h->stream>>>(h->nE, h->nHown, h->edge_he_tail, h->edge_he_head, h->edge_counted, h->perf_on ? h->p_edge_delta : nullptr, h->xc, h->mu,
-                                                                   h->z, h->ctrl, h->partials, h->ticket, fuse, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, h->nHghost, h->PV_dev);
+#define EDGE_FRAMES(MINB) if (h->p.outer_alpha != 1.0) EDGE_FRAMES_(MINB, true); else EDGE_FRAMES_(MINB, false)
+#define EDGE_FRAMES_(MINB, OA) edge_frames_kernel<MINB, OA><<<blocks, EDGE_THREADS, 0, h->stream>>>(h->nE, h->nHown, h->edge_he_tail, h->edge_he_head, h->edge_counted, \
+            h->perf_on ? h->p_edge_delta : nullptr, h->xc, h->mu, h->z, h->ctrl, h->partials, h->ticket, fuse, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, h->nHghost, h->PV_dev, h->perf_on ? h->p_tile_res : nullptr, h->perf_on ? h->PT.ntiles : 0)
+        if (h->edge_minb == 4) { EDGE_FRAMES(4); } else if (h->edge_minb == 3) { EDGE_FRAMES(3); } else { EDGE_FRAMES(2); }
+#undef EDGE_FRAMES
+#undef EDGE_FRAMES_
         return 0;
     }
     edge_kernel<<<h->edge_blocks, EDGE_THREADS, 0, h->stream>>>(h->nE, h->nHown, h->edge_he_tail, h->edge_he_head, h->edge_counted, h->xc, h->mu, h->z, h->ctrl,
-                                                                h->partials, h->ticket, fuse, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, h->nHghost, h->PV_dev);
+                                                                h->partials, h->ticket, fuse, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, h->nHghost, h->PV_dev, h->perf_on ? h->p_tile_res : nullptr, h->perf_on ? h->PT.ntiles : 0);
     return 0;
 }
 static int launch_ctrl(GcsHandle *h) {
@@ -807,7 +832,7 @@ static int fetch_ctrl(GcsHandle *h) {
 static void fill_status_one(const Ctrl *c, GcsStatus *st) {
     st->iterations = c->it; st->converged = c->opt; st->diverged = c->diverged; st->inner_fail = c->inner_fail;
     st->inner_iters = (int64_t)c->inner_iters; st->skipped = (int64_t)c->skipped; st->rho = c->rho; st->pri_res = c->pri; st->dual_res = c->dual;
-    st->eps_pri = c->eps_pri; st->eps_dual = c->eps_dual;
+    st->eps_pri = c->eps_pri; st->eps_dual = c->eps_dual; st->inner_res = c->inner;
 }
 // batched handles: iterations = max, converged = all, residuals = worst problem, counters summed
 static void fill_status(const GcsHandle *h, GcsStatus *st) {
@@ -819,6 +844,7 @@ static void fill_status(const GcsHandle *h, GcsStatus *st) {
         st->inner_fail += t.inner_fail; st->inner_iters += t.inner_iters; st->skipped += t.skipped;
         if (t.pri_res > st->pri_res) { st->pri_res = t.pri_res; st->eps_pri = t.eps_pri; }
         if (t.dual_res > st->dual_res) { st->dual_res = t.dual_res; st->eps_dual = t.eps_dual; }
+        if (t.inner_res > st->inner_res) st->inner_res = t.inner_res;
     }
 }
 static bool all_stopped(const GcsHandle *h) {
@@ -1182,6 +1208,7 @@ extern "C" int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *c) {
     }
     if (!rc) rc = upload(&h->p_tstate, (const double *)nullptr, 12 * (size_t)c->n_blocks);
     if (!rc) rc = upload(&h->p_tn, (const double *)nullptr, 2 * (size_t)h->nV);
+    if (!rc) rc = upload(&h->p_tile_res, (const double *)nullptr, (size_t)c->n_tiles);
     if (!rc && c->edge_delta) rc = upload(&h->p_edge_delta, c->edge_delta, 2 * (size_t)h->nE);
     if (rc) { free_perf(h); return rc; }
     h->perf_nblocks = c->n_blocks;
@@ -1189,7 +1216,7 @@ extern "C" int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *c) {
     h->PT.vclass = h->p_vclass; h->PT.cls_tab = h->p_cls_tab; h->PT.cone_off = h->p_cone_off; h->PT.cone = h->p_cone;
     h->PT.blk_off = h->p_blk_off; h->PT.blk_rec = h->p_blk_rec; h->PT.vrec = h->p_vrec; h->PT.tile_rec = h->p_tile_rec;
     h->PT.ntiles = c->n_tiles; h->PT.tstate = h->p_tstate; h->PT.tn = h->p_tn; h->PT.inner_iters = c->inner_iters;
-    h->PT.alpha = c->alpha; h->PT.kappa = c->kappa; h->PT.theta = c->theta > 0.0 ? c->theta : 1.0; h->PT.edge_delta = h->p_edge_delta;
+    h->PT.alpha = c->alpha; h->PT.kappa = c->kappa; h->PT.theta = c->theta > 0.0 ? c->theta : 1.0; h->PT.edge_delta = h->p_edge_delta; h->PT.tile_res = h->p_tile_res;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
     const size_t bytes = (size_t)(h->PL.work + 2 * h->PL.stage) * sizeof(double);      // work arrays + two stage buffers

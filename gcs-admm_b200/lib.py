@@ -55,7 +55,7 @@ class GcsPerfConfig(C.Structure):
 class GcsStatus(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("diverged", C.c_int32),
                 ("inner_fail", C.c_int32), ("inner_iters", C.c_int64), ("skipped", C.c_int64), ("rho", C.c_double), ("pri_res", C.c_double),
-                ("dual_res", C.c_double), ("eps_pri", C.c_double), ("eps_dual", C.c_double)]
+                ("dual_res", C.c_double), ("eps_pri", C.c_double), ("eps_dual", C.c_double), ("inner_res", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -212,8 +212,20 @@ class Solver:
             c.edge_delta = _ptr(keep["edge_delta"])
         _check(load().gcsadmm_enable_perf(self._h, C.byref(c)))
         self._frames = T.get("edge_delta") is not None
+        self._edge_delta = keep.get("edge_delta")
         self.perf = dict(inner_iters=int(inner_iters), alpha=float(alpha), kappa=float(T["kappa"]), classes=len(T["classes"]),
                          n_blocks=c.n_blocks, n_tiles=c.n_tiles, frames="local" if self._frames else "global")
+        return self
+
+    def warm_start(self, field="dijkstra", rho=None):
+        """perf mode, before the first iteration: duals from a cost-to-go field over the portal graph (``warmstart.dual_start``);
+        primal variables stay zero.  Same fixed point, far fewer iterations on large maps."""
+        from . import warmstart
+        if not getattr(self, "perf", None):
+            raise GcsError(-1, "warm_start is an option of the perf mode (enable_perf first)")
+        rho = float(self.status()["rho"] if rho is None else rho)
+        mu = warmstart.dual_start(self.g, self._edge_delta, rho, field=field)
+        self.set_state(None, mu, None, rho, 0)
         return self
 
     def perf_state(self):

@@ -43,7 +43,7 @@ def perf_abs_tol(g):
 
 
 def solve(As, bs, n, *, device=0, max_it=MAX_IT, round_solution=True, seed=None, verbose=False,
-          graph=None, one_call=True, mode="parity", inner_iters=1, rounding_kw=None, frames="global", **params):
+          graph=None, one_call=True, mode="parity", inner_iters=1, rounding_kw=None, frames="global", warm_start=None, **params):
     """Solve the convex relaxation of the GCS shortest-path problem by full-vertex-split ADMM.
 
     Parameters mirror the reference's literals (``rho0, tau_incr, tau_decr, nu, frac, eps_abs,
@@ -61,6 +61,9 @@ def solve(As, bs, n, *, device=0, max_it=MAX_IT, round_solution=True, seed=None,
     ``rounding_kw``: overrides of the rounding literals ``N=5, M=20`` (reference ``GCS_utils.py:92``).
     ``frames="local"`` (perf mode): vertex programs in coordinates centred on their own regions — the same problem, a
     translation-invariant and much better conditioned ADMM on large maps (``perf.perf_tables``).
+    ``warm_start="dijkstra"`` (perf mode): the duals start from a shortest-path cost-to-go field over the portal graph instead
+    of zero (``warmstart.py``; the reference starts cold, ``admm_solver_v3.py:621-652``) — same fixed point, about half the
+    iterations on large maps; ``outer_alpha`` (1 < a < 2, e.g. 1.7) over-relaxes the consensus step.
     """
     if int(n) != 2:
         raise ValueError("gcs-admm_b200 implements the 2-D case (n = 2), like all reference data")
@@ -85,6 +88,8 @@ def solve(As, bs, n, *, device=0, max_it=MAX_IT, round_solution=True, seed=None,
         s = lib.Solver(g, device=device, max_it=max_it, **params)
         if mode == "perf":
             s.enable_perf(inner_iters=inner_iters, frames=frames)
+            if warm_start:
+                s.warm_start(field=warm_start)
         st = s.run(max_it)
         x_v, z_v, y_v, z_e = s.solution()
         rho, pri, dual = s.history()

@@ -106,6 +106,8 @@ typedef struct GcsStatus {
     int64_t inner_iters;         /* interior-point iterations summed over all vertex programs */
     int64_t skipped;             /* vertex programs answered by the zero-target shortcut */
     double rho, pri_res, dual_res, eps_pri, eps_dual;
+    double inner_res;            /* perf mode: residual of the vertex programs' own cone constraints, |(M u + m0) - c| over all pairs
+                                    (0 in the exact mode); part of the abs_stop test */
 } GcsStatus;
 
 const char *gcsadmm_version(void);

@@ -182,3 +182,22 @@ def test_batched_perf_queries_equal_individual_solves():
         assert np.allclose(zs, z_v[v0:v1], rtol=0, atol=1e-12) and np.allclose(es, z_e[e0:e1], rtol=0, atol=1e-12)
         s.close()
     sb.close()
+
+
+def test_inner_residual_is_part_of_the_absolute_stop_rule():
+    """perf mode: GcsStatus.inner_res = |(M u + m0) - c| over all (point, flow) pairs (how far the vertex programs' own cone
+    constraints are from being met) is reported every iteration and must be below abs_tol too before the run stops"""
+    from gcs_admm_b200.lib import Solver
+    As, bs, n, d, keys = load_golden("benchmark2")
+    g = pack_graph(As, bs)
+    s = Solver(g, max_it=400000, abs_stop=1, abs_tol=3e-5, frac=0.0, check_every=64).enable_perf(inner_iters=1)
+    s.step(50)
+    st = s.status()
+    assert np.isfinite(st["inner_res"]) and st["inner_res"] > 3e-5        # far from converged after 50 iterations
+    st = s.run()
+    assert st["converged"] == 1 and max(st["pri_res"], st["dual_res"], st["inner_res"]) < 3e-5
+    s.close()
+    e = Solver(g)
+    e.step(3)
+    assert e.status()["inner_res"] == 0.0                                   # exact mode: the vertex programs are solved to 1e-8
+    e.close()
