@@ -221,7 +221,8 @@ def main():
                          "nccl = all_to_all_single + all_reduce per iteration")
     ap.add_argument("--dist-graph", action="store_true", help="N > 1, --dist nccl: replay one captured CUDA graph per ADMM iteration (kernels + NCCL collectives)")
     ap.add_argument("--residual-budget", type=float, default=-1.0,
-                    help="seconds allowed for the time-to-residual-1e-4 run (perf mode, cold start); -1: 240 for the metric workload on 1 GPU, else 0")
+                    help="seconds allowed for the time-to-residual-1e-4 run (perf mode); -1: 330 for the metric workload on 1 GPU, else 0; N > 1: any value > 0 enables the run (bounded by --residual-cap)")
+    ap.add_argument("--residual-cap", type=int, default=1_200_000, help="N > 1: iteration cap of the time-to-residual run (ranks cannot agree on a wall-clock budget)")
     ap.add_argument("--outer-alpha", type=float, default=1.0, help="over-relaxation of the consensus step in the time-to-residual run")
     args = ap.parse_args()
     if args.grid:

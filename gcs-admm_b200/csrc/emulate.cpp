@@ -74,7 +74,8 @@ extern "C" int gcsemu_vertex_update_perf_all(int nV, int nE, const int *poly_off
         for (int t = 0; t < ntiles; ++t) {
             memset(S, poison, sizeof(double) * L.total);
             Ctrl local = ctrl;
-            gcs_perf_tile(G, St, T, L, S, S + L.work, t, &local, 0);
+            double rin = 0.0;
+            gcs_perf_tile<false>(G, St, T, L, S, S + L.work, t, &local, 0, rin);
         }
         free(S);
     }

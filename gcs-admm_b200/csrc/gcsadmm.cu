@@ -97,6 +97,7 @@ struct GcsHandle {
     void *flush_buf; size_t flush_bytes;
     // perf mode (inexact x-update by K closed-form splitting iterations)
     int perf_on, perf_smem, perf_threads, perf_grid;
+    int inner_on;       // perf mode: the K1 variant that also produces the inner residual is in use (switched on by gcsadmm_run near convergence)
     GcsPerfLayout PL;
     GcsPerfTables PT;
     long long perf_nblocks;
@@ -163,6 +164,7 @@ __device__ __forceinline__ void peer_wait_halo(const PeerView &PV) {
 // (<= 256 (point, flow) pairs per tile).  Two stage buffers: while a block computes tile i from one, the bulk copies (TMA unit,
 // mbarrier-signalled) of tile i + gridDim.x fill the other, and the bulk stores of tile i - gridDim.x drain — the DRAM latency of
 // the per-tile state, cone records and descriptors never sits on the critical path.  ~43 KB of shared memory per block.
+template <bool INNER>
 __global__ void __launch_bounds__(GCS_PERF_THREADS, 4)
 vertex_perf_kernel(GcsGraphView G, GcsStateView St, GcsPerfTables T, Ctrl *ctrl_all, const int *__restrict__ vprob, GcsPerfLayout L, PeerPush P) {
     extern __shared__ __align__(16) double smem[];
@@ -179,6 +181,7 @@ vertex_perf_kernel(GcsGraphView G, GcsStateView St, GcsPerfTables T, Ctrl *ctrl_
     }
     __syncthreads();                   // the barrier objects are initialised before anybody polls them
     unsigned phase = 0;                // bit b: parity of the next completion of bar[b]
+    double rin = 0.0;                  // INNER: this thread's share of the block's squared inner residual
     for (int buf = 0; tile < T.ntiles; tile += gridDim.x, buf ^= 1) {
         const int next = tile + gridDim.x;
         if (threadIdx.x == 0 && next < T.ntiles) {
@@ -187,10 +190,22 @@ vertex_perf_kernel(GcsGraphView G, GcsStateView St, GcsPerfTables T, Ctrl *ctrl_
         }
         gcs_mbar_wait(&bar[buf], (phase >> buf) & 1u);
         phase ^= 1u << buf;
-        gcs_perf_tile(G, St, T, L, smem, STAGE(buf), tile, ctrl_all, vprob);
+        gcs_perf_tile<INNER>(G, St, T, L, smem, STAGE(buf), tile, ctrl_all, vprob, rin);
     }
     if (threadIdx.x == 0) gcs_bulk_wait_read();   // shared memory stays valid until the last stores have read it
 #undef STAGE
+    if (INNER) {     // one partial per thread block, summed in a fixed order (static tile assignment: reproducible run to run)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) rin += __shfl_xor_sync(0xffffffffu, rin, o);
+        __syncthreads();                                  // the work arrays are free
+        if ((threadIdx.x & 31) == 0) smem[L.rin + (threadIdx.x >> 5)] = rin;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) s += smem[L.rin + w2];
+            T.tile_res[blockIdx.x] = s;
+        }
+    }
     if (P.PV) {      // peer mode: the LAST block to finish pushes the cut half-edges to the neighbours (no separate launch)
         __shared__ int is_last;
         __threadfence();
@@ -229,14 +244,15 @@ __device__ void control_apply(Ctrl *ctrl, const GcsParams &p, long long n_x, lon
     const double nAx = sqrt(s[2]), nBz = sqrt(2.0 * s[3]), nmu = scale * sqrt(s[4]);
     const double eps_pri = sqrt((double)n_x) * p.eps_abs + p.eps_rel * fmax(nAx, nBz);   // :605-610
     const double eps_dual = sqrt((double)n_mu) * p.eps_abs + p.eps_rel * nmu;            // :613-614
-    const double inner = sqrt(s[6]);                     // perf mode: residual of the vertex programs' own cone constraints (0 otherwise)
+    const double inner = s[6] < 0.0 ? -1.0 : sqrt(s[6]);   // perf mode: residual of the vertex programs' own cone constraints (-1: not computed
+                                                           // in this iteration, 0 in the exact mode)
     ctrl->it = it; ctrl->pri = pri; ctrl->dual = dual; ctrl->eps_pri = eps_pri; ctrl->eps_dual = eps_dual; ctrl->inner = inner;
     ctrl->rho = rho_new; ctrl->mu_scale = scale;
     if (it < hist_cap) { hist[it] = rho_new; hist[hist_cap + it] = pri; hist[2 * hist_cap + it] = dual; }
     if (s[5] != 0.0 || !isfinite(pri) || !isfinite(dual)) { ctrl->diverged = 1; ctrl->stop = 1; return; }  // :662-664
     // abs_stop (the "residual < tol" metric): the inexact x-update's own residual counts too — an iterate whose consensus
     // residuals are small while its vertex programs still violate their cone constraints is not a solution
-    const bool opt = p.abs_stop ? (fmax(fmax(pri, dual), inner) < p.abs_tol) : (pri < eps_pri && dual < eps_dual);        // :712
+    const bool opt = p.abs_stop ? (inner >= 0.0 && fmax(fmax(pri, dual), inner) < p.abs_tol) : (pri < eps_pri && dual < eps_dual);        // :712
     if (opt) { ctrl->opt = 1; ctrl->stop = 1; }
 }
 
@@ -280,7 +296,8 @@ __device__ __forceinline__ void edge_finish(double r2, double dz2, double x2, do
     for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
 #pragma unroll
         for (int q = 0; q < 6; ++q) acc[q] += __ldcg(partials + (size_t)b * NSUMS + q);
-    if (tile_res) for (int b = threadIdx.x; b < ntiles; b += blockDim.x) acc[6] += __ldcg(tile_res + b);
+    if (tile_res) { for (int b = threadIdx.x; b < ntiles; b += blockDim.x) acc[6] += __ldcg(tile_res + b); }
+    else if (ntiles < 0 && threadIdx.x == 0) acc[6] = -1.0;           // perf mode, inner residual not computed in this iteration
 #pragma unroll
     for (int q = 0; q < 7; ++q) sh[threadIdx.x][q] = acc[q];
     __syncthreads();
@@ -756,12 +773,16 @@ static GcsStateView state_view(const GcsHandle *h) {
 static int launch_k1(GcsHandle *h) {
     if (h->perf_on) {
         PeerPush P = {h->send_he, h->send_rank, h->send_slot, h->nsend, h->peer_on ? h->PV_dev : nullptr, h->push_ticket};
-        vertex_perf_kernel<<<h->perf_grid, h->perf_threads, h->perf_smem, h->stream>>>(graph_view(h), state_view(h), h->PT, h->ctrl, h->vprob, h->PL, P);
+        if (h->inner_on) vertex_perf_kernel<true><<<h->perf_grid, h->perf_threads, h->perf_smem, h->stream>>>(graph_view(h), state_view(h), h->PT, h->ctrl, h->vprob, h->PL, P);
+        else vertex_perf_kernel<false><<<h->perf_grid, h->perf_threads, h->perf_smem, h->stream>>>(graph_view(h), state_view(h), h->PT, h->ctrl, h->vprob, h->PL, P);
         return 0;
     }
     vertex_kernel<<<h->k1_blocks, h->k1_warps * 32, h->k1_smem, h->stream>>>(graph_view(h), state_view(h), h->ctrl, h->vprob, h->L, h->p.inner_tol, h->p.inner_max_iter);
     return 0;
 }
+// (tile_res, n) of the edge kernels: perf mode with the inner residual on -> the K1 blocks' partials; perf mode without -> (null, -1):
+// "not computed this iteration" (sums[6] = -1, the absolute stop test cannot pass); exact mode -> (null, 0): sums[6] = 0
+#define INNER_ARGS(h) ((h)->perf_on && (h)->inner_on ? (h)->p_tile_res : nullptr), ((h)->perf_on && (h)->nP == 1 ? ((h)->inner_on ? (h)->perf_grid : -1) : 0)
 // K2-K5.  fuse: the control step runs inside the edge kernel's last block (single GPU); otherwise only sums[] is produced
 static int launch_edge(GcsHandle *h, int fuse) {
     if (h->nP > 1) {   // edges, sums and control of every problem in one launch
@@ -776,14 +797,14 @@ static int launch_edge(GcsHandle *h, int fuse) {
         if (blocks < 1) blocks = 1;
 #define EDGE_FRAMES(MINB) if (h->p.outer_alpha != 1.0) EDGE_FRAMES_(MINB, true); else EDGE_FRAMES_(MINB, false)
 #define EDGE_FRAMES_(MINB, OA) edge_frames_kernel<MINB, OA><<<blocks, EDGE_THREADS, 0, h->stream>>>(h->nE, h->nHown, h->edge_he_tail, h->edge_he_head, h->edge_counted, \
-            h->perf_on ? h->p_edge_delta : nullptr, h->xc, h->mu, h->z, h->ctrl, h->partials, h->ticket, fuse, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, h->nHghost, h->PV_dev, h->perf_on ? h->p_tile_res : nullptr, h->perf_on ? h->PT.ntiles : 0)
+            h->perf_on ? h->p_edge_delta : nullptr, h->xc, h->mu, h->z, h->ctrl, h->partials, h->ticket, fuse, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, h->nHghost, h->PV_dev, INNER_ARGS(h))
         if (h->edge_minb == 4) { EDGE_FRAMES(4); } else if (h->edge_minb == 3) { EDGE_FRAMES(3); } else { EDGE_FRAMES(2); }
 #undef EDGE_FRAMES
 #undef EDGE_FRAMES_
         return 0;
     }
     edge_kernel<<<h->edge_blocks, EDGE_THREADS, 0, h->stream>>>(h->nE, h->nHown, h->edge_he_tail, h->edge_he_head, h->edge_counted, h->xc, h->mu, h->z, h->ctrl,
-                                                                h->partials, h->ticket, fuse, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, h->nHghost, h->PV_dev, h->perf_on ? h->p_tile_res : nullptr, h->perf_on ? h->PT.ntiles : 0);
+                                                                h->partials, h->ticket, fuse, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, h->nHghost, h->PV_dev, INNER_ARGS(h));
     return 0;
 }
 static int launch_ctrl(GcsHandle *h) {
@@ -888,6 +909,12 @@ extern "C" int gcsadmm_run(GcsHandle *h, int max_iters, GcsStatus *st) {
         CK(cudaGetLastError());
         rc = fetch_ctrl(h); if (rc) return rc;
         done += chunk;
+        if (h->perf_on && h->nP == 1 && h->p.abs_stop) {
+            // near the absolute target the K1 variant that also measures the inner residual takes over (the stop test needs it);
+            // far from it the throughput variant runs.  Every rank of a partitioned run sees the same control block, so all switch together.
+            const int want = fmax(h->ctrl_host->pri, h->ctrl_host->dual) < 4.0 * h->p.abs_tol;
+            if (want != h->inner_on) { h->inner_on = want; drop_graph(h); }
+        }
     }
     if (st) fill_status(h, st);
     if (any_diverged(h)) return set_err(GCS_E_DIVERGED, "non-finite residuals (divergence)%s", "");
@@ -1231,8 +1258,10 @@ extern "C" int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *c) {
         const long long cap = (long long)prop.multiProcessorCount * per_sm;
         h->perf_grid = (int)(c->n_tiles < cap ? c->n_tiles : cap);
     }
-    CK(cudaFuncSetAttribute(vertex_perf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->perf_smem));
-    CK(cudaFuncSetAttribute(vertex_perf_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(vertex_perf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->perf_smem));
+    CK(cudaFuncSetAttribute(vertex_perf_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(vertex_perf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->perf_smem));
+    CK(cudaFuncSetAttribute(vertex_perf_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     perf_init_dead_kernel<<<(h->nV + 255) / 256, 256, 0, h->stream>>>(graph_view(h), state_view(h));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));

@@ -69,7 +69,7 @@ struct GcsPerfTables {
     const double *edge_delta;  // [nE][2] or null.  Non-null = LOCAL FRAMES: every vertex program works in coordinates centred on its
                                // own region (polytopes / cones shifted by cent[v]); the two copies of an edge e = (u, w) then agree through
                                // x_head = z_e,  x_tail = B_e z_e  with  B_e (p1, p2, y) = (p1, p2 - y delta_e, y),  delta_e = cent[u] - cent[w]
-    double *tile_res;          // [ntiles] or null (host emulation); out: squared INNER residual of the tile, sum over its pairs of |(M u + m0) - c|^2 after the last pass
+    double *tile_res;          // [grid] or null (host emulation); out: squared INNER residual summed over the tiles a thread block walked (INNER kernel variant)
 };
 
 // shared memory of one tile (offsets in doubles).  Two regions: the STAGED arrays that arrive by bulk copies (state t, cone
@@ -265,8 +265,12 @@ __device__ __forceinline__ void gcs_perf_stage(const GcsPerfTables &T, const Gcs
 
 // x-update of one tile of vertices in perf mode.  S: work arrays, B: the tile's staged arrays (device build: already filled by
 // gcs_perf_stage and waited for; the new state leaves B by bulk stores that the CALLER waits for before B is refilled).
+// INNER: also accumulate (into `rin`, per thread) the squared inner residual  |(M u + m0) - c|^2  of the tile's pairs after the
+// last pass — compiled in only for the kernel variant the host switches to near convergence (gcsadmm_run), so the throughput
+// path carries none of it.
+template <bool INNER>
 GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const GcsPerfTables &T, const GcsPerfLayout &L,
-                           double *S, double *B, int tile, Ctrl *ctrl_all, const int *vprob) {
+                           double *S, double *B, int tile, Ctrl *ctrl_all, const int *vprob, double &rin) {
     // single problem: rho / mu_scale are uniform — loaded once into registers here
     // (batched problems: per vertex, from its problem's control block)
     const double rho_u = ctrl_all->rho, ms_u = ctrl_all->mu_scale;
@@ -340,7 +344,6 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
         St.xc[5 * (size_t)h + c] = x;
     }
     const double alpha = T.alpha, kappa = T.kappa;
-    double rin = 0.0;              // this thread's share of the tile's squared inner residual (last pass)
     for (int it = 0; it < T.inner_iters; ++it) {
         const bool last = it + 1 == T.inner_iters;
         // ---- P2: c-step.  d = c - lam (what the v-step sees) replaces t in place; e = (1 - alpha) c + lam waits for the t-step
@@ -420,7 +423,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
             double p0 = gcs_block_u(rS, co, tab, info, b, 2 * i), p1 = gcs_block_u(rS, co, tab, info, b, 2 * i + 1), p2 = gcs_block_u(rS, co, tab, info, b, 4);
             if (fam) { p0 = co[2 * i] - p0; p1 = co[2 * i + 1] - p1; p2 = 1.0 - p2; }
             double *t = tS + 3 * p;
-            if (last) {      // inner residual  (M u + m0) - c  of the pair:  t holds d = c - lam, e = (1 - alpha) c + lam  =>  c = (d + e) / (2 - alpha)
+            if (INNER && last) {      // inner residual  (M u + m0) - c  of the pair:  t holds d = c - lam, e = (1 - alpha) c + lam  =>  c = (d + e) / (2 - alpha)
                 const double ic = 1.0 / (2.0 - alpha), r0 = p0 - ic * (t[0] + e[0]), r1 = p1 - ic * (t[1] + e[1]), r2_ = p2 - ic * (t[2] + e[2]);
                 rin += r0 * r0 + r1 * r1 + r2_ * r2_;
             }
@@ -430,7 +433,7 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
             const int *w = vi + GCS_VI_N * i;
             if (!ACT_W || !w[GCS_VI_NB]) continue;
             const double *zz = cout + GCS_NCX * i + 4;
-            if (last) {
+            if (INNER && last) {
                 const double ic = 1.0 / (2.0 - alpha), r0 = (zz[0] - zz[2]) - ic * (tnS[2 * i] + enS[2 * i]), r1 = (zz[1] - zz[3]) - ic * (tnS[2 * i + 1] + enS[2 * i + 1]);
                 rin += r0 * r0 + r1 * r1;
             }
@@ -464,18 +467,11 @@ GCS_DEV void gcs_perf_tile(const GcsGraphView &G, const GcsStateView &St, const 
 #if defined(GCS_EMULATE)
     memcpy(T.tstate + 12 * (size_t)b0, tS, sizeof(double) * 12 * nb);
     memcpy(T.tn + 2 * (size_t)v0, tnS, sizeof(double) * 2 * nvt);
-    if (T.tile_res) T.tile_res[tile] = rin;
     if (!vprob) ctrl_all->inner_iters += (unsigned long long)T.inner_iters * (unsigned long long)nvt;
 #else
-#pragma unroll
-    for (int o = 16; o; o >>= 1) rin += __shfl_xor_sync(0xffffffffu, rin, o);
-    if ((threadIdx.x & 31) == 0) S[L.rin + (threadIdx.x >> 5)] = rin;
     gcs_fence_async_smem();
     GCS_CTA_SYNC();
     if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) s += S[L.rin + w2];     // fixed order: the sum does not depend on timing
-        T.tile_res[tile] = s;
         if (nb) gcs_bulk_s2g(T.tstate + 12 * (size_t)b0, tS, (unsigned)(sizeof(double) * 12 * nb));
         gcs_bulk_s2g(T.tn + 2 * (size_t)v0, tnS, (unsigned)(sizeof(double) * 2 * nvt));
         gcs_bulk_commit();

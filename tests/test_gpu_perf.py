@@ -186,16 +186,16 @@ def test_batched_perf_queries_equal_individual_solves():
 
 def test_inner_residual_is_part_of_the_absolute_stop_rule():
     """perf mode: GcsStatus.inner_res = |(M u + m0) - c| over all (point, flow) pairs (how far the vertex programs' own cone
-    constraints are from being met) is reported every iteration and must be below abs_tol too before the run stops"""
+    constraints are from being met).  It is produced by a second variant of K1 that gcsadmm_run switches to once the consensus
+    residuals are within 4x of abs_tol (-1 = not computed in the last iteration), and must be below abs_tol too for the stop."""
     from gcs_admm_b200.lib import Solver
     As, bs, n, d, keys = load_golden("benchmark2")
     g = pack_graph(As, bs)
     s = Solver(g, max_it=400000, abs_stop=1, abs_tol=3e-5, frac=0.0, check_every=64).enable_perf(inner_iters=1)
     s.step(50)
-    st = s.status()
-    assert np.isfinite(st["inner_res"]) and st["inner_res"] > 3e-5        # far from converged after 50 iterations
+    assert s.status()["inner_res"] == -1.0                                  # throughput variant: not computed, and the run cannot stop
     st = s.run()
-    assert st["converged"] == 1 and max(st["pri_res"], st["dual_res"], st["inner_res"]) < 3e-5
+    assert st["converged"] == 1 and 0.0 <= st["inner_res"] < 3e-5 and max(st["pri_res"], st["dual_res"]) < 3e-5
     s.close()
     e = Solver(g)
     e.step(3)
