@@ -14,13 +14,15 @@ computation over the PORTALS (one point in the overlap of every edge's two regio
 discretisation of the portal points in O(|E| log |E|) on the host; the ADMM then only has to correct local errors.
 
 The primal variables and the inner (cone-splitting) state start from zero as before; any start gives the same fixed point (the
-relaxation's optimum) because the iteration is a convergent ADMM from every initial dual.
+relaxation's optimum) because the iteration is a convergent ADMM from every initial dual.  (Also starting the primal variables
+from the unit flow along the portal path was tried and dropped: the single path is not the relaxation's fractional optimum and
+the inner duals of the cone constraints are unknown, so the first x-update moves away from it — same residuals after 50 iterations.)
 """
 from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["portal_points", "cost_to_go", "dual_start"]
+__all__ = ["portal_points", "cost_to_go", "dual_start", "portal_path"]
 
 
 def portal_points(g):
@@ -36,7 +38,7 @@ def portal_points(g):
     return p
 
 
-def cost_to_go(g, field="dijkstra"):
+def cost_to_go(g, field="dijkstra", return_next=False):
     """(J[nE], grad[nE, 2]): cost-to-go from the portal of every edge and its gradient (minus the unit direction of travel).
     ``field="euclid"``: straight-line distance to the target (exact on obstacle-free maps); ``"dijkstra"``: shortest path over
     the portal graph (portal of e = (u, w) -> portal of f = (w, x), weight = their distance), valid for any region graph.
@@ -50,6 +52,8 @@ def cost_to_go(g, field="dijkstra"):
         d = tgt[None, :] - p
         J = np.linalg.norm(d, axis=1)
         grad = -d / np.where(J > 0, J, 1.0)[:, None]
+        if return_next:
+            raise ValueError("the euclid field has no successor structure; use field='dijkstra'")
         return J, grad
     from scipy.sparse import csr_matrix
     from scipy.sparse.csgraph import dijkstra
@@ -83,6 +87,8 @@ def cost_to_go(g, field="dijkstra"):
     d = to - p
     n = np.linalg.norm(d, axis=1)
     grad = np.where((ok & (n > 1e-9))[:, None], -d / np.where(n > 1e-9, n, 1.0)[:, None], 0.0)
+    if return_next:
+        return J, grad, np.where(ok, nxt, -1)
     return J, grad
 
 
@@ -111,3 +117,22 @@ def dual_start(g, edge_delta, rho, field="dijkstra"):
     mu[hh] = mh
     mu[ht] = mt
     return mu / float(rho)
+
+
+def portal_path(g):
+    """edges of the shortest s-t path over the portal graph (None if the target cannot be reached)"""
+    J, _, nxt = cost_to_go(g, "dijkstra", return_next=True)
+    tail = np.asarray(g.edge_tail, np.int64)
+    p = portal_points(g)
+    c = np.asarray(g.interior_points())
+    start = np.nonzero((tail == g.src) & (nxt >= 0))[0]
+    if start.shape[0] == 0:
+        return None
+    e = int(start[np.argmin(J[start] + np.linalg.norm(p[start] - c[g.src], axis=1))])
+    path = [e]
+    while nxt[e] != g.nE:
+        e = int(nxt[e])
+        if e < 0 or len(path) > g.nE:
+            return None
+        path.append(e)
+    return path

@@ -28,7 +28,7 @@ if mode != "cold":
 t0 = time.time()
 for it in range(1, max_iters + 1):
     a.step()
-    if it % 500 == 0 or max(a.pri[-1], a.dual[-1]) < tol:
+    if it % 500 == 0 or it in (1, 2, 5, 10, 20, 50, 100, 200) or max(a.pri[-1], a.dual[-1]) < tol:
         print(it, "pri %.3e dual %.3e cost %.5f  (%.1fs)" % (a.pri[-1], a.dual[-1], a.cost(), time.time() - t0), flush=True)
     if max(a.pri[-1], a.dual[-1]) < tol:
         break

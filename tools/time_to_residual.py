@@ -39,7 +39,9 @@ done, chunk = 0, max(256, a.max_iters // a.trace)
 while done < a.max_iters and time.perf_counter() - t0 < a.budget:
     st = s.run(min(chunk, a.max_iters - done))
     done = st["iterations"]
-    print(json.dumps(dict(it=done, s=round(time.perf_counter() - t0, 3), pri=st["pri_res"], dual=st["dual_res"], inner=st["inner_res"], rho=st["rho"])), flush=True)
+    _, zv_, _, ze_ = s.solution()
+    cost_ = float(np.sum(np.linalg.norm(zv_[:, :2] - zv_[:, 2:], axis=1)) + 1e-4 * np.sum(ze_[:, 4]))
+    print(json.dumps(dict(it=done, s=round(time.perf_counter() - t0, 3), pri=st["pri_res"], dual=st["dual_res"], inner=st["inner_res"], rho=st["rho"], cost=cost_)), flush=True)
     if st["converged"] or st["diverged"]:
         break
 x_v, z_v, y_v, z_e = s.solution()
