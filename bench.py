@@ -374,8 +374,8 @@ TTR = dict(rho0=3.0, outer_alpha=1.7, warm="dijkstra", frames="local", inner=1, 
 
 
 def time_to_residual(g, tables, budget_s, outer_alpha=None, ms_hint=None, tol=1e-4, certify=True):
-    """BASELINE metric, second half: wall time of a perf-mode run to max(pri, dual) < 1e-4 (device-side stop test every
-    iteration, host polls every 256).  Local coordinate frames (perf.perf_tables frames="local": the same problem, vertex programs
+    """BASELINE metric, second half: wall time of a perf-mode run to max(pri, dual, inner) < 1e-4 with pri / dual by the reference's
+    definitions (global coordinates: GcsStatus.pri_res_ref / dual_res_ref; device-side stop test every iteration, host polls every 256).  Local coordinate frames (perf.perf_tables frames="local": the same problem, vertex programs
     centred on their regions), rho0 = 3, over-relaxed consensus step (1.7) and duals started from the portal-graph cost-to-go
     field (gcs_admm_b200.warmstart; primal variables start at zero) — all three change the trajectory, not the fixed point.
     The clock covers the host-side table build and warm start too.  Bounded by `budget_s`; reports what was reached, plus the
@@ -398,7 +398,8 @@ def time_to_residual(g, tables, budget_s, outer_alpha=None, ms_hint=None, tol=1e
         st = s.run(chunk)
     dt = time.perf_counter() - t0
     out = {"reached": bool(st["converged"]), "seconds": dt, "seconds_with_host_setup": time.perf_counter() - t_all, "iterations": st["iterations"],
-           "pri_res": st["pri_res"], "dual_res": st["dual_res"], "inner_res": st["inner_res"], "rho": st["rho"], "tolerance": tol, "budget_seconds": budget_s, "outer_alpha": oa,
+           "pri_res": st["pri_res"], "dual_res": st["dual_res"], "inner_res": st["inner_res"], "pri_res_reference_definition": st["pri_res_ref"],
+           "dual_res_reference_definition": st["dual_res_ref"], "rho": st["rho"], "tolerance": tol, "budget_seconds": budget_s, "outer_alpha": oa,
            "mode": f"perf K={TTR['inner']}, local coordinate frames, rho0 = {TTR['rho0']} (reference rho rule during the first {TTR['window']} iterations), "
                    f"over-relaxed consensus step, duals started from the portal-graph cost-to-go field ({TTR['warm']}), primal start 0",
            "host_table_seconds": t_tab, "host_warm_start_seconds": t_w}

@@ -101,7 +101,7 @@ struct GcsHandle {
     GcsPerfLayout PL;
     GcsPerfTables PT;
     long long perf_nblocks;
-    int *p_vclass, *p_cone_off, *p_blk_off, *p_blk_rec, *p_vrec, *p_tile_rec; double *p_cls_tab, *p_cone, *p_tstate, *p_tn, *p_edge_delta, *p_tile_res;
+    int *p_vclass, *p_cone_off, *p_blk_off, *p_blk_rec, *p_vrec, *p_tile_rec; double *p_cls_tab, *p_cone, *p_tstate, *p_tn, *p_edge_delta, *p_edge_cent, *p_tile_res;
     // one CUDA graph per chunk of `check_every` iterations (own stream only)
     cudaGraphExec_t graph_exec; int graph_iters;
     // peer mode (multi-GPU over NVLink peer memory, one process per GPU): see the "peer mode" section
@@ -246,40 +246,46 @@ __device__ void control_apply(Ctrl *ctrl, const GcsParams &p, long long n_x, lon
     const double eps_dual = sqrt((double)n_mu) * p.eps_abs + p.eps_rel * nmu;            // :613-614
     const double inner = s[6] < 0.0 ? -1.0 : sqrt(s[6]);   // perf mode: residual of the vertex programs' own cone constraints (-1: not computed
                                                            // in this iteration, 0 in the exact mode)
+    // local frames: the same two residuals evaluated in GLOBAL coordinates — what the reference's definitions (:598, :602) give for
+    // this iterate.  A flow mismatch eps between the two copies of an edge at position c is a position mismatch eps * |c| there.
+    const double pri_g = s[7] < 0.0 ? -1.0 : sqrt(s[7]), dual_g = s[8] < 0.0 ? -1.0 : rho * sqrt(2.0 * s[8]);
+    ctrl->pri_g = pri_g; ctrl->dual_g = dual_g;
     ctrl->it = it; ctrl->pri = pri; ctrl->dual = dual; ctrl->eps_pri = eps_pri; ctrl->eps_dual = eps_dual; ctrl->inner = inner;
     ctrl->rho = rho_new; ctrl->mu_scale = scale;
     if (it < hist_cap) { hist[it] = rho_new; hist[hist_cap + it] = pri; hist[2 * hist_cap + it] = dual; }
     if (s[5] != 0.0 || !isfinite(pri) || !isfinite(dual)) { ctrl->diverged = 1; ctrl->stop = 1; return; }  // :662-664
     // abs_stop (the "residual < tol" metric): the inexact x-update's own residual counts too — an iterate whose consensus
     // residuals are small while its vertex programs still violate their cone constraints is not a solution
-    const bool opt = p.abs_stop ? (inner >= 0.0 && fmax(fmax(pri, dual), inner) < p.abs_tol) : (pri < eps_pri && dual < eps_dual);        // :712
+    const bool opt = p.abs_stop ? (inner >= 0.0 && fmax(fmax(pri_g >= 0.0 ? pri_g : pri, dual_g >= 0.0 ? dual_g : dual), inner) < p.abs_tol)
+                                : (pri < eps_pri && dual < eps_dual);        // :712
     if (opt) { ctrl->opt = 1; ctrl->stop = 1; }
 }
 
 // Block reduction of the six partial sums, then the LAST block to finish (ticket) adds all blocks' partials in a fixed order and
 // applies the control step (fuse = 1), publishes this rank's sums to every peer (fuse = 2) or just leaves them in ctrl->sums (fuse = 0)
-__device__ __forceinline__ void edge_finish(double r2, double dz2, double x2, double z2, double m2, Ctrl *ctrl, double *__restrict__ partials,
+__device__ __forceinline__ void edge_finish(double r2, double dz2, double x2, double z2, double m2, double r2g, double dz2g, Ctrl *ctrl, double *__restrict__ partials,
                                             unsigned int *ticket, int fuse, const GcsParams &p, long long n_x, long long n_mu, double *hist,
                                             int hist_cap, const PeerView *PVp, const double *__restrict__ tile_res, int ntiles) {
     double bad = 0;
     if (!isfinite(r2) || !isfinite(dz2) || !isfinite(x2) || !isfinite(z2)) bad = 1.0;
     // block reduction (fixed order: shuffles, then warp partials in shared memory)
-    __shared__ double sh[EDGE_THREADS][7];
+    // columns: 0-5 the six sums | 6 inner residual^2 (filled by the last block from K1's partials) | 7, 8 r2 / dz2 in global coordinates
+    __shared__ double sh[EDGE_THREADS][9];
     __shared__ int is_last;
-    double vals[6] = {r2, dz2, x2, z2, m2, bad};
+    double vals[8] = {r2, dz2, x2, z2, m2, bad, r2g, dz2g};
 #pragma unroll
-    for (int q = 0; q < 6; ++q)
+    for (int q = 0; q < 8; ++q)
 #pragma unroll
         for (int o = 16; o; o >>= 1) vals[q] += __shfl_xor_sync(0xffffffffu, vals[q], o);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0)
 #pragma unroll
-        for (int q = 0; q < 6; ++q) sh[warp][q] = vals[q];
+        for (int q = 0; q < 8; ++q) sh[warp][q] = vals[q];
     __syncthreads();
-    if (threadIdx.x < 6) {
+    if (threadIdx.x < 8) {
         double s = 0.0;
         for (int w2 = 0; w2 < EDGE_THREADS / 32; ++w2) s += sh[w2][threadIdx.x];
-        partials[(size_t)blockIdx.x * NSUMS + threadIdx.x] = s;
+        partials[(size_t)blockIdx.x * NSUMS + (threadIdx.x < 6 ? threadIdx.x : threadIdx.x + 1)] = s;      // (slot 6 belongs to the inner residual)
         __threadfence();
     }
     __syncthreads();
@@ -292,26 +298,26 @@ __device__ __forceinline__ void edge_finish(double r2, double dz2, double x2, do
     __threadfence();
     // last block: every block's partials are visible; sum them in an order that does not depend on which block is last
     // (seventh sum, perf mode: the tiles' squared inner residuals written by K1 of this iteration)
-    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
 #pragma unroll
-        for (int q = 0; q < 6; ++q) acc[q] += __ldcg(partials + (size_t)b * NSUMS + q);
+        for (int q = 0; q < 9; ++q) if (q != 6) acc[q] += __ldcg(partials + (size_t)b * NSUMS + q);
     if (tile_res) { for (int b = threadIdx.x; b < ntiles; b += blockDim.x) acc[6] += __ldcg(tile_res + b); }
     else if (ntiles < 0 && threadIdx.x == 0) acc[6] = -1.0;           // perf mode, inner residual not computed in this iteration
 #pragma unroll
-    for (int q = 0; q < 7; ++q) sh[threadIdx.x][q] = acc[q];
+    for (int q = 0; q < 9; ++q) sh[threadIdx.x][q] = acc[q];
     __syncthreads();
     for (int st = EDGE_THREADS / 2; st > 0; st >>= 1) {
         if (threadIdx.x < st)
 #pragma unroll
-            for (int q = 0; q < 7; ++q) sh[threadIdx.x][q] += sh[threadIdx.x + st][q];
+            for (int q = 0; q < 9; ++q) sh[threadIdx.x][q] += sh[threadIdx.x + st][q];
         __syncthreads();
     }
-    if (threadIdx.x < 7) ctrl->sums[threadIdx.x] = sh[0][threadIdx.x];
+    if (threadIdx.x < 9) ctrl->sums[threadIdx.x] = sh[0][threadIdx.x];
     __syncthreads();
     if (fuse == 2) {       // peer mode: this rank's sums into every rank's inbox, then the flag
         const int me = PVp->rank, world = PVp->world, k = PVp->comm[me]->k + 1, par = k & 1;
-        if (threadIdx.x < 7)
+        if (threadIdx.x < 9)
             for (int q = 0; q < world; ++q) PVp->comm[q]->sums_in[par][me][threadIdx.x] = sh[0][threadIdx.x];
         __threadfence_system();
         __syncthreads();
@@ -363,7 +369,8 @@ edge_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *
         if (ot) { const double r = zn - xt, mn = ms * mt + (zn - at); mu[it_] = mn; r2 += r * r; x2 += xt * xt; m2 += mn * mn; }
         if (oh) { const double r = zn - xh, mn = ms * mh + (zn - ah); mu[ih_] = mn; r2 += r * r; x2 += xh * xh; m2 += mn * mn; }
     }
-    edge_finish(r2, dz2, x2, z2, m2, ctrl, partials, ticket, fuse, p, n_x, n_mu, hist, hist_cap, PVp, tile_res, ntiles);
+    const double none = (blockIdx.x == 0 && threadIdx.x == 0) ? -1.0 : 0.0;      // global-coordinate residuals: this kernel works in global frames already
+    edge_finish(r2, dz2, x2, z2, m2, none, none, ctrl, partials, ticket, fuse, p, n_x, n_mu, hist, hist_cap, PVp, tile_res, ntiles);
 }
 
 // local frames (perf-mode option, vertex_perf.cuh GcsPerfTables.edge_delta): the consensus constraint of edge e is
@@ -371,17 +378,21 @@ edge_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *
 // so the z-update is the least-squares solve  (I + B'B) z = x_head + B' x_tail  (the duals drop out: B' mu_tail + mu_head = 0 is an
 // invariant of the iteration), closed form per edge; mu_head += z - x_head, mu_tail += B z - x_tail; the dual residual is
 // rho sqrt(|dz|^2 + |B dz|^2).  One thread per edge: the three coupled scalars (p2, y) are needed together.
-template <int MINB, bool OA>
+// GRES (check variant, local frames only): also the primal / dual residual sums in GLOBAL coordinates.  The copies of an edge
+// (u, w) live in the frame of u (both points of the tail's copy, the first point of the head's copy) or of w (the head's own first
+// point); adding  flow * centre-of-frame  to a point gives its global value, so  r_global = r_local + r_flow * centre.
+template <int MINB, bool OA, bool GRES>
 __global__ void __launch_bounds__(EDGE_THREADS, MINB)
 edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, const int *__restrict__ edge_he_head,
-                   const unsigned char *__restrict__ edge_counted, const double *__restrict__ edge_delta, const double *__restrict__ xc,
+                   const unsigned char *__restrict__ edge_counted, const double *__restrict__ edge_delta, const double *__restrict__ edge_cent, const double *__restrict__ xc,
                    double *__restrict__ mu, double *__restrict__ z, Ctrl *ctrl, double *__restrict__ partials, unsigned int *ticket, int fuse,
                    GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap, int nHghost, const PeerView *PVp, const double *__restrict__ tile_res, int ntiles) {
     if (ctrl->stop && !ctrl->ignore_stop) return;
     if (fuse == 2) peer_wait_halo(*PVp);
     const double ms = ctrl->mu_scale, oa = p.outer_alpha, ob = 1.0 - p.outer_alpha;
     const int gpar = fuse == 2 ? ((PVp->comm[PVp->rank]->k + 1) & 1) * nHghost : 0;
-    double r2 = 0, dz2 = 0, x2 = 0, z2 = 0, m2 = 0;
+    double r2 = 0, dz2 = 0, x2 = 0, z2 = 0, m2 = 0, r2g = 0, dz2g = 0;
+    if (!GRES && blockIdx.x == 0 && threadIdx.x == 0) r2g = dz2g = -1.0;      // "not computed in this iteration"
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
         const int ht = edge_he_tail[e], hh = edge_he_head[e];
         const bool ot = ht < nHown, oh = hh < nHown;
@@ -418,6 +429,12 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
         const double db2 = dd[2] - d0 * dd[4], db3 = dd[3] - d1 * dd[4];
         dz2 += 0.5 * w * (2.0 * (dd[0] * dd[0] + dd[1] * dd[1] + dd[4] * dd[4]) + dd[2] * dd[2] + dd[3] * dd[3] + db2 * db2 + db3 * db3);
         z2 += 0.5 * w * (2.0 * (zn[0] * zn[0] + zn[1] * zn[1] + zn[4] * zn[4]) + zn[2] * zn[2] + zn[3] * zn[3] + bz[2] * bz[2] + bz[3] * bz[3]);
+        double cu0 = 0.0, cu1 = 0.0, cw0 = 0.0, cw1 = 0.0;
+        if (GRES) {
+            cu0 = edge_cent[2 * (size_t)e]; cu1 = edge_cent[2 * (size_t)e + 1]; cw0 = cu0 - d0; cw1 = cu1 - d1;
+            const double g0 = dd[0] + dd[4] * cu0, g1 = dd[1] + dd[4] * cu1, g2 = dd[2] + dd[4] * cw0, g3 = dd[3] + dd[4] * cw1;
+            dz2g += w * (g0 * g0 + g1 * g1 + g2 * g2 + g3 * g3 + dd[4] * dd[4]);
+        }
         if (MINB > 2) asm volatile("" ::: "memory");     // keeps the compiler from hoisting the dual loads above this point
         if (ot) {
             if (MINB > 2) {
@@ -426,6 +443,10 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
             }
 #pragma unroll
             for (int c = 0; c < 5; ++c) { const double r = bz[c] - xt[c], mn = ms * mt[c] + (bz[c] - at[c]); mu[5 * (size_t)ht + c] = mn; r2 += r * r; x2 += xt[c] * xt[c]; m2 += mn * mn; }
+            if (GRES) {      // every slot of the tail's copy lives in the tail's frame
+                const double ry = bz[4] - xt[4], a0 = bz[0] - xt[0] + ry * cu0, a1 = bz[1] - xt[1] + ry * cu1, a2 = bz[2] - xt[2] + ry * cu0, a3 = bz[3] - xt[3] + ry * cu1;
+                r2g += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + ry * ry;
+            }
         }
         if (oh) {
             if (MINB > 2) {
@@ -434,9 +455,13 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
             }
 #pragma unroll
             for (int c = 0; c < 5; ++c) { const double r = zn[c] - xh[c], mn = ms * mh[c] + (zn[c] - ah[c]); mu[5 * (size_t)hh + c] = mn; r2 += r * r; x2 += xh[c] * xh[c]; m2 += mn * mn; }
+            if (GRES) {      // the tail's first point in the tail's frame, the head's own first point in the head's frame
+                const double ry = zn[4] - xh[4], a0 = zn[0] - xh[0] + ry * cu0, a1 = zn[1] - xh[1] + ry * cu1, a2 = zn[2] - xh[2] + ry * cw0, a3 = zn[3] - xh[3] + ry * cw1;
+                r2g += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + ry * ry;
+            }
         }
     }
-    edge_finish(r2, dz2, x2, z2, m2, ctrl, partials, ticket, fuse, p, n_x, n_mu, hist, hist_cap, PVp, tile_res, ntiles);
+    edge_finish(r2, dz2, x2, z2, m2, r2g, dz2g, ctrl, partials, ticket, fuse, p, n_x, n_mu, hist, hist_cap, PVp, tile_res, ntiles);
 }
 
 // ------------------------------------------------------------------------------------------ peer mode (kernels)
@@ -461,7 +486,7 @@ __global__ void peer_control_kernel(Ctrl *ctrl, GcsParams p, long long n_x, long
     __threadfence_system();
     __syncwarp();
     if (threadIdx.x == 0) {
-        for (int j = 0; j < 7; ++j) {
+        for (int j = 0; j < 9; ++j) {
             double s = 0.0;
             for (int r = 0; r < PV.world; ++r) s += *(volatile double *)&me->sums_in[par][r][j];
             ctrl->sums[j] = s;
@@ -583,10 +608,10 @@ static int reset_ctrl(GcsHandle *h) {
 }
 
 static void free_perf(GcsHandle *h) {
-    void *pp[] = {h->p_vclass, h->p_cone_off, h->p_blk_off, h->p_blk_rec, h->p_vrec, h->p_tile_rec, h->p_cls_tab, h->p_cone, h->p_tstate, h->p_tn, h->p_edge_delta, h->p_tile_res};
+    void *pp[] = {h->p_vclass, h->p_cone_off, h->p_blk_off, h->p_blk_rec, h->p_vrec, h->p_tile_rec, h->p_cls_tab, h->p_cone, h->p_tstate, h->p_tn, h->p_edge_delta, h->p_edge_cent, h->p_tile_res};
     for (void *q : pp) if (q) cudaFree(q);
     h->p_vclass = h->p_cone_off = h->p_blk_off = h->p_blk_rec = h->p_vrec = h->p_tile_rec = nullptr;
-    h->p_cls_tab = h->p_cone = h->p_tstate = h->p_tn = h->p_edge_delta = h->p_tile_res = nullptr;
+    h->p_cls_tab = h->p_cone = h->p_tstate = h->p_tn = h->p_edge_delta = h->p_edge_cent = h->p_tile_res = nullptr;
     h->perf_on = 0;
 }
 static void drop_graph(GcsHandle *h) {
@@ -795,9 +820,11 @@ static int launch_edge(GcsHandle *h, int fuse) {
         int blocks = (h->nE + EDGE_THREADS - 1) / EDGE_THREADS;
         if (blocks > h->edge_blocks) blocks = h->edge_blocks;
         if (blocks < 1) blocks = 1;
-#define EDGE_FRAMES(MINB) if (h->p.outer_alpha != 1.0) EDGE_FRAMES_(MINB, true); else EDGE_FRAMES_(MINB, false)
-#define EDGE_FRAMES_(MINB, OA) edge_frames_kernel<MINB, OA><<<blocks, EDGE_THREADS, 0, h->stream>>>(h->nE, h->nHown, h->edge_he_tail, h->edge_he_head, h->edge_counted, \
-            h->perf_on ? h->p_edge_delta : nullptr, h->xc, h->mu, h->z, h->ctrl, h->partials, h->ticket, fuse, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, h->nHghost, h->PV_dev, INNER_ARGS(h))
+        const bool gres = h->perf_on && h->inner_on && h->p_edge_delta && h->p_edge_cent;      // check variant in local frames
+#define EDGE_FRAMES(MINB) if (gres) { if (h->p.outer_alpha != 1.0) EDGE_FRAMES_(MINB, true, true); else EDGE_FRAMES_(MINB, false, true); } \
+                          else { if (h->p.outer_alpha != 1.0) EDGE_FRAMES_(MINB, true, false); else EDGE_FRAMES_(MINB, false, false); }
+#define EDGE_FRAMES_(MINB, OA, GRES) edge_frames_kernel<MINB, OA, GRES><<<blocks, EDGE_THREADS, 0, h->stream>>>(h->nE, h->nHown, h->edge_he_tail, h->edge_he_head, h->edge_counted, \
+            h->perf_on ? h->p_edge_delta : nullptr, h->perf_on ? h->p_edge_cent : nullptr, h->xc, h->mu, h->z, h->ctrl, h->partials, h->ticket, fuse, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, h->nHghost, h->PV_dev, INNER_ARGS(h))
         if (h->edge_minb == 4) { EDGE_FRAMES(4); } else if (h->edge_minb == 3) { EDGE_FRAMES(3); } else { EDGE_FRAMES(2); }
 #undef EDGE_FRAMES
 #undef EDGE_FRAMES_
@@ -853,7 +880,7 @@ static int fetch_ctrl(GcsHandle *h) {
 static void fill_status_one(const Ctrl *c, GcsStatus *st) {
     st->iterations = c->it; st->converged = c->opt; st->diverged = c->diverged; st->inner_fail = c->inner_fail;
     st->inner_iters = (int64_t)c->inner_iters; st->skipped = (int64_t)c->skipped; st->rho = c->rho; st->pri_res = c->pri; st->dual_res = c->dual;
-    st->eps_pri = c->eps_pri; st->eps_dual = c->eps_dual; st->inner_res = c->inner;
+    st->eps_pri = c->eps_pri; st->eps_dual = c->eps_dual; st->inner_res = c->inner; st->pri_res_ref = c->pri_g >= 0.0 ? c->pri_g : c->pri; st->dual_res_ref = c->dual_g >= 0.0 ? c->dual_g : c->dual;
 }
 // batched handles: iterations = max, converged = all, residuals = worst problem, counters summed
 static void fill_status(const GcsHandle *h, GcsStatus *st) {
@@ -866,6 +893,8 @@ static void fill_status(const GcsHandle *h, GcsStatus *st) {
         if (t.pri_res > st->pri_res) { st->pri_res = t.pri_res; st->eps_pri = t.eps_pri; }
         if (t.dual_res > st->dual_res) { st->dual_res = t.dual_res; st->eps_dual = t.eps_dual; }
         if (t.inner_res > st->inner_res) st->inner_res = t.inner_res;
+        if (t.pri_res_ref > st->pri_res_ref) st->pri_res_ref = t.pri_res_ref;
+        if (t.dual_res_ref > st->dual_res_ref) st->dual_res_ref = t.dual_res_ref;
     }
 }
 static bool all_stopped(const GcsHandle *h) {
@@ -1237,6 +1266,7 @@ extern "C" int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *c) {
     if (!rc) rc = upload(&h->p_tn, (const double *)nullptr, 2 * (size_t)h->nV);
     if (!rc) rc = upload(&h->p_tile_res, (const double *)nullptr, (size_t)c->n_tiles);
     if (!rc && c->edge_delta) rc = upload(&h->p_edge_delta, c->edge_delta, 2 * (size_t)h->nE);
+    if (!rc && c->edge_delta && c->edge_cent) rc = upload(&h->p_edge_cent, c->edge_cent, 2 * (size_t)h->nE);
     if (rc) { free_perf(h); return rc; }
     h->perf_nblocks = c->n_blocks;
     h->PL = gcs_perf_layout(c->cap_blocks, c->cap_verts, c->cap_cone);

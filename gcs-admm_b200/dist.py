@@ -40,7 +40,7 @@ class CudaBackend:
         self.solver.set_stream(torch.cuda.current_stream().cuda_stream)
         nall = lp.he_off[-1] + lp.nH_ghost
         self.xc = torch.as_tensor(_DevArray(self.solver.xc_ptr(), (int(nall), 5)), device=self.device)
-        self.sums = torch.as_tensor(_DevArray(self.solver.sums_ptr(), (8,)), device=self.device)
+        self.sums = torch.as_tensor(_DevArray(self.solver.sums_ptr(), (10,)), device=self.device)
 
     supports_graph = True
 

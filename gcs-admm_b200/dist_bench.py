@@ -205,7 +205,8 @@ def time_to_residual(args, g, lp, rank, local_rank, tol=1e-4):
     dist.all_reduce(part)
     drv.close()
     return {"reached": bool(st["converged"]), "seconds": float(t.item()), "iterations": int(st["iterations"]), "pri_res": st["pri_res"], "dual_res": st["dual_res"],
-            "inner_res": st["inner_res"], "rho": st["rho"], "tolerance": tol, "iteration_cap": cap, "outer_alpha": cfg["outer_alpha"],
+            "inner_res": st["inner_res"], "pri_res_reference_definition": st["pri_res_ref"], "dual_res_reference_definition": st["dual_res_ref"],
+            "rho": st["rho"], "tolerance": tol, "iteration_cap": cap, "outer_alpha": cfg["outer_alpha"],
             "relaxed_cost": float(part[0].item() + part[1].item()), "host_setup_seconds_rank0": t_host,
             "mode": f"perf K={cfg['inner']}, local coordinate frames, rho0 = {cfg['rho0']}, over-relaxed consensus step, duals started from the portal-graph "
                     f"cost-to-go field ({cfg['warm']}); strips over the GPUs, peer-memory exchange; max over ranks of the wall time of the run"}

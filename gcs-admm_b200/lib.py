@@ -49,13 +49,14 @@ class GcsPerfConfig(C.Structure):
                 ("n_blocks", C.c_int32), ("blk_off", C.c_void_p), ("blk_he", C.c_void_p), ("blk_info", C.c_void_p),
                 ("n_tiles", C.c_int32), ("tile_voff", C.c_void_p),
                 ("cap_blocks", C.c_int32), ("cap_verts", C.c_int32), ("cap_cone", C.c_int32), ("threads", C.c_int32),
-                ("theta", C.c_double), ("edge_delta", C.c_void_p)]
+                ("theta", C.c_double), ("edge_delta", C.c_void_p), ("edge_cent", C.c_void_p)]
 
 
 class GcsStatus(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("diverged", C.c_int32),
                 ("inner_fail", C.c_int32), ("inner_iters", C.c_int64), ("skipped", C.c_int64), ("rho", C.c_double), ("pri_res", C.c_double),
-                ("dual_res", C.c_double), ("eps_pri", C.c_double), ("eps_dual", C.c_double), ("inner_res", C.c_double)]
+                ("dual_res", C.c_double), ("eps_pri", C.c_double), ("eps_dual", C.c_double), ("inner_res", C.c_double),
+                ("pri_res_ref", C.c_double), ("dual_res_ref", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -210,6 +211,9 @@ class Solver:
         if T.get("edge_delta") is not None:
             keep["edge_delta"] = np.ascontiguousarray(T["edge_delta"], f64)
             c.edge_delta = _ptr(keep["edge_delta"])
+            if T.get("edge_cent") is not None:
+                keep["edge_cent"] = np.ascontiguousarray(T["edge_cent"], f64)
+                c.edge_cent = _ptr(keep["edge_cent"])
         _check(load().gcsadmm_enable_perf(self._h, C.byref(c)))
         self._frames = T.get("edge_delta") is not None
         self._edge_delta = keep.get("edge_delta")

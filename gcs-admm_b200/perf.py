@@ -278,7 +278,7 @@ TILE_THREADS = int(_os.environ.get("GCS_TILE_THREADS", str(min(256, 4 * TILE_BLO
 TILE_VERTS, TILE_CONE, TILE_HE = 32, 160, 128
 
 
-def perf_tables(g, kappa=1.0, cone=None, theta=1.0, frames="global", edge_delta=None):
+def perf_tables(g, kappa=1.0, cone=None, theta=1.0, frames="global", edge_delta=None, edge_cent=None):
     """Everything ``gcsadmm_enable_perf`` uploads (``include/gcsadmm.h`` ``GcsPerfConfig``): class tables, cone records,
     the block list (one block per live half-edge plus one per vertex for (z_v, y_v)) and the tiling of the vertices.
     ``cone = (cone_off, cone)`` reuses records computed elsewhere (multi-GPU: sliced from the global graph).
@@ -314,6 +314,7 @@ def perf_tables(g, kappa=1.0, cone=None, theta=1.0, frames="global", edge_delta=
         if not hasattr(g, "edge_tail"):
             raise ValueError("local frames need edge_tail / edge_head (single-GPU graphs)")
         edge_delta = np.ascontiguousarray(cent[np.asarray(g.edge_tail, dtype=np.int64)] - cent[np.asarray(g.edge_head, dtype=np.int64)])
+        edge_cent = np.ascontiguousarray(cent[np.asarray(g.edge_tail, dtype=np.int64)])       # residuals in global coordinates (check variant)
     # blocks: live half-edges of every live vertex in half-edge order, then its (z_v, y_v) block
     nlive = np.where(alive, din + dout, 0).astype(np.int64)
     nblk = np.where(alive, nlive + 1, 0).astype(np.int64)
@@ -341,7 +342,8 @@ def perf_tables(g, kappa=1.0, cone=None, theta=1.0, frames="global", edge_delta=
                 he=int((np.asarray(g.he_off, np.int64)[tv1] - np.asarray(g.he_off, np.int64)[tv0]).max()) if nV else 1)
     return dict(vclass=vclass, cls_tab=cls_tab, cone_off=np.asarray(cone_off, dtype=np.int32), cone=np.ascontiguousarray(cone_rec),
                 blk_off=blk_off.astype(np.int32), blk_he=blk_he, blk_info=blk_info, tile_voff=tile_voff.astype(np.int32),
-                caps=caps, classes=keys, kappa=float(kappa), theta=float(theta), edge_delta=edge_delta, frames=frames, threads=TILE_THREADS)
+                caps=caps, classes=keys, kappa=float(kappa), theta=float(theta), edge_delta=edge_delta, edge_cent=edge_cent if frames == "local" else None,
+                frames=frames, threads=TILE_THREADS)
 
 
 def _greedy_tiles(nblk, he_cnt, cone_cnt):
@@ -374,4 +376,6 @@ def local_tables(T, lp):
     idx = np.repeat(off[lv] - loff[:-1], cnt) + np.arange(int(loff[-1]))
     frames = T.get("frames", "global")
     delta = np.ascontiguousarray(T["edge_delta"][np.asarray(lp.global_edges, dtype=np.int64)]) if frames == "local" else None
-    return perf_tables(lp, T["kappa"], cone=(loff.astype(np.int32), np.ascontiguousarray(rec[idx])), theta=T.get("theta", 1.0), frames=frames, edge_delta=delta)
+    ecent = np.ascontiguousarray(T["edge_cent"][np.asarray(lp.global_edges, dtype=np.int64)]) if frames == "local" and T.get("edge_cent") is not None else None
+    return perf_tables(lp, T["kappa"], cone=(loff.astype(np.int32), np.ascontiguousarray(rec[idx])), theta=T.get("theta", 1.0), frames=frames, edge_delta=delta,
+                       edge_cent=ecent)

@@ -108,6 +108,10 @@ typedef struct GcsStatus {
     double rho, pri_res, dual_res, eps_pri, eps_dual;
     double inner_res;            /* perf mode: residual of the vertex programs' own cone constraints, |(M u + m0) - c| over all pairs
                                     (0 in the exact mode); part of the abs_stop test */
+    double pri_res_ref, dual_res_ref;   /* the residuals by the reference's definitions (:598, :602), i.e. in global coordinates.  Equal to
+                                    pri_res / dual_res except in perf mode with local frames near convergence, where the check variant
+                                    of the edge kernel evaluates them (a flow mismatch far from the origin is a large position mismatch);
+                                    the abs_stop test uses these */
 } GcsStatus;
 
 const char *gcsadmm_version(void);
@@ -185,6 +189,9 @@ typedef struct GcsPerfConfig {
                                     conditioned ADMM: the perspective variables y * (p - cent) stay O(region size) instead of O(|p|), which is
                                     what lets large maps converge.  x_v / z_v come back in global coordinates; xc, mu, z
                                     (get_state) are in the local frames */
+    const double *edge_cent;     /* local frames: [nE][2] = cent[tail] (NULL: the residuals of the abs_stop test stay in local coordinates).
+                                    With it the check variant of the edge kernel evaluates the residuals in GLOBAL coordinates, i.e. by the
+                                    reference's own definitions (GcsStatus.pri_res_ref / dual_res_ref) */
 } GcsPerfConfig;
 int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *cfg);
 /* the warm-start state of the perf mode (t = c + lam of every pair, 12 doubles per block, and 2 doubles per vertex for the

@@ -41,12 +41,12 @@ while done < a.max_iters and time.perf_counter() - t0 < a.budget:
     done = st["iterations"]
     _, zv_, _, ze_ = s.solution()
     cost_ = float(np.sum(np.linalg.norm(zv_[:, :2] - zv_[:, 2:], axis=1)) + 1e-4 * np.sum(ze_[:, 4]))
-    print(json.dumps(dict(it=done, s=round(time.perf_counter() - t0, 3), pri=st["pri_res"], dual=st["dual_res"], inner=st["inner_res"], rho=st["rho"], cost=cost_)), flush=True)
+    print(json.dumps(dict(it=done, s=round(time.perf_counter() - t0, 3), pri=st["pri_res"], dual=st["dual_res"], inner=st["inner_res"], pri_ref=st["pri_res_ref"], dual_ref=st["dual_res_ref"], rho=st["rho"], cost=cost_)), flush=True)
     if st["converged"] or st["diverged"]:
         break
 x_v, z_v, y_v, z_e = s.solution()
 cost = float(np.sum(np.linalg.norm(z_v[:, :2] - z_v[:, 2:], axis=1)) + 1e-4 * np.sum(z_e[:, 4]))
 print(json.dumps(dict(workload=f"grid{a.grid}x{a.grid}", vertices=g.nV, edges=g.nE, mode=f"perf K={a.inner}", tol=a.tol, reached=bool(st["converged"]), iterations=done,
-                      seconds=time.perf_counter() - t0, pri=st["pri_res"], dual=st["dual_res"], inner=st["inner_res"], rho=st["rho"], cost=cost,
+                      seconds=time.perf_counter() - t0, pri=st["pri_res"], dual=st["dual_res"], inner=st["inner_res"], pri_ref=st["pri_res_ref"], dual_ref=st["dual_res_ref"], rho=st["rho"], cost=cost,
                       straight_line=float(np.sqrt(2.0) * (a.grid - 1)), params=vars(a))))
 s.close()
