@@ -201,3 +201,30 @@ def test_inner_residual_is_part_of_the_absolute_stop_rule():
     e.step(3)
     assert e.status()["inner_res"] == 0.0                                   # exact mode: the vertex programs are solved to 1e-8
     e.close()
+
+
+def test_reference_definition_residuals_in_local_frames_vs_numpy():
+    """local frames: the check variant of the edge kernel evaluates the primal residual in GLOBAL coordinates (the reference's
+    definition :598) — compared with numpy from the state of the stop iteration.  abs_tol is huge, so the run stops at the first
+    iteration the check variant runs (iteration check_every + 1)."""
+    from gcs_admm_b200.lib import Solver
+    from gcs_admm_b200 import perf
+    g = pack_graph(*load_golden("benchmark4")[:2])
+    T = perf.perf_tables(g, frames="local")
+    s = Solver(g, abs_stop=1, abs_tol=1e9, check_every=8, frac=0.0, max_it=1000).enable_perf(inner_iters=1, tables=T)
+    st = s.run(64)
+    assert st["converged"] == 1 and st["iterations"] == 9 and st["inner_res"] >= 0.0
+    xc, mu, z, rho, it = s.state()
+    s.close()
+    d, cu = T["edge_delta"], T["edge_cent"]
+    cw = cu - d
+    xt, xh = xc[g.edge_he_tail], xc[g.edge_he_head]
+    bz = z.copy()
+    bz[:, 2:4] -= d * z[:, 4:5]
+    rt, rh = bz - xt, z - xh                                   # local residuals of the two copies
+    assert abs(np.sqrt(np.sum(rt ** 2) + np.sum(rh ** 2)) - st["pri_res"]) < 1e-10 * max(1.0, st["pri_res"])
+    gt = rt.copy(); gt[:, 0:2] += rt[:, 4:5] * cu; gt[:, 2:4] += rt[:, 4:5] * cu          # every slot of the tail's copy: the tail's frame
+    gh = rh.copy(); gh[:, 0:2] += rh[:, 4:5] * cu; gh[:, 2:4] += rh[:, 4:5] * cw          # head: tail's point in the tail's frame, own point in its own
+    ref = np.sqrt(np.sum(gt ** 2) + np.sum(gh ** 2))
+    assert abs(ref - st["pri_res_ref"]) < 1e-10 * max(1.0, ref)
+    assert st["pri_res_ref"] > st["pri_res"]                   # benchmark4's regions are far from the origin: flow mismatches are amplified
