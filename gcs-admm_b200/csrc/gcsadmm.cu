@@ -256,7 +256,8 @@ __device__ void control_apply(Ctrl *ctrl, const GcsParams &p, long long n_x, lon
     if (s[5] != 0.0 || !isfinite(pri) || !isfinite(dual)) { ctrl->diverged = 1; ctrl->stop = 1; return; }  // :662-664
     // abs_stop (the "residual < tol" metric): the inexact x-update's own residual counts too — an iterate whose consensus
     // residuals are small while its vertex programs still violate their cone constraints is not a solution
-    const bool opt = p.abs_stop ? (inner >= 0.0 && fmax(fmax(pri_g >= 0.0 ? pri_g : pri, dual_g >= 0.0 ? dual_g : dual), inner) < p.abs_tol)
+    const bool ref = p.stop_ref && pri_g >= 0.0 && dual_g >= 0.0;
+    const bool opt = p.abs_stop ? (inner >= 0.0 && fmax(fmax(ref ? pri_g : pri, ref ? dual_g : dual), inner) < p.abs_tol)
                                 : (pri < eps_pri && dual < eps_dual);        // :712
     if (opt) { ctrl->opt = 1; ctrl->stop = 1; }
 }
@@ -577,7 +578,7 @@ extern "C" void gcsadmm_default_params(GcsParams *p) {
     p->rho0 = 1.0; p->tau_incr = 2.0; p->tau_decr = 2.0; p->nu = 10.0; p->frac = 0.1;
     p->eps_abs = 1e-4; p->eps_rel = 1e-3; p->max_it = 1000; p->inner_tol = 1e-8; p->inner_max_iter = 60;
     p->check_every = 8; p->abs_stop = 0; p->abs_tol = 1e-4; p->warm_theta = 1e-3; p->zero_tol = 1e-12;
-    p->outer_alpha = 1.0; p->use_graph = 1; p->adapt_every = 1;
+    p->outer_alpha = 1.0; p->use_graph = 1; p->adapt_every = 1; p->stop_ref = 0;
 }
 extern "C" int gcsadmm_scratch_bytes(int max_live_degree, int max_rows) {
     return (int)(gcs_scratch_layout(max_live_degree, max_rows).total * sizeof(double));

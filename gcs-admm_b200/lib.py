@@ -40,7 +40,7 @@ class GcsParams(C.Structure):
                 ("frac", C.c_double), ("eps_abs", C.c_double), ("eps_rel", C.c_double), ("max_it", C.c_int32),
                 ("inner_tol", C.c_double), ("inner_max_iter", C.c_int32), ("check_every", C.c_int32),
                 ("abs_stop", C.c_int32), ("abs_tol", C.c_double), ("warm_theta", C.c_double), ("zero_tol", C.c_double),
-                ("outer_alpha", C.c_double), ("use_graph", C.c_int32), ("adapt_every", C.c_int32)]
+                ("outer_alpha", C.c_double), ("use_graph", C.c_int32), ("adapt_every", C.c_int32), ("stop_ref", C.c_int32)]
 
 
 class GcsPerfConfig(C.Structure):

@@ -96,6 +96,10 @@ typedef struct GcsParams {       /* literals of admm_solver_v3.py:621-651 */
                                     accelerated choice, Boyd et al. 3.4.3) — perf-mode runs only, the parity mode keeps 1 */
     int32_t use_graph;           /* 1: gcsadmm_run replays one CUDA graph per chunk of check_every iterations (own stream only) */
     int32_t adapt_every;         /* 1 = the reference's per-iteration rho test (:703-709); N > 1: tested on every N-th iteration only */
+    int32_t stop_ref;            /* abs_stop in perf mode with local frames: 0 (default) = the test uses the residuals of the local-frame
+                                    formulation (translation-invariant); 1 = it uses the reference's definitions, i.e. the residuals in global
+                                    coordinates (GcsStatus.pri_res_ref / dual_res_ref) — an absolute threshold on those depends on where the
+                                    map's origin is: a flow mismatch eps at position c counts as eps * |c| */
 } GcsParams;
 
 typedef struct GcsStatus {

@@ -21,6 +21,7 @@ ap.add_argument("--tau", type=float, default=2.0)
 ap.add_argument("--frames", type=str, default="local", choices=["local", "global"])
 ap.add_argument("--theta", type=float, default=1.0, help="penalty of the flow scalars = theta * rho")
 ap.add_argument("--warm", type=str, default="none", choices=["none", "dijkstra", "euclid"], help="dual start from a cost-to-go field (gcs_admm_b200.warmstart)")
+ap.add_argument("--stop-ref", action="store_true", help="stop on the residuals in global coordinates (the reference's definitions) instead of the local-frame ones")
 ap.add_argument("--trace", type=int, default=20, help="trace points")
 ap.add_argument("--budget", type=float, default=1e9, help="seconds")
 a = ap.parse_args()
@@ -28,7 +29,7 @@ g = grid_packed_graph(a.grid)
 T = perf.perf_tables(g, frames=a.frames, theta=a.theta)
 # rho adapts while it < frac * max_it (reference rule :703): the window is a parameter of the reference's algorithm
 s = lib.Solver(g, max_it=a.max_iters + 8, frac=a.window / (a.max_iters + 8), abs_stop=1, abs_tol=a.tol, check_every=256, rho0=a.rho0, nu=a.nu,
-               tau_incr=a.tau, tau_decr=a.tau, outer_alpha=a.outer_alpha, adapt_every=a.adapt_every).enable_perf(inner_iters=a.inner, tables=T)
+               tau_incr=a.tau, tau_decr=a.tau, outer_alpha=a.outer_alpha, adapt_every=a.adapt_every, stop_ref=int(a.stop_ref)).enable_perf(inner_iters=a.inner, tables=T)
 t0 = time.perf_counter()
 if a.warm != "none":
     from gcs_admm_b200 import warmstart
