@@ -1,10 +1,12 @@
 """GPU: `perf` mode of K1 (inexact x-update, K closed-form splitting iterations).  Its trajectory is not the
 reference's; it is validated (a) against the CPU emulation of the same kernel source, iterate by iterate, and
 (b) at convergence against the classic relaxation optimum stored in the reference's pickles."""
+import os
+
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from conftest import ROOT, load_golden
 from gcs_admm_b200.graph import pack_graph
 
 pytestmark = pytest.mark.gpu
@@ -228,3 +230,26 @@ def test_reference_definition_residuals_in_local_frames_vs_numpy():
     ref = np.sqrt(np.sum(gt ** 2) + np.sum(gh ** 2))
     assert abs(ref - st["pri_res_ref"]) < 1e-10 * max(1.0, ref)
     assert st["pri_res_ref"] > st["pri_res"]                   # benchmark4's regions are far from the origin: flow mismatches are amplified
+
+
+@pytest.mark.parametrize("G", [12, 16, 24])
+def test_grid_fixed_point_equals_classic_optimum(G):
+    """the scalable benchmark family at sizes the host interior-point comparator can still finish (fixture:
+    tests/golden/grid_classic.json, made by tools/gen_grid_classic_golden.py): the perf-mode ADMM with the accelerated
+    configuration of the time-to-residual run (local frames, rho0 = 3, over-relaxed consensus step, dual warm start), iterated to
+    1e-5, has the classic relaxation's optimal cost to 1e-4 relative"""
+    import json
+    from gcs_admm_b200.generator import grid_packed_graph
+    from gcs_admm_b200.lib import Solver
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "grid_classic.json")))
+    if str(G) not in gold:
+        pytest.skip(f"no classic optimum stored for G = {G}")
+    g = grid_packed_graph(G)
+    s = Solver(g, max_it=2_000_000, abs_stop=1, abs_tol=1e-5, check_every=256, frac=100 / 2_000_000, rho0=3.0, outer_alpha=1.7)
+    s.enable_perf(inner_iters=1, frames="local").warm_start("dijkstra", rho=3.0)
+    st = s.run()
+    x_v, z_v, y_v, z_e = s.solution()
+    s.close()
+    cost = float(np.sum(np.linalg.norm(z_v[:, :2] - z_v[:, 2:], axis=1)) + 1e-4 * np.sum(z_e[:, 4]))
+    assert st["converged"] == 1 and max(st["pri_res"], st["dual_res"], st["inner_res"]) < 1e-5
+    assert abs(cost - gold[str(G)]["cost"]) <= 1e-4 * gold[str(G)]["cost"], (cost, gold[str(G)]["cost"], st["iterations"])
