@@ -394,10 +394,16 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
     const int gpar = fuse == 2 ? ((PVp->comm[PVp->rank]->k + 1) & 1) * nHghost : 0;
     double r2 = 0, dz2 = 0, x2 = 0, z2 = 0, m2 = 0, r2g = 0, dz2g = 0;
     if (!GRES && blockIdx.x == 0 && threadIdx.x == 0) r2g = dz2g = -1.0;      // "not computed in this iteration"
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
-        const int ht = edge_he_tail[e], hh = edge_he_head[e];
-        const bool ot = ht < nHown, oh = hh < nHown;
-        const double *pt = xc + 5 * (size_t)(ot ? ht : ht + gpar), *ph = xc + 5 * (size_t)(oh ? hh : hh + gpar);
+    // the half-edge indices of a thread's NEXT edge are loaded while the current one is processed: the dependent
+    // index -> record load chain of a grid-stride step then starts with the indices already in registers
+    const int estride = gridDim.x * blockDim.x;
+    int e = blockIdx.x * blockDim.x + threadIdx.x, ht = 0, hh = 0;
+    if (e < nE) { ht = edge_he_tail[e]; hh = edge_he_head[e]; }
+    for (; e < nE; e += estride) {
+        const int en = e + estride, ht_ = ht, hh_ = hh;       // this edge's half-edges; ht / hh now receive the next edge's
+        if (en < nE) { ht = edge_he_tail[en]; hh = edge_he_head[en]; }
+        const bool ot = ht_ < nHown, oh = hh_ < nHown;
+        const double *pt = xc + 5 * (size_t)(ot ? ht_ : ht_ + gpar), *ph = xc + 5 * (size_t)(oh ? hh_ : hh_ + gpar);
         double xt[5], xh[5], zo[5], mt[5], mh[5];
 #pragma unroll
         for (int c = 0; c < 5; ++c) { xt[c] = pt[c]; xh[c] = ph[c]; zo[c] = z[5 * (size_t)e + c]; }
@@ -405,7 +411,7 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
         // MINB > 2 (<= 80 / 64 registers, more resident warps): they are loaded after z has been written, one side at a time
         if (MINB == 2) {
 #pragma unroll
-            for (int c = 0; c < 5; ++c) { mt[c] = ot ? mu[5 * (size_t)ht + c] : 0.0; mh[c] = oh ? mu[5 * (size_t)hh + c] : 0.0; }
+            for (int c = 0; c < 5; ++c) { mt[c] = ot ? mu[5 * (size_t)ht_ + c] : 0.0; mh[c] = oh ? mu[5 * (size_t)hh_ + c] : 0.0; }
         }
         const double d0 = edge_delta ? edge_delta[2 * (size_t)e] : 0.0, d1 = edge_delta ? edge_delta[2 * (size_t)e + 1] : 0.0;
         const double w = edge_counted ? (double)edge_counted[e] : 1.0;
@@ -440,10 +446,10 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
         if (ot) {
             if (MINB > 2) {
 #pragma unroll
-                for (int c = 0; c < 5; ++c) mt[c] = mu[5 * (size_t)ht + c];
+                for (int c = 0; c < 5; ++c) mt[c] = mu[5 * (size_t)ht_ + c];
             }
 #pragma unroll
-            for (int c = 0; c < 5; ++c) { const double r = bz[c] - xt[c], mn = ms * mt[c] + (bz[c] - at[c]); mu[5 * (size_t)ht + c] = mn; r2 += r * r; x2 += xt[c] * xt[c]; m2 += mn * mn; }
+            for (int c = 0; c < 5; ++c) { const double r = bz[c] - xt[c], mn = ms * mt[c] + (bz[c] - at[c]); mu[5 * (size_t)ht_ + c] = mn; r2 += r * r; x2 += xt[c] * xt[c]; m2 += mn * mn; }
             if (GRES) {      // every slot of the tail's copy lives in the tail's frame
                 const double ry = bz[4] - xt[4], a0 = bz[0] - xt[0] + ry * cu0, a1 = bz[1] - xt[1] + ry * cu1, a2 = bz[2] - xt[2] + ry * cu0, a3 = bz[3] - xt[3] + ry * cu1;
                 r2g += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + ry * ry;
@@ -452,10 +458,10 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
         if (oh) {
             if (MINB > 2) {
 #pragma unroll
-                for (int c = 0; c < 5; ++c) mh[c] = mu[5 * (size_t)hh + c];
+                for (int c = 0; c < 5; ++c) mh[c] = mu[5 * (size_t)hh_ + c];
             }
 #pragma unroll
-            for (int c = 0; c < 5; ++c) { const double r = zn[c] - xh[c], mn = ms * mh[c] + (zn[c] - ah[c]); mu[5 * (size_t)hh + c] = mn; r2 += r * r; x2 += xh[c] * xh[c]; m2 += mn * mn; }
+            for (int c = 0; c < 5; ++c) { const double r = zn[c] - xh[c], mn = ms * mh[c] + (zn[c] - ah[c]); mu[5 * (size_t)hh_ + c] = mn; r2 += r * r; x2 += xh[c] * xh[c]; m2 += mn * mn; }
             if (GRES) {      // the tail's first point in the tail's frame, the head's own first point in the head's frame
                 const double ry = zn[4] - xh[4], a0 = zn[0] - xh[0] + ry * cu0, a1 = zn[1] - xh[1] + ry * cu1, a2 = zn[2] - xh[2] + ry * cw0, a3 = zn[3] - xh[3] + ry * cw1;
                 r2g += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + ry * ry;
