@@ -111,5 +111,8 @@ def certificate(g, z_v, z_e, tol=1e-3, max_chain=1500):
         out["ok"] = bool(lower <= length * (1 + tol) and length <= best * (1 + tol))
     else:
         out["ok"] = bool(lower <= length * (1 + tol))
+    # with every equality and consensus constraint met exactly the relaxed length cannot be below |t - s| (the segments telescope);
+    # a deficit measures how far the iterate still is from consensus in GLOBAL coordinates
+    out["relaxed_length_minus_lower_bound_rel"] = (length - lower) / lower
     out["seconds"] = time.perf_counter() - t0
     return out
