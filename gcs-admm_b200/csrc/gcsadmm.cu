@@ -77,7 +77,7 @@ struct GcsHandle {
     long long n_x, n_mu;
     int dcap, mcap;
     GcsScratchLayout L;
-    int k1_smem, k1_blocks, k1_warps, edge_blocks, edge_per_edge, edge_minb;
+    int k1_smem, k1_blocks, k1_warps, edge_blocks, edge_per_edge, edge_minb, edge_coop, coop_blocks;
     // device
     int *poly_off, *he_off, *he_edge, *edge_he_tail, *edge_he_head;
     double *polyA, *polyb, *cent;
@@ -471,6 +471,106 @@ edge_frames_kernel(int nE, int nHown, const int *__restrict__ edge_he_tail, cons
     edge_finish(r2, dz2, x2, z2, m2, r2g, dz2g, ctrl, partials, ticket, fuse, p, n_x, n_mu, hist, hist_cap, PVp, tile_res, ntiles);
 }
 
+// Warp-cooperative variant of the edge kernel for the single-GPU throughput path (every half-edge owned, no ghost slots, no
+// check variant): a warp takes 32 consecutive edges.  The 5-double records of its 32 tail half-edges, 32 head half-edges and 32
+// edges are moved between HBM and shared memory as five passes of 32 CONSECUTIVE doubles of the concatenated records (lane l of
+// pass k handles double l + 32 k, i.e. scalar (l + 32 k) % 5 of record (l + 32 k) / 5, the record's index coming from the lane that
+// owns the edge by a shuffle) — a request then touches ~7 records instead of 32, a third of the L1 wavefronts of the
+// one-thread-per-record pattern; each lane then reads / writes its own edge's records in shared memory with stride 5 (conflict-free).
+// The arithmetic per edge is the one of edge_frames_kernel, expression by expression (bit-identical z and mu).
+#define COOP_WARPS (EDGE_THREADS / 32)
+#define COOP_SMEM_DOUBLES (COOP_WARPS * 5 * 160)
+template <bool OA, int MINB>
+__global__ void __launch_bounds__(EDGE_THREADS, MINB)
+edge_coop_kernel(int nE, const int *__restrict__ edge_he_tail, const int *__restrict__ edge_he_head, const double *__restrict__ edge_delta,
+                 const double *__restrict__ xc, double *__restrict__ mu, double *__restrict__ z, Ctrl *ctrl, double *__restrict__ partials,
+                 unsigned int *ticket, int fuse, GcsParams p, long long n_x, long long n_mu, double *hist, int hist_cap,
+                 const double *__restrict__ tile_res, int ntiles) {
+    extern __shared__ __align__(16) double coop_sm[];
+    if (ctrl->stop && !ctrl->ignore_stop) return;
+    const double ms = ctrl->mu_scale, oa = p.outer_alpha, ob = 1.0 - p.outer_alpha;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *xtS = coop_sm + (size_t)warp * 800, *xhS = xtS + 160, *zoS = xtS + 320, *mtS = xtS + 480, *mhS = xtS + 640;
+    double r2 = 0, dz2 = 0, x2 = 0, z2 = 0, m2 = 0, r2g = 0, dz2g = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) r2g = dz2g = -1.0;      // global-coordinate residuals: not computed by this variant
+    const int nchunks = (nE + 31) >> 5;
+    for (int chunk = blockIdx.x * COOP_WARPS + warp; chunk < nchunks; chunk += gridDim.x * COOP_WARPS) {
+        const int e = (chunk << 5) + lane;
+        const bool valid = e < nE;
+        const int ht = valid ? edge_he_tail[e] : 0, hh = valid ? edge_he_head[e] : 0;     // (lanes past the end read record 0 and store nothing)
+        const double d0 = valid && edge_delta ? edge_delta[2 * (size_t)e] : 0.0, d1 = valid && edge_delta ? edge_delta[2 * (size_t)e + 1] : 0.0;
+        const size_t zbase = (size_t)chunk * 160;
+        // ---- HBM -> shared memory: 5 passes x 5 arrays, all 25 loads of a lane in flight before the first is used
+        double vx[5], vh[5], vz[5], vm[5], vn[5];
+        int tj[5], hj[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int i = lane + 32 * k, j = i / 5, c = i - 5 * j;
+            tj[k] = 5 * __shfl_sync(0xffffffffu, ht, j) + c;
+            hj[k] = 5 * __shfl_sync(0xffffffffu, hh, j) + c;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int i = lane + 32 * k;
+            vx[k] = xc[tj[k]]; vh[k] = xc[hj[k]]; vm[k] = mu[tj[k]]; vn[k] = mu[hj[k]];
+            vz[k] = zbase + i < 5 * (size_t)nE ? z[zbase + i] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int i = lane + 32 * k;
+            xtS[i] = vx[k]; xhS[i] = vh[k]; mtS[i] = vm[k]; mhS[i] = vn[k]; zoS[i] = vz[k];
+        }
+        __syncwarp();
+        // ---- the lane's own edge
+        double xt[5], xh[5], zo[5], mt[5], mh[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { xt[c] = xtS[5 * lane + c]; xh[c] = xhS[5 * lane + c]; zo[c] = zoS[5 * lane + c]; mt[c] = mtS[5 * lane + c]; mh[c] = mhS[5 * lane + c]; }
+        __syncwarp();                    // every lane has read its records: the buffers can take the results
+        double zn[5], bz[5], at[5], ah[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { at[c] = xt[c]; ah[c] = xh[c]; }
+        if (OA) {
+            const double bo[5] = {zo[0], zo[1], zo[2] - d0 * zo[4], zo[3] - d1 * zo[4], zo[4]};
+#pragma unroll
+            for (int c = 0; c < 5; ++c) { at[c] = oa * xt[c] + ob * bo[c]; ah[c] = oa * xh[c] + ob * zo[c]; }
+        }
+        zn[0] = 0.5 * (ah[0] + at[0]); zn[1] = 0.5 * (ah[1] + at[1]);
+        const double q0 = ah[2] + at[2], q1 = ah[3] + at[3], q2 = ah[4] + at[4] - (d0 * at[2] + d1 * at[3]);
+        zn[4] = (q2 + 0.5 * (d0 * q0 + d1 * q1)) / (2.0 + 0.5 * (d0 * d0 + d1 * d1));
+        zn[2] = 0.5 * (q0 + d0 * zn[4]); zn[3] = 0.5 * (q1 + d1 * zn[4]);
+        bz[0] = zn[0]; bz[1] = zn[1]; bz[2] = zn[2] - d0 * zn[4]; bz[3] = zn[3] - d1 * zn[4]; bz[4] = zn[4];
+        double dd[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { dd[c] = zn[c] - zo[c]; zoS[5 * lane + c] = zn[c]; }
+        const double db2 = dd[2] - d0 * dd[4], db3 = dd[3] - d1 * dd[4];
+        if (valid) {
+            dz2 += 0.5 * (2.0 * (dd[0] * dd[0] + dd[1] * dd[1] + dd[4] * dd[4]) + dd[2] * dd[2] + dd[3] * dd[3] + db2 * db2 + db3 * db3);
+            z2 += 0.5 * (2.0 * (zn[0] * zn[0] + zn[1] * zn[1] + zn[4] * zn[4]) + zn[2] * zn[2] + zn[3] * zn[3] + bz[2] * bz[2] + bz[3] * bz[3]);
+        }
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const double r = bz[c] - xt[c], mn = ms * mt[c] + (bz[c] - at[c]);
+            mtS[5 * lane + c] = mn;
+            if (valid) { r2 += r * r; x2 += xt[c] * xt[c]; m2 += mn * mn; }
+        }
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const double r = zn[c] - xh[c], mn = ms * mh[c] + (zn[c] - ah[c]);
+            mhS[5 * lane + c] = mn;
+            if (valid) { r2 += r * r; x2 += xh[c] * xh[c]; m2 += mn * mn; }
+        }
+        __syncwarp();
+        // ---- shared memory -> HBM, the same five passes
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int i = lane + 32 * k, j = i / 5;
+            if ((chunk << 5) + j < nE) { z[zbase + i] = zoS[i]; mu[tj[k]] = mtS[i]; mu[hj[k]] = mhS[i]; }
+        }
+        __syncwarp();                    // the buffers are free for the warp's next chunk
+    }
+    edge_finish(r2, dz2, x2, z2, m2, r2g, dz2g, ctrl, partials, ticket, fuse, p, n_x, n_mu, hist, hist_cap, nullptr, tile_res, ntiles);
+}
+
 // ------------------------------------------------------------------------------------------ peer mode (kernels)
 // exact mode: the push is a launch of its own after K1 (the perf kernel's last block does it itself)
 __global__ void __launch_bounds__(1024)
@@ -701,8 +801,17 @@ static int create_impl(GcsHandle *h, const GcsGraph *g) {
         // one thread per (edge, scalar) 68 us (6 blocks per SM) .. 84 us (24); the env variables are tuning knobs
         const char *bps = getenv("GCS_EDGE_BLOCKS_PER_SM"), *ek = getenv("GCS_EDGE_KERNEL");
         h->edge_per_edge = !(ek && !strcmp(ek, "per_scalar"));
+        h->edge_coop = ek && !strcmp(ek, "coop");               // warp-cooperative variant (single GPU, no ghosts): opt-in tuning knob
+        h->coop_blocks = prop.multiProcessorCount * (bps && atoi(bps) > 0 ? atoi(bps) : 2);
         const char *mb = getenv("GCS_EDGE_MINB");        // register budget of the per-edge kernel: 2, 3 or 4 resident blocks per SM
         h->edge_minb = mb && atoi(mb) >= 2 && atoi(mb) <= 4 ? atoi(mb) : 2;
+        if (h->edge_coop) {
+            const int smb = (int)(sizeof(double) * COOP_SMEM_DOUBLES);
+            CK(cudaFuncSetAttribute(edge_coop_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb));
+            CK(cudaFuncSetAttribute(edge_coop_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb));
+            CK(cudaFuncSetAttribute(edge_coop_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb));
+            CK(cudaFuncSetAttribute(edge_coop_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb));
+        }
         const long long cap = (long long)prop.multiProcessorCount * (bps && atoi(bps) > 0 ? atoi(bps) : (h->edge_per_edge ? 4 : 6));
         h->edge_blocks = (int)(need < 1 ? 1 : (need > cap ? cap : need));
     }
@@ -821,6 +930,19 @@ static int launch_edge(GcsHandle *h, int fuse) {
         const int blocks = h->nP < 148 * 16 ? h->nP : 148 * 16;
         batched_edge_kernel<<<blocks, BATCH_THREADS, 0, h->stream>>>(h->nP, h->prob_eoff, h->nHown, h->edge_he_tail, h->edge_he_head, h->xc, h->mu, h->z,
                                                                      h->ctrl, h->p, h->prob_nx, h->prob_nmu, h->hist, h->hist_cap);
+        return 0;
+    }
+    if (h->edge_coop && h->nHghost == 0 && !h->edge_counted && !(h->perf_on && h->inner_on)) {     // single-GPU throughput path
+        const int nchunks = (h->nE + 31) / 32;
+        int blocks = (nchunks + COOP_WARPS - 1) / COOP_WARPS;
+        if (blocks > h->coop_blocks) blocks = h->coop_blocks;
+        if (blocks < 1) blocks = 1;
+        const size_t sm = sizeof(double) * COOP_SMEM_DOUBLES;
+#define EDGE_COOP(OA, MINB) edge_coop_kernel<OA, MINB><<<blocks, EDGE_THREADS, sm, h->stream>>>(h->nE, h->edge_he_tail, h->edge_he_head, h->perf_on ? h->p_edge_delta : nullptr, \
+            h->xc, h->mu, h->z, h->ctrl, h->partials, h->ticket, fuse, h->p, h->n_x, h->n_mu, h->hist, h->hist_cap, INNER_ARGS(h))
+        if (h->p.outer_alpha != 1.0) { if (h->edge_minb >= 3) EDGE_COOP(true, 3); else EDGE_COOP(true, 2); }
+        else { if (h->edge_minb >= 3) EDGE_COOP(false, 3); else EDGE_COOP(false, 2); }
+#undef EDGE_COOP
         return 0;
     }
     if ((h->perf_on && h->p_edge_delta) || h->edge_per_edge) {      // local frames (or the one-thread-per-edge variant by request)
