@@ -797,11 +797,13 @@ static int create_impl(GcsHandle *h, const GcsGraph *g) {
     h->k1_blocks = (g->nV + h->k1_warps - 1) / h->k1_warps;
     {   // edge kernel: 5 threads per edge, a whole number of waves of resident blocks (8 blocks of 256 threads per SM)
         const long long need = (5ll * g->nE + EDGE_THREADS - 1) / EDGE_THREADS;
-        // measured on the 100k-vertex grid (profiles/r02_edge_variants.txt): one thread per edge with 4 blocks per SM 55 us,
+        // measured on the 100k-vertex grid: warp-cooperative 38 us (2 blocks per SM; 44 us with 3), one thread per edge 54 us,
         // one thread per (edge, scalar) 68 us (6 blocks per SM) .. 84 us (24); the env variables are tuning knobs
         const char *bps = getenv("GCS_EDGE_BLOCKS_PER_SM"), *ek = getenv("GCS_EDGE_KERNEL");
         h->edge_per_edge = !(ek && !strcmp(ek, "per_scalar"));
-        h->edge_coop = ek && !strcmp(ek, "coop");               // warp-cooperative variant (single GPU, no ghosts): opt-in tuning knob
+        // warp-cooperative variant: the default wherever it applies (single GPU, no ghost slots, throughput path): 38 us vs 54 us
+        // for one thread per edge on the 100k-vertex grid; GCS_EDGE_KERNEL=per_edge / per_scalar select the others
+        h->edge_coop = !(ek && (!strcmp(ek, "per_edge") || !strcmp(ek, "per_scalar")));
         h->coop_blocks = prop.multiProcessorCount * (bps && atoi(bps) > 0 ? atoi(bps) : 2);
         const char *mb = getenv("GCS_EDGE_MINB");        // register budget of the per-edge kernel: 2, 3 or 4 resident blocks per SM
         h->edge_minb = mb && atoi(mb) >= 2 && atoi(mb) <= 4 ? atoi(mb) : 2;
