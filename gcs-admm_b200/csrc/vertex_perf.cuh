@@ -36,7 +36,7 @@
 
 #define GCS_CONE_REC 12   // doubles per polygon vertex in the cone table
 #define GCS_NCX 19        // extended core of the v-step: x(4) z(4) y_v | beta_in(5) | beta_out(5)
-#define GCS_CLS_G0 361    // class table: G (19 x 19) | g0 (19) | dinv (2 x 5) | pad
+#define GCS_CLS_G0 361    // class table: G transposed (19 x 19) | g0 (19) | dinv (2 x 5) | pad
 #define GCS_CLS_DINV 380
 #define GCS_CLS_STRIDE 392
 #define GCS_PERF_THREADS 256
@@ -205,11 +205,13 @@ GCS_DEV double gcs_core_input(const double *tS, const double *rS, const int *bre
 }
 // output k of the extended core:  (x, z_v, y_v, beta_in, beta_out)[k] = g0[k] + G[k, :] . in
 GCS_DEV double gcs_core_output(const double *tab, const double *in, int k) {
-    const double *gk = tab + GCS_NCX * k;
+    // G is stored TRANSPOSED (tab[19 j + k] = G[k, j]): the 19 lanes that evaluate the 19 outputs of a vertex read 19 consecutive
+    // doubles per step (2 cache lines) instead of 19 doubles 152 bytes apart (19 lines)
+    const double *gk = tab + k;
     double s0 = tab[GCS_CLS_G0 + k], s1 = 0.0;
 #pragma unroll
-    for (int j = 0; j + 1 < GCS_NCX; j += 2) { s0 += gk[j] * in[j]; s1 += gk[j + 1] * in[j + 1]; }
-    return s0 + s1 + gk[GCS_NCX - 1] * in[GCS_NCX - 1];
+    for (int j = 0; j + 1 < GCS_NCX; j += 2) { s0 += gk[GCS_NCX * j] * in[j]; s1 += gk[GCS_NCX * (j + 1)] * in[j + 1]; }
+    return s0 + s1 + gk[GCS_NCX * (GCS_NCX - 1)] * in[GCS_NCX - 1];
 }
 
 // right-hand side r[q] of block-variable q = 5 b + tau of vertex vl (see P3 in gcs_perf_tile); d = c - lam of the block's pairs

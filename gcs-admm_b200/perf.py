@@ -166,7 +166,7 @@ def _cone_one(P):
 
 CORE_IDX = (0, 1, 2, 3, 5, 6, 7, 8, 9)      # x(4), z(4), y_v in the u-space layout (index 4 is the unused epigraph variable)
 NCX = 19                                      # extended core: x(4) z(4) y_v | beta_in(5) | beta_out(5)
-CLS_STRIDE = NCX * NCX + NCX + 10 + 2          # G (19 x 19) | g0 (19) | dinv (2 x 5) | pad -> 392 doubles per class
+CLS_STRIDE = NCX * NCX + NCX + 10 + 2          # G transposed (19 x 19) | g0 (19) | dinv (2 x 5) | pad -> 392 doubles per class
 
 
 def class_tables(vtype, din, dout, kappa, theta=1.0):
@@ -301,7 +301,7 @@ def perf_tables(g, kappa=1.0, cone=None, theta=1.0, frames="global", edge_delta=
         key = (int(cd // 1000000), int((cd // 1000) % 1000), int(cd % 1000))
         keys[key] = len(keys)
         T = class_tables(*key, kappa, theta)
-        tabs.append(np.concatenate([T["G"].reshape(-1), T["g0"], T["dinv"].reshape(-1), np.zeros(2)]))
+        tabs.append(np.concatenate([np.ascontiguousarray(T["G"].T).reshape(-1), T["g0"], T["dinv"].reshape(-1), np.zeros(2)]))      # G transposed (coalesced lanes)
         vclass[(code == cd) & alive] = keys[key]
     cls_tab = np.ascontiguousarray(np.concatenate(tabs)) if tabs else np.zeros(CLS_STRIDE)
     # frames = "local": every vertex program in coordinates centred on its own region (gcsadmm.h GcsPerfConfig.edge_delta)

@@ -174,7 +174,7 @@ typedef struct GcsPerfConfig {
     double kappa;                /* sigma = kappa * rho */
     int32_t n_classes;           /* vertex classes (type, #live in-edges, #live out-edges) */
     const int32_t *vclass;       /* [nV] class of each vertex (-1 for vtype 3) */
-    const double *cls_tab;       /* [n_classes][392]: the class's v-step in structured form: G (19 x 19) | g0 (19) | dinv (2 x 5) | pad */
+    const double *cls_tab;       /* [n_classes][392]: the class's v-step in structured form: G TRANSPOSED (19 x 19: [19 j + k] = G[k, j]) | g0 (19) | dinv (2 x 5) | pad */
     const int32_t *cone_off;     /* [nV+1] polygon vertices of each region, counter-clockwise */
     const double *cone;          /* 12 doubles per polygon vertex: Vx, Vy, unit outward normal (3) of the cone face to the
                                     next vertex's ray, 1 / (Vx^2 + Vy^2 + 1), the face's two in-plane sector normals (3 + 3) */
