@@ -16,6 +16,13 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX v3: ranges are no-ops unless a profiler injects itself
+
+// NVTX range of a C-ABI call (nsys / ncu --nvtx timelines): create, enable_perf, every chunk of iterations, the downloads
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 #include "../../include/gcsadmm.h"
 #include "gcs_ctrl.h"
@@ -865,6 +872,7 @@ static int create_impl(GcsHandle *h, const GcsGraph *g) {
 }
 
 extern "C" int gcsadmm_create(const GcsGraph *g, const GcsParams *p, int device, GcsHandle **out) {
+    NvtxRange nvtx_("gcsadmm_create");
     if (!g || !out) return set_err(GCS_E_INVALID, "null argument%s", "");
     *out = nullptr;
     if (g->n != 2) return set_err(GCS_E_INVALID, "the CUDA path is specialised to n = 2 (2-D GCS)%s", "");
@@ -981,6 +989,7 @@ static void launch_rest(GcsHandle *h) {
 static void launch_iteration(GcsHandle *h) { launch_k1(h); launch_rest(h); }
 // `iters` iterations as one CUDA graph launch (captured once per chunk length; the kernels read rho / stop from the control block)
 static int launch_chunk(GcsHandle *h, int iters) {
+    NvtxRange nvtx_("gcsadmm: chunk of ADMM iterations");
     // only whole chunks of check_every iterations are replayed (a remainder would force a re-instantiation every time)
     if (!h->p.use_graph || h->stream != h->own_stream || iters < 2 || iters != h->p.check_every) { for (int i = 0; i < iters; ++i) launch_iteration(h); return 0; }
     if (!h->graph_exec || h->graph_iters != iters) {
@@ -1058,6 +1067,7 @@ extern "C" int gcsadmm_step(GcsHandle *h, int k) {
 }
 
 extern "C" int gcsadmm_run(GcsHandle *h, int max_iters, GcsStatus *st) {
+    NvtxRange nvtx_("gcsadmm_run");
     if (!h) return set_err(GCS_E_INVALID, "null handle%s", "");
     CK(cudaSetDevice(h->device));
     int rc = fetch_ctrl(h); if (rc) return rc;
@@ -1120,6 +1130,7 @@ extern "C" int gcsadmm_get_history(GcsHandle *h, double *rho, double *pri, doubl
 }
 
 extern "C" int gcsadmm_get_solution(GcsHandle *h, double *x_v, double *z_v, double *y_v, double *z_e) {
+    NvtxRange nvtx_("gcsadmm_get_solution");
     if (!h) return set_err(GCS_E_INVALID, "null handle%s", "");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
@@ -1193,6 +1204,7 @@ extern "C" int gcsadmm_time_steps(GcsHandle *h, int k, float *ms_total, float *m
 // event pair) and bracketed by its own CUDA events: the host never waits between iterations, so launch latency and the skew
 // between ranks of a multi-GPU run are not part of what is measured.  ms_iter[k], ms_k1[k] (optional): per-iteration times.
 extern "C" int gcsadmm_time_window(GcsHandle *h, int k, long long flush_bytes, float *ms_iter, float *ms_k1) {
+    NvtxRange nvtx_("gcsadmm_time_window");
     if (!h || !ms_iter || k < 1) return set_err(GCS_E_INVALID, "bad argument%s", "");
     CK(cudaSetDevice(h->device));
     if (flush_bytes > 0 && (!h->flush_buf || h->flush_bytes < (size_t)flush_bytes)) {
@@ -1327,6 +1339,7 @@ extern "C" int gcsadmm_flush_l2(GcsHandle *h, long long bytes) {
 // Switches the x-update to the inexact `perf` mode (vertex_perf.cuh).  Tables are built by the host
 // (gcs-admm_b200/perf.py): the structured v-step of every vertex class, the polygon cones, the block list and the tiling.
 extern "C" int gcsadmm_enable_perf(GcsHandle *h, const GcsPerfConfig *c) {
+    NvtxRange nvtx_("gcsadmm_enable_perf");
     if (!h || !c) return set_err(GCS_E_INVALID, "null argument%s", "");
     if (c->inner_iters < 1 || c->n_classes < 1 || c->n_tiles < 1 || c->n_blocks < 0 || !c->vclass || !c->cls_tab || !c->cone_off || !c->cone ||
         !c->blk_off || !c->tile_voff || (c->n_blocks && (!c->blk_he || !c->blk_info)))
