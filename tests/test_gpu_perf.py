@@ -232,7 +232,7 @@ def test_reference_definition_residuals_in_local_frames_vs_numpy():
     assert st["pri_res_ref"] > st["pri_res"]                   # benchmark4's regions are far from the origin: flow mismatches are amplified
 
 
-@pytest.mark.parametrize("G", [12, 16, 24, 32])
+@pytest.mark.parametrize("G", [12, 16, 24, 32, 64])
 def test_grid_fixed_point_equals_classic_optimum(G):
     """the scalable benchmark family at sizes the host interior-point comparator can still finish (fixture:
     tests/golden/grid_classic.json, made by tools/gen_grid_classic_golden.py): the perf-mode ADMM with the accelerated
