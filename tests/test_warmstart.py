@@ -51,3 +51,28 @@ def test_unreachable_edges_get_zero_duals():
     g = pack_graph(*load_golden("benchmark4")[:2])
     J, grad = warmstart.cost_to_go(g, "dijkstra")
     assert np.isfinite(J).all() and np.isfinite(grad).all()
+
+
+def test_dual_start_sliced_to_a_partition_keeps_the_invariant_in_local_indices():
+    """multi-GPU time-to-residual run (dist_bench.time_to_residual): every rank takes mu_global[lp.global_he]; for every local edge
+    whose two half-edges are owned the invariant must hold with the rank's OWN indices and its own slice of edge_delta"""
+    from gcs_admm_b200.partition import partition_vertices, split_graph
+    g = grid_packed_graph(10)
+    T = perf.perf_tables(g, frames="local")
+    mu = warmstart.dual_start(g, T["edge_delta"], rho=3.0)
+    for lp in split_graph(g, partition_vertices(g, 3), 3):
+        ml = mu[np.asarray(lp.global_he, dtype=np.int64)]
+        Tl = perf.local_tables(T, lp)
+        d = Tl["edge_delta"]
+        assert np.allclose(Tl["edge_cent"], T["edge_cent"][np.asarray(lp.global_edges, dtype=np.int64)])
+        nH = int(lp.he_off[-1])
+        both = (lp.edge_he_tail < nH) & (lp.edge_he_head < nH)
+        assert both.any() and (~both).any()                      # interior edges and cut edges
+        mt, mh = ml[lp.edge_he_tail[both]], ml[lp.edge_he_head[both]]
+        inv = mt + mh
+        inv[:, 4] -= np.sum(d[both] * mt[:, 2:4], axis=1)
+        assert np.max(np.abs(inv)) < 1e-12
+        # a cut edge: the owned side carries the same dual as in the global array
+        cut_t = (lp.edge_he_tail < nH) & ~both
+        ge = np.asarray(lp.global_edges, dtype=np.int64)[cut_t]
+        assert np.allclose(ml[lp.edge_he_tail[cut_t]], mu[g.edge_he_tail[ge]])
