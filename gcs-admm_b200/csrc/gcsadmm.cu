@@ -1,12 +1,16 @@
 // libgcsadmm.so — kernels and C-ABI (include/gcsadmm.h).  sm_100a only; no CPU path.
 //
 //   K1  vertex_kernel        one warp per vertex, interior-point prox solve in shared memory   (vertex_update.cuh)
-//       vertex_perf_kernel   perf mode: one thread block per tile of vertices, closed-form splitting iterations (vertex_perf.cuh)
-//   K2-5 edge_kernel         one thread per (edge, consensus scalar): z-update (average of the two copies), dual update of
-//                            both half-edges, the five squared norms; block partials (no atomics on the data), and the
-//                            LAST block to finish reduces them in a fixed order and applies the control step: residuals,
-//                            rho adaptation, stop rule, history (reference admm_solver_v3.py:697-713)
-//   control_kernel           the same control step as a separate launch (multi-GPU: the sums are all-reduced in between)
+//       vertex_perf_kernel   perf mode: persistent thread blocks walking tiles of vertices with two bulk-copy stage buffers,
+//                            closed-form splitting iterations (vertex_perf.cuh)
+//   K2-5 edge_coop_kernel    single-GPU throughput path: a warp per 32 consecutive edges, records moved HBM <-> shared memory in
+//                            coalesced passes; z-update, dual update of both half-edges, the squared norms; block partials (no
+//                            atomics on the data), and the LAST block to finish reduces them in a fixed order and applies the
+//                            control step: residuals, rho adaptation, stop rule, history (reference admm_solver_v3.py:697-713)
+//       edge_frames_kernel   the same with one thread per edge: partitions with ghost slots (multi-GPU), the check variant that
+//                            also evaluates the residuals in global coordinates; edge_kernel: one thread per (edge, scalar)
+//   control_kernel           the same control step as a separate launch (NCCL multi-GPU: the sums are all-reduced in between);
+//   peer_control_kernel      peer-memory multi-GPU: waits for every rank's sums, then the control step
 // Every kernel returns immediately once the stop flag is set, so the host can enqueue iterations in
 // chunks (one CUDA graph per chunk) and poll the control block once per chunk while keeping the reference's exact
 // stop iteration.

@@ -18,7 +18,8 @@
 // map of (r_x, r_z, r_yv, sum_in r, sum_out r): O(d) work per vertex instead of a dense (5d)^2 product
 // (tables: gcs-admm_b200/perf.py class_tables).
 //
-// Mapping: one thread block per TILE of consecutive vertices (<= 64 blocks = 256 pairs); every phase is a flat loop
+// Mapping: a thread block works on one TILE of consecutive vertices at a time (<= 64 blocks = 256 pairs; the kernel's blocks are
+// persistent and walk tiles, staging the next one while they compute — gcsadmm.cu vertex_perf_kernel); every phase is a flat loop
 // over (pair | block variable | vertex) items of the whole tile, so lanes stay busy whatever the degrees are; phases
 // exchange data through shared memory only.  The per-tile state t, the cone records and the path-length state are
 // contiguous in HBM and move with 1-D bulk async copies (cp.async.bulk + mbarrier).
